@@ -1,0 +1,147 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the REFERENCE ITSELF, run in this container.
+
+  * MFCC: the reference's own src/feature/MFCC.py + utils.py are read from /root/reference and
+    executed in memory.  They are Python 2; the only edits applied (to the in-memory text, never
+    written anywhere) are the mechanical ones SURVEY.md s7 item 3 lists:
+        `/` -> `//` at the two integer divisions, xrange -> range, cast['float'] -> asarray(float),
+        `from utils import` resolved by pre-seeding sys.modules, builtin min kept.
+  * GMM: the reference's own C++ compiled by oracle/Makefile into oracle/_ref (unmodified sources).
+
+Inputs are seeded (speaker_recognition_b200.synth) and stored next to the outputs so the fixtures
+are self-contained: /root/reference does not exist on the GPU box.
+Run:  python tests/golden/make_golden.py      (needs /root/reference and `make -C oracle`)
+"""
+import builtins
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from speaker_recognition_b200 import synth  # noqa: E402
+from oracle import ref_so  # noqa: E402
+
+
+def load_reference_mfcc():
+    """exec the reference's feature/utils.py and feature/MFCC.py (py3-patched in memory)."""
+    with open(os.path.join(REF, "src/feature/utils.py")) as f:
+        utils_src = f.read()
+    utils_mod = types.ModuleType("utils")
+    exec(compile(utils_src, "ref:feature/utils.py", "exec"), utils_mod.__dict__)
+    sys.modules["utils"] = utils_mod
+    with open(os.path.join(REF, "src/feature/MFCC.py")) as f:
+        src = f.read()
+    patched = (src
+               .replace("(len(signal) - self.FRAME_LEN) / self.FRAME_SHIFT + 1",
+                        "(len(signal) - self.FRAME_LEN) // self.FRAME_SHIFT + 1")
+               .replace("[:self.FFT_SIZE / 2 + 1]", "[:self.FFT_SIZE // 2 + 1]")
+               .replace("xrange", "range")
+               .replace("signal = cast['float'](signal)", "signal = asarray(signal, dtype=float)"))
+    assert patched.count("//") == 3 and "xrange" not in patched   # 2 divisions + the URL in a docstring
+    mod = types.ModuleType("MFCC_ref")
+    exec(compile(patched, "ref:feature/MFCC.py", "exec"), mod.__dict__)
+    # `from numpy import *` shadows the builtin min under NumPy 2; the reference ran under NumPy 1
+    # where it did not.  Restore the builtin the reference used at MFCC.py:94.
+    mod.__dict__["min"] = builtins.min
+    del sys.modules["utils"]
+    return mod, utils_mod
+
+
+def gen_mfcc():
+    MFCC, utils = load_reference_mfcc()
+    cases = {}
+    # C1: 5 s @ 16 kHz defaults
+    sig = synth.audio(80000, seed=0, fs=16000)
+    cases["c1_16k"] = dict(fs=16000, signal=sig, kwargs={}, out=MFCC.extract(16000, sig))
+    # diff=True on a shorter clip
+    sig = synth.audio(24000, seed=1, fs=16000)
+    cases["diff_16k"] = dict(fs=16000, signal=sig, kwargs={}, out=MFCC.extract((16000, sig), diff=True))
+    # 39-dim: extract then diff_feature(nd=2)
+    cases["d39_16k"] = dict(fs=16000, signal=sig, kwargs={}, out=utils.diff_feature(MFCC.extract(16000, sig), nd=2))
+    # 8 kHz (the GUI's recording rate, gui.py:49) -> FRAME_LEN 256, SHIFT 128
+    sig = synth.audio(16000, seed=2, fs=8000)
+    cases["c_8k"] = dict(fs=8000, signal=sig, kwargs={}, out=MFCC.extract(8000, sig))
+    # non-default kwargs (the sweep in src/test/test-feature.py): 19 ceps, 55 filters, 20/10 ms
+    sig = synth.audio(20000, seed=3, fs=16000)
+    kw = dict(n_ceps=19, n_filters=55, win_length_ms=20, win_shift_ms=10, FFT_SIZE=1024, pre_emphasis_coef=0.97)
+    cases["kw_16k"] = dict(fs=16000, signal=sig, kwargs=kw, out=MFCC.extract(16000, sig, **kw))
+    # raw (un-normalised) cepstra + tables for the default extractor, to localise failures
+    ex = MFCC.get_mfcc_extractor(16000)
+    tab = dict(window=ex.window, mel=ex.M, dct=ex.D)
+    flat = {}
+    for name, c in cases.items():
+        flat[name + "/fs"] = np.int64(c["fs"])
+        flat[name + "/signal"] = c["signal"]
+        flat[name + "/out"] = c["out"]
+        flat[name + "/kwargs"] = np.array(repr(c["kwargs"]))
+    for k, v in tab.items():
+        flat["tables16k/" + k] = v
+    np.savez_compressed(os.path.join(HERE, "mfcc_ref.npz"), **flat)
+    print("mfcc_ref.npz:", {k: v["out"].shape for k, v in cases.items()})
+
+
+def gen_gmm():
+    from oracle import gmm_ref
+    flat = {}
+    rng = np.random.default_rng(7)
+    # (1) shipped real-parameter models (D=34): params + frames drawn from them + reference scores
+    for tag, fname, n in [("ubm32", "ubm.mixture-32.utt-300.model", 500),
+                          ("ubm64", "ubm.mixture-64.utt-300.model", 300),
+                          ("ubm256", "ubm.mixture-256.nperson-300.immature.model", 300)]:
+        path = os.path.join(REF, "src/gui/model", fname)
+        g = ref_so.RefGMM.load(path)
+        w, m, s = g.params()
+        X = synth.draw(w, m, s, n, seed=11)
+        X[: n // 10] *= 1.7                    # some poorly-explained frames
+        flat[tag + "/w"], flat[tag + "/mean"], flat[tag + "/sigma"], flat[tag + "/X"] = w, m, s, X
+        flat[tag + "/score_fastexp"] = g.score(X, 4)
+        flat[tag + "/score_libmexp"] = g.score_exactexp(X)
+        flat[tag + "/score_all"] = np.float64(g.score_all_abi(X, 4))
+        g.free()
+    # (2) synthetic config-2-shaped speakers (D=39, K=128): 4 speakers, frames from speaker 3
+    W, M, S = synth.models(4, 128, 39, seed0=1000)
+    X = synth.draw(W[3], M[3], S[3], 500, seed=12)
+    flat["c2/w"], flat["c2/mean"], flat["c2/sigma"], flat["c2/X"] = W, M, S, X
+    sc = []
+    for i in range(4):
+        g = ref_so.RefGMM(W[i], M[i], S[i])
+        sc.append(g.score(X, 4))
+        g.free()
+    flat["c2/score_fastexp"] = np.stack(sc)
+    # (3) underflow behaviour: frames scaled so that some totals underflow (safe_log clamp, gmm.cc:34-38)
+    w, m, s = flat["ubm32/w"], flat["ubm32/mean"], flat["ubm32/sigma"]
+    Xu = synth.draw(w, m, s, 400, seed=13) * np.linspace(1.0, 8.0, 400)[:, None]
+    g = ref_so.RefGMM(w, m, s)
+    flat["underflow/X"] = Xu
+    flat["underflow/score_fastexp"] = g.score(Xu, 2)
+    g.free()
+    # (4) one EM iteration and one MAP iteration from an injected start (K=8, D=13 and K=32, D=34)
+    w0, m0, s0 = synth.model(8, 13, seed=21, floor_frac=0.0)
+    Xt = synth.draw(*synth.model(8, 13, seed=22, floor_frac=0.0), 1500, seed=23)
+    g = ref_so.RefGMM(w0, m0, s0)
+    g.em_iteration(Xt, 1e-3, 2)
+    flat["em/w0"], flat["em/mean0"], flat["em/sigma0"], flat["em/X"] = w0, m0, s0, Xt
+    flat["em/w1"], flat["em/mean1"], flat["em/sigma1"] = g.params()
+    g.em_iteration(Xt, 1e-3, 2)
+    flat["em/w2"], flat["em/mean2"], flat["em/sigma2"] = g.params()
+    g.free()
+    ubm = ref_so.RefGMM(w, m, s)
+    spk = ref_so.RefGMM(w, m, s)
+    Xa = synth.draw(w, m + 0.3 * rng.standard_normal(m.shape), s, 600, seed=24)
+    spk.map_iteration(ubm, Xa, 2)
+    flat["map/X"] = Xa
+    flat["map/w1"], flat["map/mean1"], flat["map/sigma1"] = spk.params()
+    ubm.free(), spk.free()
+    np.savez_compressed(os.path.join(HERE, "gmm_ref.npz"), **flat)
+    print("gmm_ref.npz keys:", len(flat))
+
+
+if __name__ == "__main__":
+    gen_mfcc()
+    gen_gmm()

