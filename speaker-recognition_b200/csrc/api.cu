@@ -1,0 +1,911 @@
+// api.cu -- the extern "C" surface of libsrb200.so (include/srb200.h): handle management, model text I/O,
+// host<->device marshalling, the training driver.  All arithmetic of the hot path happens in the kernels of
+// gmm_score.cu / gmm_em.cu / mfcc.cu; this file has no CPU compute path for scoring, EM statistics or MFCC.
+#include <float.h>
+#include <math.h>
+#include <stdarg.h>
+#include <algorithm>
+#include "../../include/srb200.h"
+#include "kernels.h"
+
+namespace srb {
+
+// ---------------------------------------------------------------------------------------------
+// errors, context, buffers
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string t_err;
+void set_error(const char *fmt, ...) {
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	t_err = buf;
+}
+void clear_error() { t_err.clear(); }
+
+int DevBuf::ensure(size_t bytes) {
+	if (bytes <= cap && p) return 0;
+	if (p) {
+		cudaDeviceSynchronize();
+		cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+	size_t want = bytes + bytes / 4 + 256;
+	SRB_CUDA(cudaMalloc(&p, want));
+	cap = want;
+	return 0;
+}
+void DevBuf::release() {
+	if (p) cudaFree(p);
+	p = nullptr;
+	cap = 0;
+}
+int PinBuf::ensure(size_t bytes) {
+	if (bytes <= cap && p) return 0;
+	if (p) {
+		cudaDeviceSynchronize();
+		cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+	size_t want = bytes + bytes / 4 + 256;
+	SRB_CUDA(cudaMallocHost(&p, want));
+	cap = want;
+	return 0;
+}
+void PinBuf::release() {
+	if (p) cudaFreeHost(p);
+	p = nullptr;
+	cap = 0;
+}
+
+Context &ctx() {
+	static Context c;
+	return c;
+}
+
+int Context::init() {
+	if (inited) return 0;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		set_error("libsrb200: no usable CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+		return 1;
+	}
+	SRB_REQUIRE(device >= 0 && device < n, "libsrb200: device %d out of range (have %d)", device, n);
+	SRB_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	SRB_CUDA(cudaGetDeviceProperties(&prop, device));
+	SRB_REQUIRE(prop.major >= 10, "libsrb200: device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major, prop.minor);
+	sm_count = prop.multiProcessorCount;
+	SRB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+	inited = true;
+	return 0;
+}
+
+void PackedModels::release() {
+	if (d_tiles) cudaFree(d_tiles);
+	d_tiles = nullptr;
+	bytes = 0;
+	S = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packing: host float64 parameters -> fp32 tiles (layout documented in gmm_model.h)
+// ---------------------------------------------------------------------------------------------
+void pack_models_host(int S, int K, int D, const double *const *weights, const double *const *means, const double *const *sigmas,
+                      const int *Ks, std::vector<float> &out, int *Kpad_out) {
+	const int Kpad = ceil_div(K, MT) * MT;
+	const int tiles = Kpad / MT;
+	const size_t tf = tile_floats(D);
+	out.assign((size_t)S * tiles * tf, 0.f);
+	const double A0 = 0.84932180028801904272;   // sqrt(log2(e)/2)
+	for (int s = 0; s < S; ++s) {
+		for (int r = 0; r < Kpad; ++r) {
+			float *tile = out.data() + ((size_t)s * tiles + (r >> 5)) * tf;
+			const int m = r & 31;
+			float c2 = PAD_C2;
+			if (r < Ks[s]) {
+				const double *mu = means[s] + (size_t)r * D, *sg = sigmas[s] + (size_t)r * D;
+				double c = weights[s][r] > 0.0 ? log2(weights[s][r]) : -1.0e30;
+				for (int d = 0; d < D; ++d) {
+					const double a = A0 / sg[d];
+					float *t = tile + (size_t)d * 64 + (m >> 1) * 4 + (m & 1) * 2;
+					t[0] = (float)a;
+					t[1] = (float)(-mu[d] * a);
+					c -= log2(2.5066282746310002 * sg[d]);   // SQRT_2_PI, gmm.cc:22
+				}
+				c2 = (c < -1.0e30 || c != c) ? PAD_C2 : (float)c;
+			}
+			tile[64 * D + m] = c2;
+		}
+	}
+	*Kpad_out = Kpad;
+}
+
+int upload_packed(PackedModels &pm, int S, int K, int D, const std::vector<float> &host, int Kpad, cudaStream_t st) {
+	const size_t bytes = host.size() * sizeof(float);
+	if (pm.d_tiles == nullptr || pm.bytes < bytes) {
+		pm.release();
+		SRB_CUDA(cudaMalloc(&pm.d_tiles, bytes));
+		pm.bytes = bytes;
+	}
+	SRB_CUDA(cudaMemcpyAsync(pm.d_tiles, host.data(), bytes, cudaMemcpyHostToDevice, st));
+	SRB_CUDA(cudaStreamSynchronize(st));
+	pm.S = S;
+	pm.K = K;
+	pm.Kpad = Kpad;
+	pm.D = D;
+	pm.tiles_per_model = Kpad / MT;
+	return 0;
+}
+
+int gmm_pull_device_master(GMM *g) {
+	if (!g->host_stale) return 0;
+	const int K = g->nr_mixtures, D = g->dim;
+	std::vector<double> buf((size_t)K + 2 * (size_t)K * D);
+	SRB_CUDA(cudaMemcpy(buf.data(), g->d_params, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+	g->weights.assign(buf.begin(), buf.begin() + K);
+	g->means.assign(buf.begin() + K, buf.begin() + K + (size_t)K * D);
+	g->sigmas.assign(buf.begin() + K + (size_t)K * D, buf.end());
+	g->host_stale = false;
+	return 0;
+}
+
+int gmm_ensure_device_master(GMM *g) {
+	const int K = g->nr_mixtures, D = g->dim;
+	SRB_REQUIRE(K > 0 && D > 0 && (int)g->weights.size() == K, "gmm: model has no parameters");
+	if (g->master_valid && g->d_params && g->d_params_K == K && g->d_params_D == D) return 0;
+	if (g->d_params && (g->d_params_K != K || g->d_params_D != D)) {
+		cudaFree(g->d_params);
+		g->d_params = nullptr;
+	}
+	const size_t n = (size_t)K + 2 * (size_t)K * D;
+	if (!g->d_params) SRB_CUDA(cudaMalloc(&g->d_params, n * sizeof(double)));
+	g->d_params_K = K;
+	g->d_params_D = D;
+	std::vector<double> buf;
+	buf.reserve(n);
+	buf.insert(buf.end(), g->weights.begin(), g->weights.end());
+	buf.insert(buf.end(), g->means.begin(), g->means.end());
+	buf.insert(buf.end(), g->sigmas.begin(), g->sigmas.end());
+	SRB_CUDA(cudaMemcpy(g->d_params, buf.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+	g->master_valid = true;
+	return 0;
+}
+
+int gmm_ensure_packed(GMM *g) {
+	if (g->packed_valid) return 0;
+	if (gmm_pull_device_master(g)) return 1;
+	const int K = g->nr_mixtures, D = g->dim;
+	SRB_REQUIRE(K > 0 && D > 0 && (int)g->weights.size() == K && (int)g->means.size() == K * D, "gmm: model has no parameters (train, load or set_params first)");
+	SRB_REQUIRE(D <= MAX_DIM, "gmm: dim %d > %d unsupported", D, MAX_DIM);
+	std::vector<float> host;
+	int Kpad = 0;
+	const double *w = g->weights.data(), *m = g->means.data(), *s = g->sigmas.data();
+	pack_models_host(1, K, D, &w, &m, &s, &K, host, &Kpad);
+	if (upload_packed(g->packed, 1, K, D, host, Kpad, ctx().stream)) return 1;
+	g->packed_valid = true;
+	return 0;
+}
+
+}  // namespace srb
+
+GMM::~GMM() {
+	packed.release();
+	if (d_params) cudaFree(d_params);
+}
+
+struct srb200_gmmset {
+	srb::PackedModels packed;
+	int S = 0, D = 0, K = 0;
+};
+
+struct srb200_mfcc {
+	srb::MfccPlan *plan = nullptr;
+};
+
+using namespace srb;
+
+#define API_ENTER()                                    \
+	std::lock_guard<std::recursive_mutex> lk_(ctx().mu); \
+	clear_error()
+
+// ---------------------------------------------------------------------------------------------
+// model text I/O -- format of GMM::dump/load (gmm.cc:655-682) and Gaussian::dump/load (gmm.cc:101-150)
+// ---------------------------------------------------------------------------------------------
+static int read_model_file(const char *path, GMM *g) {
+	FILE *f = fopen(path, "rb");
+	SRB_REQUIRE(f != nullptr, "load: cannot open '%s'", path);
+	std::string txt;
+	char buf[1 << 16];
+	size_t n;
+	while ((n = fread(buf, 1, sizeof buf, f)) > 0) txt.append(buf, n);
+	fclose(f);
+	const char *p = txt.c_str();
+	auto next_num = [&](double *out) -> bool {
+		char *end = nullptr;
+		while (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r') ++p;
+		if (!*p) return false;
+		*out = strtod(p, &end);
+		if (end == p) return false;
+		p = end;
+		return true;
+	};
+	double v;
+	SRB_REQUIRE(next_num(&v) && v >= 1 && v < 1e7, "load: '%s' is not a GMM model file", path);
+	const int K = (int)v;
+	g->weights.resize(K);
+	for (int k = 0; k < K; ++k) SRB_REQUIRE(next_num(&g->weights[k]), "load: '%s' truncated in the weights", path);
+	int D = 0;
+	for (int k = 0; k < K; ++k) {
+		double dd, cov;
+		SRB_REQUIRE(next_num(&dd) && next_num(&cov), "load: '%s' truncated at gaussian %d", path, k);
+		SRB_REQUIRE((int)cov == 1, "load: only diagonal covariance supported (gmm.cc:211-215)");
+		if (k == 0) {
+			D = (int)dd;
+			SRB_REQUIRE(D >= 1 && D <= 100000, "load: bad dimension in '%s'", path);
+			g->means.resize((size_t)K * D);
+			g->sigmas.resize((size_t)K * D);
+		}
+		SRB_REQUIRE((int)dd == D, "load: inconsistent dimensions in '%s'", path);
+		for (int d = 0; d < D; ++d) SRB_REQUIRE(next_num(&g->means[(size_t)k * D + d]), "load: '%s' truncated", path);
+		for (int d = 0; d < D; ++d) SRB_REQUIRE(next_num(&g->sigmas[(size_t)k * D + d]), "load: '%s' truncated", path);
+	}
+	g->nr_mixtures = K;
+	g->dim = D;
+	g->covariance_type = 1;
+	g->invalidate();
+	return 0;
+}
+
+static int write_model_file(GMM *g, const char *path, int digits) {
+	if (gmm_pull_device_master(g)) return 1;
+	SRB_REQUIRE((int)g->weights.size() == g->nr_mixtures && g->nr_mixtures > 0, "dump: model has no parameters");
+	FILE *f = fopen(path, "wb");
+	SRB_REQUIRE(f != nullptr, "dump: cannot open '%s' for writing", path);
+	char fmt[16];
+	snprintf(fmt, sizeof fmt, "%%.%dg ", digits);
+	const int K = g->nr_mixtures, D = g->dim;
+	fprintf(f, "%d\n", K);
+	for (int k = 0; k < K; ++k) fprintf(f, fmt, g->weights[k]);
+	fprintf(f, "\n");
+	for (int k = 0; k < K; ++k) {
+		fprintf(f, "%d %d\n", D, 1);
+		for (int d = 0; d < D; ++d) fprintf(f, fmt, g->means[(size_t)k * D + d]);
+		fprintf(f, "\n");
+		for (int d = 0; d < D; ++d) fprintf(f, fmt, g->sigmas[(size_t)k * D + d]);
+		fprintf(f, "\n");
+	}
+	const bool ok = !ferror(f);
+	fclose(f);
+	SRB_REQUIRE(ok, "dump: write error on '%s'", path);
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host scoring helpers
+// ---------------------------------------------------------------------------------------------
+struct RowSrc {      // where the host frames come from
+	const double *const *pp = nullptr;   // double** (reference ABI)
+	const double *c64 = nullptr;         // contiguous [n][dim]
+	const float *c32 = nullptr;
+};
+
+static int stage_frames(const RowSrc &src, int n, int dim, int *ld_out) {
+	Context &c = ctx();
+	const int ld = (dim + 3) & ~3;
+	if (c.h_x.ensure((size_t)n * ld * sizeof(float)) || c.d_x.ensure((size_t)n * ld * sizeof(float))) return 1;
+	float *h = c.h_x.as<float>();
+	for (int i = 0; i < n; ++i) {
+		float *row = h + (size_t)i * ld;
+		if (src.pp) {
+			const double *r = src.pp[i];
+			for (int d = 0; d < dim; ++d) row[d] = (float)r[d];
+		} else if (src.c64) {
+			const double *r = src.c64 + (size_t)i * dim;
+			for (int d = 0; d < dim; ++d) row[d] = (float)r[d];
+		} else {
+			const float *r = src.c32 + (size_t)i * dim;
+			for (int d = 0; d < dim; ++d) row[d] = r[d];
+		}
+		for (int d = dim; d < ld; ++d) row[d] = 0.f;
+	}
+	SRB_CUDA(cudaMemcpyAsync(c.d_x.p, h, (size_t)n * ld * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+	*ld_out = ld;
+	return 0;
+}
+
+// scores n staged frames against pm; returns sums[S] and optionally per-frame values for model 0
+static int score_staged(const PackedModels &pm, int n, int ld, int dim, double *sums, float *frame_out_host) {
+	Context &c = ctx();
+	const int S = pm.S;
+	if (c.d_sums.ensure((size_t)S * sizeof(double)) || c.h_out.ensure(std::max((size_t)S * sizeof(double), (size_t)n * sizeof(float)))) return 1;
+	float *d_frame = nullptr;
+	if (frame_out_host) {
+		if (c.d_frame.ensure((size_t)n * sizeof(float))) return 1;
+		d_frame = c.d_frame.as<float>();
+	}
+	const int utt_off[2] = {0, n};
+	if (launch_score(pm, c.d_x.as<float>(), ld, dim, utt_off, 1, c.d_sums.as<double>(), d_frame, n, nullptr, c.compat_clamp, 0, c.stream)) return 1;
+	SRB_CUDA(cudaMemcpyAsync(c.h_out.p, c.d_sums.p, (size_t)S * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	SRB_CUDA(cudaStreamSynchronize(c.stream));
+	memcpy(sums, c.h_out.p, (size_t)S * sizeof(double));
+	if (frame_out_host) {
+		SRB_CUDA(cudaMemcpyAsync(c.h_out.p, d_frame, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+		SRB_CUDA(cudaStreamSynchronize(c.stream));
+		memcpy(frame_out_host, c.h_out.p, (size_t)n * sizeof(float));
+	}
+	return 0;
+}
+
+static int gmm_score_host(GMM *g, const RowSrc &src, int n, int dim, double *frame_out64, float *frame_out32, double *sum_out) {
+	SRB_REQUIRE(g != nullptr, "score: null model");
+	if (ctx().init()) return 1;
+	if (gmm_ensure_packed(g)) return 1;
+	SRB_REQUIRE(dim == g->dim, "score: nr_dim %d != model dim %d (the reference asserts here, gmm.cc:177)", dim, g->dim);
+	if (n <= 0) {
+		if (sum_out) *sum_out = 0.0;
+		return 0;
+	}
+	int ld = 0;
+	if (stage_frames(src, n, dim, &ld)) return 1;
+	std::vector<float> tmp;
+	float *fo = frame_out32;
+	if (frame_out64 && !fo) {
+		tmp.resize(n);
+		fo = tmp.data();
+	}
+	double sum = 0.0;
+	if (score_staged(g->packed, n, ld, dim, &sum, fo)) return 1;
+	if (frame_out64)
+		for (int i = 0; i < n; ++i) frame_out64[i] = (double)fo[i];
+	if (sum_out) *sum_out = sum;
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// training driver (GMMTrainerBaseline::train, gmm.cc:581-653, on device-resident frames)
+// ---------------------------------------------------------------------------------------------
+static int em_estep(GMM *g, const float *dX, int n, int ld, int D, double *d_stats, cudaStream_t st) {
+	Context &c = ctx();
+	if (c.d_frame.ensure((size_t)n * sizeof(float)) || c.d_sums.ensure(sizeof(double))) return 1;
+	const int utt_off[2] = {0, n};
+	// pass A: per-frame log2 p(x) (unclamped) + total log-likelihood (clamped like the reference's monitor, gmm.cc:635)
+	if (launch_score(g->packed, dX, ld, D, utt_off, 1, c.d_sums.as<double>(), c.d_frame.as<float>(), n, nullptr, c.compat_clamp, 1, st)) return 1;
+	// pass B: responsibilities + sufficient statistics
+	return launch_estep_accumulate(g->packed, dX, n, ld, D, g->nr_mixtures, c.d_frame.as<float>(), c.d_sums.as<double>(), d_stats,
+	                               c.compat_clamp, st);
+}
+
+static int train_driver(GMM *g, const float *dX, int n, int ld, int D, const Parameter *p, int mode, GMM *ubm, int *iters_out, double *ll_out) {
+	Context &c = ctx();
+	const int K = g->nr_mixtures;
+	g->master_valid = false;
+	if (gmm_ensure_device_master(g)) return 1;
+	if (launch_pack_from_master(g->d_params, K, D, g->packed, c.stream)) return 1;
+	g->packed_valid = true;
+	const double *d_ubm = nullptr;
+	if (mode == 1) {
+		if (gmm_pull_device_master(ubm)) return 1;
+		ubm->master_valid = ubm->master_valid && !ubm->host_stale;
+		if (gmm_ensure_device_master(ubm)) return 1;
+		d_ubm = ubm->d_params;
+	}
+	if (c.d_stats.ensure((size_t)em_stats_len(K, D) * sizeof(double))) return 1;
+	double *d_stats = c.d_stats.as<double>();
+	double last_ll = -DBL_MAX, ll = 0.0;
+	int iters = 0;
+	for (int i = 0; i < p->nr_iteration; ++i) {
+		if (em_estep(g, dX, n, ld, D, d_stats, c.stream)) return 1;
+		if (launch_mstep(g->d_params, d_ubm, K, D, d_stats, (long long)n, p->min_covar, mode, c.stream)) return 1;
+		if (launch_pack_from_master(g->d_params, K, D, g->packed, c.stream)) return 1;
+		++iters;
+		if (i % 2 == 0) continue;                       // gmm.cc:622
+		// monitor the log-likelihood of the UPDATED model (gmm.cc:631-651)
+		const int utt_off[2] = {0, n};
+		if (launch_score(g->packed, dX, ld, D, utt_off, 1, c.d_sums.as<double>(), nullptr, 0, nullptr, c.compat_clamp, 0, c.stream)) return 1;
+		SRB_CUDA(cudaMemcpyAsync(&ll, c.d_sums.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+		SRB_CUDA(cudaStreamSynchronize(c.stream));
+		if (p->verbosity >= 1) {
+			printf("iter %d: ll %lf\n", i, ll);
+			fflush(stdout);
+		}
+		const double ll_diff = ll - last_ll;
+		if (fabs(ll_diff) / fabs(ll) < p->threshold && ll_diff < p->threshold) {
+			if (p->verbosity >= 1) printf("too small log likelihood increment, abort iteration.\n");
+			break;
+		}
+		last_ll = ll;
+	}
+	SRB_CUDA(cudaStreamSynchronize(c.stream));
+	g->host_stale = true;
+	g->master_valid = true;
+	if (gmm_pull_device_master(g)) return 1;
+	if (iters_out) *iters_out = iters;
+	if (ll_out) *ll_out = ll;
+	return 0;
+}
+
+static uint64_t g_train_calls = 0;
+static inline uint64_t splitmix64(uint64_t &s) {
+	uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+// init_gaussians (gmm.cc:306-361) without k-means: means = random data rows, sigma = global unbiased std, w = 1/K
+static int init_like_reference(GMM *g, const RowSrc &src, int n, int D, uint64_t seed) {
+	const int K = g->nr_mixtures;
+	auto row = [&](int i, int d) -> double { return src.pp ? src.pp[i][d] : src.c64[(size_t)i * D + d]; };
+	std::vector<double> mean(D, 0.0), var(D, 0.0);
+	for (int i = 0; i < n; ++i)
+		for (int d = 0; d < D; ++d) mean[d] += row(i, d);
+	for (int d = 0; d < D; ++d) mean[d] /= n;
+	for (int i = 0; i < n; ++i)
+		for (int d = 0; d < D; ++d) {
+			const double t = row(i, d) - mean[d];
+			var[d] += t * t;
+		}
+	g->dim = D;
+	g->weights.assign(K, 1.0 / K);
+	g->means.resize((size_t)K * D);
+	g->sigmas.resize((size_t)K * D);
+	uint64_t s = seed;
+	for (int k = 0; k < K; ++k) {
+		const double u = (double)(splitmix64(s) >> 11) * (1.0 / 9007199254740992.0);
+		int idx = (int)(u * n);                          // rand_int: rand_real() * max_val, random.hh:46-48
+		if (idx >= n) idx = n - 1;
+		for (int d = 0; d < D; ++d) {
+			g->means[(size_t)k * D + d] = row(idx, d);
+			g->sigmas[(size_t)k * D + d] = sqrt(var[d] * (1.0 / (n - 1)));   // gmm.cc:323-325
+		}
+	}
+	g->invalidate();
+	return 0;
+}
+
+static void print_param(const Parameter *p) {   // pygmm.cc:31-41 (the reference prints on every train; here only when verbose)
+	printf("nr_instance   :   %d\nnr_dim        :   %d\nnr_mixture    :   %d\nmin_covar     :   %f\nthreshold     :   %f\n"
+	       "nr_iteration  :   %d\ninit_with_kmeans: %d\nconcurrency   :   %d\nverbosity     :   %d\n",
+	       p->nr_instance, p->nr_dim, p->nr_mixture, p->min_covar, p->threshold, p->nr_iteration, p->init_with_kmeans, p->concurrency,
+	       p->verbosity);
+}
+
+static int train_host(GMM *g, GMM *ubm, const RowSrc &src, const Parameter *p, uint64_t seed, int *iters_out, double *ll_out) {
+	SRB_REQUIRE(g != nullptr && p != nullptr, "train: null argument");
+	if (ctx().init()) return 1;
+	const int n = p->nr_instance, D = p->nr_dim;
+	SRB_REQUIRE(n > 0, "X.size() == 0");                 // gmm.cc:582-586 (thrown as const char* in the reference)
+	SRB_REQUIRE(D >= 1 && D <= MAX_DIM, "train: nr_dim %d outside [1,%d]", D, MAX_DIM);
+	if (p->verbosity >= 1) print_param(p);
+	if (ubm == nullptr) {
+		SRB_REQUIRE(g->nr_mixtures >= 1, "train: model has no mixtures");
+		SRB_REQUIRE(p->init_with_kmeans == 0, "train: init_with_kmeans=1 (K-MeansII, kmeansII.cc) is not built yet; pygmm.py's default is 0");
+		SRB_REQUIRE(n >= 2, "train: need at least 2 instances");
+		if (init_like_reference(g, src, n, D, seed)) return 1;
+	} else {
+		if (gmm_pull_device_master(ubm)) return 1;
+		SRB_REQUIRE(ubm->dim == D, "train_from_ubm: UBM dim %d != data dim %d", ubm->dim, D);
+		// gmm_replace_with (gmmubm.cc:29-38): the model becomes a deep copy of the UBM
+		g->nr_mixtures = ubm->nr_mixtures;
+		g->dim = ubm->dim;
+		g->weights = ubm->weights;
+		g->means = ubm->means;
+		g->sigmas = ubm->sigmas;
+		g->invalidate();
+	}
+	int ld = 0;
+	if (stage_frames(src, n, D, &ld)) return 1;
+	return train_driver(g, ctx().d_x.as<float>(), n, ld, D, p, ubm ? 1 : 0, ubm, iters_out, ll_out);
+}
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+extern "C" {
+
+const char *srb200_last_error(void) { return t_err.c_str(); }
+const char *srb200_version(void) { return "srb200 0.1.0 (sm_100a)"; }
+
+int srb200_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+int srb200_set_device(int device) {
+	API_ENTER();
+	Context &c = ctx();
+	if (c.inited) {
+		SRB_REQUIRE(device == c.device, "set_device: the library is already bound to device %d", c.device);
+		return 0;
+	}
+	c.device = device;
+	return c.init();
+}
+int srb200_get_device(void) { return ctx().device; }
+int srb200_set_compat_clamp(int mode) {
+	API_ENTER();
+	SRB_REQUIRE(mode == 0 || mode == 1, "compat_clamp must be 0 or 1");
+	ctx().compat_clamp = mode;
+	return 0;
+}
+int srb200_get_compat_clamp(void) { return ctx().compat_clamp; }
+
+GMM *new_gmm(int nr_mixture, int covariance_type) {
+	API_ENTER();
+	if (covariance_type != 1) {
+		set_error("only diagonal matrix supported.");   // gmm.cc:211-215
+		return nullptr;
+	}
+	if (nr_mixture < 1) {
+		set_error("new_gmm: nr_mixture must be >= 1");
+		return nullptr;
+	}
+	GMM *g = new GMM();
+	g->nr_mixtures = nr_mixture;
+	return g;
+}
+
+GMM *load(const char *model_file) {
+	API_ENTER();
+	GMM *g = new GMM();
+	if (read_model_file(model_file, g)) {
+		delete g;
+		return nullptr;
+	}
+	return g;
+}
+
+void dump(GMM *gmm, const char *model_file) {
+	API_ENTER();
+	if (!gmm) {
+		set_error("dump: null model");
+		return;
+	}
+	write_model_file(gmm, model_file, 6);   // ostream default precision, gmm.cc:655-662
+}
+
+int srb200_gmm_dump_precise(GMM *gmm, const char *model_file, int digits) {
+	API_ENTER();
+	SRB_REQUIRE(gmm != nullptr, "dump: null model");
+	SRB_REQUIRE(digits >= 1 && digits <= 17, "dump: digits must be in [1,17]");
+	return write_model_file(gmm, model_file, digits);
+}
+
+void free_gmm(GMM *gmm) {
+	API_ENTER();
+	delete gmm;
+}
+
+int get_dim(GMM *gmm) { return gmm ? gmm->dim : 0; }
+int get_nr_mixtures(GMM *gmm) { return gmm ? gmm->nr_mixtures : 0; }
+
+int srb200_gmm_set_params(GMM *g, int K, int D, const double *w, const double *m, const double *s) {
+	API_ENTER();
+	SRB_REQUIRE(g && w && m && s, "set_params: null argument");
+	SRB_REQUIRE(K >= 1 && D >= 1 && D <= MAX_DIM, "set_params: bad shape K=%d D=%d", K, D);
+	for (size_t i = 0; i < (size_t)K * D; ++i) SRB_REQUIRE(s[i] > 0.0, "set_params: sigma must be positive");
+	g->nr_mixtures = K;
+	g->dim = D;
+	g->weights.assign(w, w + K);
+	g->means.assign(m, m + (size_t)K * D);
+	g->sigmas.assign(s, s + (size_t)K * D);
+	g->invalidate();
+	return 0;
+}
+
+int srb200_gmm_get_params(GMM *g, double *w, double *m, double *s) {
+	API_ENTER();
+	SRB_REQUIRE(g != nullptr, "get_params: null model");
+	if (gmm_pull_device_master(g)) return 1;
+	SRB_REQUIRE((int)g->weights.size() == g->nr_mixtures && g->dim > 0, "get_params: model has no parameters");
+	if (w) memcpy(w, g->weights.data(), g->weights.size() * sizeof(double));
+	if (m) memcpy(m, g->means.data(), g->means.size() * sizeof(double));
+	if (s) memcpy(s, g->sigmas.data(), g->sigmas.size() * sizeof(double));
+	return 0;
+}
+
+int srb200_gmm_sync_from_device(GMM *g) {
+	API_ENTER();
+	SRB_REQUIRE(g != nullptr, "null model");
+	SRB_CUDA(cudaDeviceSynchronize());
+	return gmm_pull_device_master(g);
+}
+
+// ---- scoring: the reference ABI ----
+double score_all(GMM *gmm, double **X_in, int nr_instance, int nr_dim, int /*concurrency*/) {
+	API_ENTER();
+	RowSrc src;
+	src.pp = X_in;
+	double sum = 0.0;
+	if (gmm_score_host(gmm, src, nr_instance, nr_dim, nullptr, nullptr, &sum)) return NAN;
+	return sum;
+}
+
+void score_batch(GMM *gmm, double **X_in, double *prob_out, int nr_instance, int nr_dim, int /*concurrency*/) {
+	API_ENTER();
+	RowSrc src;
+	src.pp = X_in;
+	if (gmm_score_host(gmm, src, nr_instance, nr_dim, prob_out, nullptr, nullptr))
+		for (int i = 0; i < nr_instance; ++i) prob_out[i] = NAN;
+}
+
+double score_instance(GMM *gmm, double *x_in, int nr_dim) {
+	API_ENTER();
+	RowSrc src;
+	src.c64 = x_in;
+	double sum = 0.0;
+	if (gmm_score_host(gmm, src, 1, nr_dim, nullptr, nullptr, &sum)) return NAN;
+	return sum;
+}
+
+int srb200_score_batch_f64(GMM *gmm, const double *X, int n, int dim, double *prob_out) {
+	API_ENTER();
+	RowSrc src;
+	src.c64 = X;
+	return gmm_score_host(gmm, src, n, dim, prob_out, nullptr, nullptr);
+}
+int srb200_score_all_f64(GMM *gmm, const double *X, int n, int dim, double *sum_out) {
+	API_ENTER();
+	RowSrc src;
+	src.c64 = X;
+	return gmm_score_host(gmm, src, n, dim, nullptr, nullptr, sum_out);
+}
+int srb200_score_batch_f32(GMM *gmm, const float *X, int n, int dim, float *prob_out) {
+	API_ENTER();
+	RowSrc src;
+	src.c32 = X;
+	return gmm_score_host(gmm, src, n, dim, nullptr, prob_out, nullptr);
+}
+
+// ---- training ----
+void train_model(GMM *gmm, double **X_in, Parameter *param) {
+	API_ENTER();
+	RowSrc src;
+	src.pp = X_in;
+	train_host(gmm, nullptr, src, param, 0x5EEDull + (++g_train_calls), nullptr, nullptr);
+}
+void train_model_from_ubm(GMM *gmm, GMM *ubm, double **X_in, Parameter *param) {
+	API_ENTER();
+	if (!ubm) {
+		set_error("train_model_from_ubm: null ubm");
+		return;
+	}
+	RowSrc src;
+	src.pp = X_in;
+	train_host(gmm, ubm, src, param, 0, nullptr, nullptr);
+}
+int srb200_train_f64(GMM *gmm, const double *X, const Parameter *param, uint64_t seed, int *iters_out, double *ll_out) {
+	API_ENTER();
+	RowSrc src;
+	src.c64 = X;
+	return train_host(gmm, nullptr, src, param, seed, iters_out, ll_out);
+}
+int srb200_train_from_ubm_f64(GMM *gmm, GMM *ubm, const double *X, const Parameter *param, int *iters_out, double *ll_out) {
+	API_ENTER();
+	SRB_REQUIRE(ubm != nullptr, "train_from_ubm: null ubm");
+	RowSrc src;
+	src.c64 = X;
+	return train_host(gmm, ubm, src, param, 0, iters_out, ll_out);
+}
+
+// ---- EM building blocks on device data ----
+int srb200_em_stats_len(int K, int D) { return em_stats_len(K, D); }
+
+int srb200_em_estep_dev(GMM *g, const float *dX, int n, int ld, int dim, double *d_stats, void *stream) {
+	API_ENTER();
+	SRB_REQUIRE(g && dX && d_stats, "estep: null argument");
+	if (ctx().init()) return 1;
+	SRB_REQUIRE(dim == g->dim, "estep: dim %d != model dim %d", dim, g->dim);
+	if (!g->packed_valid) {
+		// pack from the device master when it is the newest copy, else from the host arrays
+		if (g->host_stale) {
+			if (launch_pack_from_master(g->d_params, g->nr_mixtures, g->dim, g->packed, (cudaStream_t)stream)) return 1;
+			g->packed_valid = true;
+		} else if (gmm_ensure_packed(g)) return 1;
+	}
+	return em_estep(g, dX, n, ld, dim, d_stats, (cudaStream_t)stream);
+}
+
+int srb200_em_mstep_dev(GMM *g, const double *d_stats, long long n_total, double min_covar, int mode, GMM *ubm, void *stream) {
+	API_ENTER();
+	SRB_REQUIRE(g && d_stats, "mstep: null argument");
+	if (ctx().init()) return 1;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (!g->host_stale) g->master_valid = g->master_valid && g->d_params != nullptr;
+	if (gmm_ensure_device_master(g)) return 1;
+	const double *d_ubm = nullptr;
+	if (mode == 1) {
+		SRB_REQUIRE(ubm != nullptr, "mstep: MAP mode needs a UBM");
+		if (gmm_ensure_device_master(ubm)) return 1;
+		d_ubm = ubm->d_params;
+	}
+	if (launch_mstep(g->d_params, d_ubm, g->nr_mixtures, g->dim, d_stats, n_total, min_covar, mode, st)) return 1;
+	if (launch_pack_from_master(g->d_params, g->nr_mixtures, g->dim, g->packed, st)) return 1;
+	g->packed_valid = true;
+	g->host_stale = true;
+	g->master_valid = true;
+	return 0;
+}
+
+// ---- speaker sets ----
+srb200_gmmset *srb200_gmmset_create(GMM *const *models, int n_models) {
+	API_ENTER();
+	if (!models || n_models < 1) {
+		set_error("gmmset_create: no models");
+		return nullptr;
+	}
+	if (ctx().init()) return nullptr;
+	int K = 0, D = 0;
+	std::vector<const double *> w(n_models), m(n_models), s(n_models);
+	std::vector<int> Ks(n_models);
+	for (int i = 0; i < n_models; ++i) {
+		GMM *g = models[i];
+		if (!g || gmm_pull_device_master(g)) return nullptr;
+		if ((int)g->weights.size() != g->nr_mixtures || g->dim < 1) {
+			set_error("gmmset_create: model %d has no parameters", i);
+			return nullptr;
+		}
+		if (i == 0) D = g->dim;
+		if (g->dim != D) {
+			set_error("gmmset_create: model %d has dim %d, expected %d", i, g->dim, D);
+			return nullptr;
+		}
+		K = std::max(K, g->nr_mixtures);
+		Ks[i] = g->nr_mixtures;
+		w[i] = g->weights.data();
+		m[i] = g->means.data();
+		s[i] = g->sigmas.data();
+	}
+	if (D > MAX_DIM) {
+		set_error("gmmset_create: dim %d > %d unsupported", D, MAX_DIM);
+		return nullptr;
+	}
+	std::vector<float> host;
+	int Kpad = 0;
+	pack_models_host(n_models, K, D, w.data(), m.data(), s.data(), Ks.data(), host, &Kpad);
+	srb200_gmmset *set = new srb200_gmmset();
+	if (upload_packed(set->packed, n_models, K, D, host, Kpad, ctx().stream)) {
+		delete set;
+		return nullptr;
+	}
+	set->S = n_models;
+	set->D = D;
+	set->K = K;
+	return set;
+}
+
+void srb200_gmmset_free(srb200_gmmset *set) {
+	API_ENTER();
+	if (set) {
+		set->packed.release();
+		delete set;
+	}
+}
+int srb200_gmmset_size(srb200_gmmset *set) { return set ? set->S : 0; }
+int srb200_gmmset_dim(srb200_gmmset *set) { return set ? set->D : 0; }
+
+static int gmmset_score_host(srb200_gmmset *set, const RowSrc &src, int n, int dim, double *sums) {
+	SRB_REQUIRE(set && sums, "gmmset_score: null argument");
+	SRB_REQUIRE(dim == set->D, "gmmset_score: dim %d != set dim %d", dim, set->D);
+	if (n <= 0) {
+		for (int s = 0; s < set->S; ++s) sums[s] = 0.0;
+		return 0;
+	}
+	int ld = 0;
+	if (stage_frames(src, n, dim, &ld)) return 1;
+	return score_staged(set->packed, n, ld, dim, sums, nullptr);
+}
+int srb200_gmmset_score_f64(srb200_gmmset *set, const double *X, int n, int dim, double *sums) {
+	API_ENTER();
+	RowSrc src;
+	src.c64 = X;
+	return gmmset_score_host(set, src, n, dim, sums);
+}
+int srb200_gmmset_score_f32(srb200_gmmset *set, const float *X, int n, int dim, double *sums) {
+	API_ENTER();
+	RowSrc src;
+	src.c32 = X;
+	return gmmset_score_host(set, src, n, dim, sums);
+}
+int srb200_gmmset_score_dev(srb200_gmmset *set, const float *dX, int ld, int dim, const int *utt_off, int n_utt, double *d_sums,
+                            float *d_frame_ll, int ldf, int *d_best, void *stream) {
+	API_ENTER();
+	SRB_REQUIRE(set && dX && utt_off && d_sums, "gmmset_score_dev: null argument");
+	return launch_score(set->packed, dX, ld, dim, utt_off, n_utt, d_sums, d_frame_ll, ldf, d_best, ctx().compat_clamp, 0, (cudaStream_t)stream);
+}
+
+// ---- MFCC ----
+srb200_mfcc *srb200_mfcc_create(int fs, double win_length_ms, double win_shift_ms, int fft_size, int n_filters, int n_ceps,
+                                double pre_emphasis_coef) {
+	API_ENTER();
+	MfccPlan *p = mfcc_plan_create(fs, win_length_ms, win_shift_ms, fft_size, n_filters, n_ceps, pre_emphasis_coef);
+	if (!p) return nullptr;
+	srb200_mfcc *h = new srb200_mfcc();
+	h->plan = p;
+	return h;
+}
+void srb200_mfcc_free(srb200_mfcc *h) {
+	API_ENTER();
+	if (h) {
+		mfcc_plan_free(h->plan);
+		delete h;
+	}
+}
+int srb200_mfcc_frame_len(srb200_mfcc *h) { return h ? mfcc_frame_len(h->plan) : 0; }
+int srb200_mfcc_frame_shift(srb200_mfcc *h) { return h ? mfcc_frame_shift(h->plan) : 0; }
+int srb200_mfcc_num_frames(srb200_mfcc *h, long long n_samples) {
+	if (!h) return 0;
+	const long long L = mfcc_frame_len(h->plan), S = mfcc_frame_shift(h->plan);
+	if (n_samples < L) return 0;
+	return (int)((n_samples - L) / S + 1);
+}
+int srb200_mfcc_out_dim(srb200_mfcc *h, int nd) { return h ? mfcc_n_ceps(h->plan) * (nd + 1) : 0; }
+
+long long srb200_mfcc_rows_total(srb200_mfcc *h, const long long *smp_off, int n_utt, int nd) {
+	if (!h || !smp_off) return -1;
+	long long rows = 0;
+	for (int u = 0; u < n_utt; ++u) {
+		const int T = srb200_mfcc_num_frames(h, smp_off[u + 1] - smp_off[u]);
+		if (T - nd < 1) return -1;
+		rows += T - nd;
+	}
+	return rows;
+}
+
+static int mfcc_extract_host(srb200_mfcc *h, const void *pcm, int kind /*0 i16, 1 f32, 2 f64*/, long long n, int nd, int cmvn, double *out,
+                             int *rows_out) {
+	SRB_REQUIRE(h && pcm && out, "mfcc_extract: null argument");
+	SRB_REQUIRE(n > 0 && n < (1LL << 31), "mfcc_extract: bad sample count %lld", n);
+	Context &c = ctx();
+	if (c.init()) return 1;
+	const size_t esz = kind == 0 ? 2 : 4;
+	if (c.h_pcm.ensure((size_t)n * esz) || c.d_pcm.ensure((size_t)n * esz)) return 1;
+	if (kind == 2) {
+		float *dst = c.h_pcm.as<float>();
+		const double *srcp = (const double *)pcm;
+		for (long long i = 0; i < n; ++i) dst[i] = (float)srcp[i];
+	} else
+		memcpy(c.h_pcm.p, pcm, (size_t)n * esz);
+	SRB_CUDA(cudaMemcpyAsync(c.d_pcm.p, c.h_pcm.p, (size_t)n * esz, cudaMemcpyHostToDevice, c.stream));
+	const int T = srb200_mfcc_num_frames(h, n);
+	const int rows = T - nd;
+	const int cols = mfcc_n_ceps(h->plan) * (nd + 1);
+	const int ld = (cols + 3) & ~3;
+	const long long smp_off[2] = {0, n};
+	int feat_off[2];
+	if (c.d_feat.ensure((size_t)std::max(rows, 1) * ld * sizeof(float))) return 1;
+	if (launch_mfcc(h->plan, c.d_pcm.p, kind != 0, smp_off, 1, nd, cmvn, c.d_feat.as<float>(), ld, feat_off, c.stream)) return 1;
+	if (c.h_out.ensure((size_t)rows * ld * sizeof(float))) return 1;
+	SRB_CUDA(cudaMemcpyAsync(c.h_out.p, c.d_feat.p, (size_t)rows * ld * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+	SRB_CUDA(cudaStreamSynchronize(c.stream));
+	const float *src = c.h_out.as<float>();
+	for (int r = 0; r < rows; ++r)
+		for (int j = 0; j < cols; ++j) out[(size_t)r * cols + j] = (double)src[(size_t)r * ld + j];
+	if (rows_out) *rows_out = rows;
+	return 0;
+}
+int srb200_mfcc_extract_i16(srb200_mfcc *h, const int16_t *pcm, long long n, int nd, int cmvn, double *out, int *rows_out) {
+	API_ENTER();
+	return mfcc_extract_host(h, pcm, 0, n, nd, cmvn, out, rows_out);
+}
+int srb200_mfcc_extract_f32(srb200_mfcc *h, const float *pcm, long long n, int nd, int cmvn, double *out, int *rows_out) {
+	API_ENTER();
+	return mfcc_extract_host(h, pcm, 1, n, nd, cmvn, out, rows_out);
+}
+int srb200_mfcc_extract_f64(srb200_mfcc *h, const double *pcm, long long n, int nd, int cmvn, double *out, int *rows_out) {
+	API_ENTER();
+	return mfcc_extract_host(h, pcm, 2, n, nd, cmvn, out, rows_out);
+}
+int srb200_mfcc_extract_dev(srb200_mfcc *h, const int16_t *d_pcm, const long long *smp_off, int n_utt, int nd, float *d_feat, int ld,
+                            int *feat_off, void *stream) {
+	API_ENTER();
+	SRB_REQUIRE(h && d_pcm && smp_off && d_feat, "mfcc_extract_dev: null argument");
+	return launch_mfcc(h->plan, d_pcm, 0, smp_off, n_utt, nd, 1, d_feat, ld, feat_off, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,387 @@
+// gmm_score.cu -- diagonal-GMM log-likelihood scoring for sm_100a.
+//
+// Replaces the reference's hot loop #2:
+//   Gaussian::probability_of_fast_exp      src/gmm/src/gmm.cc:176-202   (per-dim exp, linear-domain product)
+//   GMM::log_probability_of_fast_exp       src/gmm/src/gmm.cc:237-244   (weighted sum, safe_log)
+//   threaded_log_probability_of            src/gmm/src/gmm.cc:533-569   (thread pool over frames, serial sum)
+// and the Python loop over speakers of GMMSet.predict_one_scores (src/testbench/gmmset.py:59-64).
+//
+// Formulation (log2 domain, no cancellation -- SURVEY.md s7 hard part 2a):
+//   t = x_d * a_kd + nb_kd            a = sqrt(log2e/2)/sigma, nb = -mean*a       (1 FFMA)
+//   acc_k = -c2_k + sum_d t*t                                                     (1 FFMA)
+//   log2 p(x) = log2 sum_k 2^(-acc_k)    via an online max/sum over 32-row mixture tiles
+// One CTA = 128 threads = 4 warps owns a tile of 256 frames (x tile transposed in shared memory for the whole
+// CTA lifetime) and walks the packed parameter tiles of its speaker chunk, which a single elected thread streams
+// with cp.async.bulk (TMA engine) into a 3-stage mbarrier ring.  Each thread keeps an 8-frame x 8-mixture
+// register tile: per dimension 2 LDS.128 (frames) + 4 LDS.128 (broadcast parameters) feed 128 FFMA.
+// The kernel is bound by the fp32 FMA pipe (2*D FFMA per frame-mixture pair); HBM traffic is the x tile once
+// and the parameters from L2 (DESIGN.md "roofline").
+#include "gmm_model.h"
+#include "kernels.h"
+
+namespace srb {
+
+constexpr int SC_THREADS = 128;
+constexpr int SC_FT = 256;          // frames per CTA tile
+constexpr int SC_STAGES = 3;
+constexpr float LN2F = 0.69314718055994531f;
+constexpr float DENORM_LOG_MIN_F = -744.4400719213812f;   // log(4.94e-324): the reference's linear-domain sum is 0 below this
+constexpr float SAFE_LOG_FLOOR_F = -34.538776394910684f;  // log(1e-15), gmm.cc:34-38
+
+struct ScoreArgs {
+	const float *X;
+	int ld, D;
+	const float *tiles;        // packed parameter tiles
+	int tiles_per_model, S, spk_per_chunk;
+	const int4 *ftiles;        // per frame tile: {first frame, frame count, utterance, 0}
+	float *frame_ll;           // optional [S][ldf]
+	int ldf;
+	double *partial;           // [n_frame_tiles][S]
+	int clamp;
+	int frame_log2;            // frame_ll receives the unclamped log2-domain value (E-step normaliser) instead of ln
+	int x_vec_ok;              // X rows are 16-B aligned and ld % 4 == 0
+};
+
+__global__ void __launch_bounds__(SC_THREADS, 3) gmm_score_kernel(const ScoreArgs A) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int D = A.D;
+	const int tileF = 64 * D + 32;
+	float *xs = reinterpret_cast<float *>(smem_raw);                  // [D][256]
+	float *ps = xs + (size_t)D * SC_FT;                               // [STAGES][tileF]
+	uint64_t *bars = reinterpret_cast<uint64_t *>(ps + (size_t)SC_STAGES * tileF);
+	double *red = reinterpret_cast<double *>(bars + SC_STAGES);       // [2][4]
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int g = lane >> 2, q = lane & 3;
+	const int4 ft = A.ftiles[blockIdx.x];
+	const int f0 = ft.x, nf = ft.y;
+	const int s_begin = blockIdx.y * A.spk_per_chunk;
+	const int s_end = min(A.S, s_begin + A.spk_per_chunk);
+	const int n_tiles = (s_end - s_begin) * A.tiles_per_model;
+	const float *gt0 = A.tiles + (size_t)s_begin * A.tiles_per_model * tileF;
+	const uint32_t tile_bytes = (uint32_t)tileF * 4u;
+
+	if (tid == 0) {
+		for (int s = 0; s < SC_STAGES; ++s) mbar_init(&bars[s], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+	if (tid == 0) {
+		const int pre = n_tiles < SC_STAGES ? n_tiles : SC_STAGES;
+		for (int i = 0; i < pre; ++i) {
+			mbar_expect_tx(&bars[i], tile_bytes);
+			bulk_g2s(ps + (size_t)i * tileF, gt0 + (size_t)i * tileF, tile_bytes, &bars[i]);
+		}
+	}
+
+	// ---- x tile: global [frame][ld] -> shared [d][frame]; each thread owns frames tid and tid+128 ----
+	for (int f = tid; f < SC_FT; f += SC_THREADS) {
+		if (f < nf) {
+			const float *row = A.X + (size_t)(f0 + f) * A.ld;
+			if (A.x_vec_ok) {
+				const float4 *row4 = reinterpret_cast<const float4 *>(row);
+				const int n4 = D >> 2;
+				for (int d4 = 0; d4 < n4; ++d4) {
+					const float4 v = __ldg(row4 + d4);
+					xs[(4 * d4 + 0) * SC_FT + f] = v.x;
+					xs[(4 * d4 + 1) * SC_FT + f] = v.y;
+					xs[(4 * d4 + 2) * SC_FT + f] = v.z;
+					xs[(4 * d4 + 3) * SC_FT + f] = v.w;
+				}
+				for (int d = n4 * 4; d < D; ++d) xs[d * SC_FT + f] = __ldg(row + d);
+			} else {
+				for (int d = 0; d < D; ++d) xs[d * SC_FT + f] = __ldg(row + d);
+			}
+		} else {
+			for (int d = 0; d < D; ++d) xs[d * SC_FT + f] = 0.f;
+		}
+	}
+	__syncthreads();
+
+	// thread's 8 frames: {warp*64 + 4g + i} and {warp*64 + 32 + 4g + i}, i = 0..3
+	const float *xbase = xs + warp * 64 + 4 * g;
+	float m_run[8], s_run[8];
+#pragma unroll
+	for (int f = 0; f < 8; ++f) {
+		m_run[f] = -3.0e38f;
+		s_run[f] = 0.f;
+	}
+	int spk = s_begin, tile_in_spk = 0;
+
+	for (int it = 0; it < n_tiles; ++it) {
+		const int stage = it % SC_STAGES;
+		mbar_wait(&bars[stage], (uint32_t)((it / SC_STAGES) & 1));
+		const float *pt = ps + (size_t)stage * tileF;
+
+		float acc[8][8];
+		{
+			const float *cp = pt + 64 * D;
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const float2 c = *reinterpret_cast<const float2 *>(cp + 2 * (4 * j + q));
+#pragma unroll
+				for (int f = 0; f < 8; ++f) {
+					acc[f][2 * j] = -c.x;
+					acc[f][2 * j + 1] = -c.y;
+				}
+			}
+		}
+		const float *pq = pt + 4 * q;
+#pragma unroll 2
+		for (int d = 0; d < D; ++d) {
+			const float4 xa = *reinterpret_cast<const float4 *>(xbase + d * SC_FT);
+			const float4 xb = *reinterpret_cast<const float4 *>(xbase + d * SC_FT + 32);
+			const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const float4 p = *reinterpret_cast<const float4 *>(pq + d * 64 + 16 * j);
+#pragma unroll
+				for (int f = 0; f < 8; ++f) {
+					const float t0 = fmaf(xv[f], p.x, p.y);
+					acc[f][2 * j] = fmaf(t0, t0, acc[f][2 * j]);
+					const float t1 = fmaf(xv[f], p.z, p.w);
+					acc[f][2 * j + 1] = fmaf(t1, t1, acc[f][2 * j + 1]);
+				}
+			}
+		}
+		// ---- online log2-sum-exp2 over this thread's 8 mixtures, per frame ----
+#pragma unroll
+		for (int f = 0; f < 8; ++f) {
+			float mn = acc[f][0];
+#pragma unroll
+			for (int m = 1; m < 8; ++m) mn = fminf(mn, acc[f][m]);
+			const float m_new = fmaxf(m_run[f], -mn);
+			float sum = 0.f;
+#pragma unroll
+			for (int m = 0; m < 8; ++m) sum += ex2_approx(-acc[f][m] - m_new);
+			s_run[f] = fmaf(s_run[f], ex2_approx(m_run[f] - m_new), sum);
+			m_run[f] = m_new;
+		}
+
+		++tile_in_spk;
+		const bool spk_done = (tile_in_spk == A.tiles_per_model);
+		if (spk_done) {
+			// merge the four mixture lanes (q) of each frame group, then finish the speaker
+			double local = 0.0;
+#pragma unroll
+			for (int f = 0; f < 8; ++f) {
+				float m = m_run[f], s = s_run[f];
+#pragma unroll
+				for (int off = 1; off <= 2; off <<= 1) {
+					const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+					const float so = __shfl_xor_sync(0xffffffffu, s, off);
+					const float M = fmaxf(m, mo);
+					s = s * ex2_approx(m - M) + so * ex2_approx(mo - M);
+					m = M;
+				}
+				const float l2 = m + log2f(s);
+				float ll = l2 * LN2F;
+				if (A.clamp && !(ll >= DENORM_LOG_MIN_F)) ll = SAFE_LOG_FLOOR_F;
+				const int fr = warp * 64 + 4 * g + (f & 3) + ((f >> 2) << 5);
+				if (fr < nf) {
+					local += (double)ll;
+					if (A.frame_ll != nullptr && q == 0) A.frame_ll[(size_t)spk * A.ldf + f0 + fr] = A.frame_log2 ? l2 : ll;
+				}
+				m_run[f] = -3.0e38f;
+				s_run[f] = 0.f;
+			}
+			// sum over the 8 frame groups of the warp (lanes with equal q hold identical values)
+#pragma unroll
+			for (int off = 4; off <= 16; off <<= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+			if (lane == 0) red[(spk & 1) * 4 + warp] = local;
+		}
+		__syncthreads();   // every warp is done with this stage (and red[] is visible)
+		if (tid == 0) {
+			if (spk_done) {
+				const double *r = red + (spk & 1) * 4;
+				A.partial[(size_t)blockIdx.x * A.S + spk] = (r[0] + r[1]) + (r[2] + r[3]);
+			}
+			const int nxt = it + SC_STAGES;
+			if (nxt < n_tiles) {
+				mbar_expect_tx(&bars[stage], tile_bytes);
+				bulk_g2s(ps + (size_t)stage * tileF, gt0 + (size_t)nxt * tileF, tile_bytes, &bars[stage]);
+			}
+		}
+		if (spk_done) {
+			++spk;
+			tile_in_spk = 0;
+		}
+	}
+}
+
+// sums[u][s] = sum over the frame tiles of utterance u (deterministic order); best[u] = first argmax_s
+__global__ void score_reduce_kernel(const double *__restrict__ partial, const int *__restrict__ utt_tile_start, int S,
+                                    double *__restrict__ sums, int *__restrict__ best) {
+	const int u = blockIdx.x;
+	const int t0 = utt_tile_start[u], t1 = utt_tile_start[u + 1];
+	__shared__ double sv[256];
+	__shared__ int si[256];
+	double bestv = -1.0e300;
+	int besti = 0x7fffffff;
+	for (int s = threadIdx.x; s < S; s += blockDim.x) {
+		double acc = 0.0;
+		for (int t = t0; t < t1; ++t) acc += partial[(size_t)t * S + s];
+		sums[(size_t)u * S + s] = acc;
+		if (acc > bestv) {   // strict: keeps the first maximum within a thread's ascending s sequence
+			bestv = acc;
+			besti = s;
+		}
+	}
+	if (best == nullptr) return;
+	sv[threadIdx.x] = bestv;
+	si[threadIdx.x] = besti;
+	__syncthreads();
+	for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+		if ((int)threadIdx.x < w) {
+			const double ov = sv[threadIdx.x + w];
+			const int oi = si[threadIdx.x + w];
+			if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) {
+				sv[threadIdx.x] = ov;
+				si[threadIdx.x] = oi;
+			}
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) best[u] = si[0] == 0x7fffffff ? 0 : si[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: frame-tile tables (cached per shape), chunking, launch
+// ------------------------------------------------------------------------------------------------
+struct TileTable {
+	std::vector<int> key;            // utt_off + S
+	int n_ftiles = 0;
+	int4 *d_ftiles = nullptr;
+	int *d_utt_tile_start = nullptr;
+	double *d_partial = nullptr;
+	uint64_t stamp = 0;
+};
+static std::vector<TileTable> g_tables;
+static uint64_t g_stamp = 0;
+
+static void free_table(TileTable &t) {
+	if (t.d_ftiles) cudaFree(t.d_ftiles);
+	if (t.d_utt_tile_start) cudaFree(t.d_utt_tile_start);
+	if (t.d_partial) cudaFree(t.d_partial);
+	t = TileTable();
+}
+
+void score_tables_release() {
+	for (auto &t : g_tables) free_table(t);
+	g_tables.clear();
+}
+
+static int get_table(const int *utt_off, int n_utt, int S, cudaStream_t st, TileTable **out) {
+	std::vector<int> key(utt_off, utt_off + n_utt + 1);
+	key.push_back(S);
+	for (auto &t : g_tables)
+		if (t.key == key) {
+			t.stamp = ++g_stamp;
+			*out = &t;
+			return 0;
+		}
+	if (g_tables.size() >= 32) {   // evict least recently used
+		size_t lru = 0;
+		for (size_t i = 1; i < g_tables.size(); ++i)
+			if (g_tables[i].stamp < g_tables[lru].stamp) lru = i;
+		SRB_CUDA(cudaStreamSynchronize(st));
+		free_table(g_tables[lru]);
+		g_tables.erase(g_tables.begin() + lru);
+	}
+	std::vector<int4> ft;
+	std::vector<int> uts(n_utt + 1);
+	for (int u = 0; u < n_utt; ++u) {
+		uts[u] = (int)ft.size();
+		const int b = utt_off[u], e = utt_off[u + 1];
+		for (int f = b; f < e; f += SC_FT) ft.push_back(make_int4(f, (e - f < SC_FT ? e - f : SC_FT), u, 0));
+	}
+	uts[n_utt] = (int)ft.size();
+	TileTable t;
+	t.key = key;
+	t.n_ftiles = (int)ft.size();
+	t.stamp = ++g_stamp;
+	const size_t nft = ft.size() ? ft.size() : 1;
+	SRB_CUDA(cudaMalloc(&t.d_ftiles, nft * sizeof(int4)));
+	SRB_CUDA(cudaMalloc(&t.d_utt_tile_start, (size_t)(n_utt + 1) * sizeof(int)));
+	SRB_CUDA(cudaMalloc(&t.d_partial, nft * (size_t)S * sizeof(double)));
+	if (!ft.empty()) SRB_CUDA(cudaMemcpyAsync(t.d_ftiles, ft.data(), ft.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+	SRB_CUDA(cudaMemcpyAsync(t.d_utt_tile_start, uts.data(), uts.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+	SRB_CUDA(cudaStreamSynchronize(st));   // the source vectors die with this scope
+	g_tables.push_back(t);
+	*out = &g_tables.back();
+	return 0;
+}
+
+// choose how many speaker chunks to cut the S axis into so that (frame tiles x chunks) fills whole waves
+static int choose_spk_per_chunk(int n_ftiles, int S, int ctas_per_wave) {
+	double best_eff = -1.0;
+	int best_spc = S;
+	for (int nchunks = 1; nchunks <= S; ++nchunks) {
+		const int spc = ceil_div(S, nchunks);
+		const int real_chunks = ceil_div(S, spc);
+		if (real_chunks != nchunks) continue;
+		const long long ctas = (long long)n_ftiles * real_chunks;
+		const long long waves = ceil_div_ll(ctas, ctas_per_wave);
+		// useful work / capacity; the x-tile load is amortised over spc speakers (small penalty for tiny chunks)
+		double eff = ((double)n_ftiles * S) / ((double)waves * ctas_per_wave * spc);
+		eff *= (double)spc / ((double)spc + 0.05);
+		if (eff > best_eff + 1e-9) {
+			best_eff = eff;
+			best_spc = spc;
+		}
+	}
+	return best_spc;
+}
+
+static size_t score_smem_bytes(int D) {
+	return (size_t)D * SC_FT * 4 + (size_t)SC_STAGES * tile_floats(D) * 4 + SC_STAGES * 8 + 8 * 8;
+}
+
+static bool g_score_attr_set = false;
+
+int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums,
+                 float *d_frame_ll, int ldf, int *d_best, int clamp, int frame_log2, cudaStream_t st) {
+	SRB_REQUIRE(pm.S > 0 && pm.d_tiles != nullptr, "score: empty model set");
+	SRB_REQUIRE(D == pm.D, "score: feature dim %d != model dim %d", D, pm.D);
+	SRB_REQUIRE(D >= 1 && D <= MAX_DIM, "score: dim %d outside [1,%d]", D, MAX_DIM);
+	SRB_REQUIRE(ld >= D, "score: ld %d < dim %d", ld, D);
+	SRB_REQUIRE(n_utt >= 1, "score: no utterances");
+	for (int u = 0; u < n_utt; ++u) SRB_REQUIRE(utt_off[u + 1] >= utt_off[u], "score: utterance offsets not ascending");
+	Context &c = ctx();
+	TileTable *tt = nullptr;
+	if (get_table(utt_off, n_utt, pm.S, st, &tt)) return 1;
+	const size_t smem = score_smem_bytes(D);
+	if (!g_score_attr_set) {
+		SRB_CUDA(cudaFuncSetAttribute(gmm_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		g_score_attr_set = true;
+	}
+	if (tt->n_ftiles > 0) {
+		int per_sm = (int)((227 * 1024) / (smem + 1024));
+		if (per_sm > 3) per_sm = 3;
+		if (per_sm < 1) per_sm = 1;
+		const int spc = choose_spk_per_chunk(tt->n_ftiles, pm.S, c.sm_count * per_sm);
+		ScoreArgs a;
+		a.X = dX;
+		a.ld = ld;
+		a.D = D;
+		a.tiles = pm.d_tiles;
+		a.tiles_per_model = pm.tiles_per_model;
+		a.S = pm.S;
+		a.spk_per_chunk = spc;
+		a.ftiles = tt->d_ftiles;
+		a.frame_ll = d_frame_ll;
+		a.ldf = ldf;
+		a.partial = tt->d_partial;
+		a.clamp = clamp;
+		a.frame_log2 = frame_log2;
+		a.x_vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(dX) & 15) == 0);
+		dim3 grid(tt->n_ftiles, ceil_div(pm.S, spc));
+		gmm_score_kernel<<<grid, SC_THREADS, smem, st>>>(a);
+		SRB_CUDA(cudaGetLastError());
+	}
+	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, d_sums, d_best);
+	SRB_CUDA(cudaGetLastError());
+	return 0;
+}
+
+}  // namespace srb

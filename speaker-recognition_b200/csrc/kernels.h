@@ -1,0 +1,38 @@
+// kernels.h -- launch entry points of the CUDA translation units (internal; the public surface is include/srb200.h)
+#pragma once
+#include "gmm_model.h"
+
+namespace srb {
+
+// ---- gmm_score.cu ----
+// dX [n_total][ld] fp32 on device; utt_off[n_utt+1] HOST frame offsets; d_sums [n_utt][S] float64;
+// d_frame_ll optional [S][ldf]; d_best optional [n_utt].
+int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums,
+                 float *d_frame_ll, int ldf, int *d_best, int clamp, int frame_log2, cudaStream_t st);
+void score_tables_release();
+
+// ---- gmm_em.cu ----
+// stats (float64): [K] N_k | [K*D] sum g x | [K*D] sum g x^2 | [1] sum log p | [1] frames used
+static inline int em_stats_len(int K, int D) { return K + 2 * K * D + 2; }
+// E-step = launch_score(frame_log2 = 1) for the per-frame normaliser + this accumulation pass.
+// d_lse2 [n] per-frame log2 p(x); d_ll_sum [1] the (clamped) total log-likelihood from the scoring pass.
+int launch_estep_accumulate(const PackedModels &pm, const float *dX, int n, int ld, int D, int K, const float *d_lse2,
+                            const double *d_ll_sum, double *d_stats, int clamp, cudaStream_t st);
+int launch_mstep(double *d_params, const double *d_ubm_params, int K, int D, const double *d_stats, long long n_total,
+                 double min_covar, int mode, cudaStream_t st);
+int launch_pack_from_master(const double *d_params, int K, int D, PackedModels &pm, cudaStream_t st);
+void em_release();
+
+// ---- mfcc.cu ----
+struct MfccPlan;
+MfccPlan *mfcc_plan_create(int fs, double win_ms, double shift_ms, int nfft, int n_filters, int n_ceps, double pre_emph);
+void mfcc_plan_free(MfccPlan *p);
+int mfcc_frame_len(const MfccPlan *p);
+int mfcc_frame_shift(const MfccPlan *p);
+int mfcc_n_ceps(const MfccPlan *p);
+// d_pcm int16 or float (is_f32) on device, smp_off[n_utt+1] HOST sample offsets.  Writes features
+// [rows_total][ld] (nd in 0..2, cmvn 0/1) and the HOST row offsets feat_off[n_utt+1].
+int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp_off, int n_utt, int nd, int cmvn,
+                float *d_feat, int ld, int *feat_off, cudaStream_t st);
+
+}  // namespace srb

@@ -1,0 +1,102 @@
+"""Batched device pipeline: PCM -> MFCC(+delta, CMVN) -> score against a speaker set -> labels, for many
+utterances per call.  This is the throughput form of ModelInterface.predict (src/gui/interface.py:85-94):
+same arithmetic, but B utterances per launch sequence and every intermediate stays in HBM.
+
+PyTorch is used only as the owner of device buffers / streams (and torch.distributed for multi-GPU plumbing);
+all compute goes through the C ABI (include/srb200.h: srb200_mfcc_extract_dev, srb200_gmmset_score_dev).
+Multi-GPU: utterances are independent, so ranks simply take disjoint utterance shards -- no collective on the
+data path (SURVEY.md s8e "Predict, many utterances").
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .feature import MFCC as _MFCC
+
+
+class BatchScorer(object):
+    """gmmset: a GMMSet/GMMSetPyGMM with enrolled models.  nd: 0/1/2 delta order (feature dim = n_ceps*(nd+1))."""
+
+    KERNELS_PER_STEP = 5   # mfcc_frames, mfcc_stats, mfcc_norm, gmm_score, score_reduce
+
+    def __init__(self, gmmset, fs=16000, nd=2, device=None, **mfcc_kwargs):
+        import torch
+        self.torch = torch
+        _lib.require_gpu()
+        self.L = _lib.lib()
+        self.gmmset = gmmset
+        self.set_h = gmmset._ensure_set()
+        self.S = self.L.srb200_gmmset_size(self.set_h)
+        self.ex = _MFCC.get_mfcc_extractor(fs, **mfcc_kwargs)
+        self.nd = nd
+        self.dim = self.L.srb200_mfcc_out_dim(self.ex._h, nd)
+        if self.dim != self.L.srb200_gmmset_dim(self.set_h):
+            raise ValueError("feature dim %d != model dim %d" % (self.dim, self.L.srb200_gmmset_dim(self.set_h)))
+        self.ld = (self.dim + 3) & ~3
+        self.device = torch.device("cuda", self.L.srb200_get_device()) if device is None else device
+        self._shape = None
+
+    def _prepare(self, lengths):
+        torch = self.torch
+        key = tuple(int(x) for x in lengths)
+        if self._shape == key:
+            return
+        B = len(key)
+        off = np.zeros(B + 1, dtype=np.int64)
+        off[1:] = np.cumsum(key)
+        self.smp_off = (C.c_longlong * (B + 1))(*off.tolist())
+        self.n_samples = int(off[-1])
+        rows = self.L.srb200_mfcc_rows_total(self.ex._h, self.smp_off, B, self.nd)
+        if rows <= 0:
+            raise ValueError("an utterance is too short for MFCC extraction")
+        self.rows = int(rows)
+        self.feat_off = (C.c_int * (B + 1))()
+        self.d_pcm = torch.empty(self.n_samples, dtype=torch.int16, device=self.device)
+        self.d_feat = torch.empty((self.rows, self.ld), dtype=torch.float32, device=self.device)
+        self.d_sums = torch.empty((B, self.S), dtype=torch.float64, device=self.device)
+        self.d_best = torch.empty(B, dtype=torch.int32, device=self.device)
+        self.h_best = torch.empty(B, dtype=torch.int32).pin_memory()
+        self.B = B
+        self._shape = key
+
+    # ---- stages (each enqueues on the current torch stream) ----
+    def upload(self, pcm_host):
+        """pcm_host: pinned int16 torch tensor holding the utterances back to back"""
+        self.d_pcm.copy_(pcm_host, non_blocking=True)
+
+    def features(self):
+        st = self.torch.cuda.current_stream().cuda_stream
+        _lib.check(self.L.srb200_mfcc_extract_dev(self.ex._h, self.d_pcm.data_ptr(), self.smp_off, self.B, self.nd,
+                                                  self.d_feat.data_ptr(), self.ld, self.feat_off, st), "mfcc_extract_dev")
+
+    def score(self):
+        st = self.torch.cuda.current_stream().cuda_stream
+        _lib.check(self.L.srb200_gmmset_score_dev(self.set_h, self.d_feat.data_ptr(), self.ld, self.dim, self.feat_off, self.B,
+                                                  self.d_sums.data_ptr(), None, 0, self.d_best.data_ptr(), st), "gmmset_score_dev")
+
+    def step_device(self):
+        """one pass of the hot path with the PCM already resident in HBM"""
+        self.features()
+        self.score()
+
+    def predict_pcm(self, pcm_host, lengths):
+        """end to end: pinned host PCM in, speaker indices (host int32 tensor, pinned) out"""
+        self._prepare(lengths)
+        self.upload(pcm_host)
+        self.step_device()
+        self.h_best.copy_(self.d_best, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        return self.h_best
+
+    def predict(self, signals):
+        """convenience: list of int16 numpy signals -> list of labels"""
+        torch = self.torch
+        lengths = [len(s) for s in signals]
+        self._prepare(lengths)
+        host = torch.from_numpy(np.concatenate([np.asarray(s, dtype=np.int16) for s in signals])).pin_memory()
+        idx = self.predict_pcm(host, lengths)
+        return [self.gmmset.y[int(i)] for i in idx]
+
+    def frames_per_step(self):
+        return self.rows

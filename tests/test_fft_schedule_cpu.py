@@ -1,0 +1,36 @@
+"""The MFCC kernel's FFT schedule (csrc/fft_core.h: Stockham radix-4 passes + radix-2 tail + real-FFT unpack) is
+host/device code; replay exactly what the CUDA threads do, serially, and compare with numpy.fft (CPU only)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def emul():
+    out = os.path.join(ROOT, "tests", "_build", "fft_emul.so")
+    src = os.path.join(ROOT, "tests", "csrc", "fft_emul.cc")
+    hdr = os.path.join(ROOT, "speaker-recognition_b200", "csrc", "fft_core.h")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-O2", "-fPIC", "-shared", "-I", os.path.dirname(hdr), "-o", out, src])
+    return C.CDLL(out)
+
+
+@pytest.mark.parametrize("N", [64, 128, 256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("workers", [1, 256])
+def test_power_spectrum_matches_numpy(emul, N, workers):
+    rng = np.random.default_rng(N)
+    batch = 4
+    y = np.zeros((batch, N), np.float32)
+    y[:, : N // 4] = (rng.standard_normal((batch, N // 4)) * 3000).astype(np.float32)   # zero-padded like MFCC.py:66
+    P = np.zeros((batch, N // 2 + 1), np.float32)
+    fp = C.POINTER(C.c_float)
+    emul.emul_power_spectrum(y.ctypes.data_as(fp), N, batch, workers, P.ctypes.data_as(fp))
+    ref = np.abs(np.fft.fft(y.astype(np.float64), axis=1)[:, : N // 2 + 1]) ** 2
+    assert np.max(np.abs(P - ref) / ref.max(axis=1, keepdims=True)) < 2e-6
