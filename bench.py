@@ -65,11 +65,16 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
+
+    def wait_started(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
 
     def stop(self):
         if self.proc is not None:
@@ -79,9 +84,12 @@ class ClockSampler(threading.Thread):
                 pass
         self.join(timeout=2)
 
-    def summary(self):
+    def summary(self, windows):
+        """only samples taken inside the timed windows [(t0, t1), ...] (host clock) count"""
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if not any(a <= ts <= b for a, b in windows):
+                continue
             try:
                 sm.append(float(r[1]))
                 smax.append(float(r[2]))
@@ -153,7 +161,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--utts", type=int, default=64, help="utterances per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -213,6 +221,9 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_started()
+    barrier()
+    w0 = time.perf_counter()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     f_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -226,6 +237,7 @@ def main():
         k_ev[i][1].record()
     ev[1].record()
     barrier()
+    w1 = time.perf_counter()
     dev_ms = ev[0].elapsed_time(ev[1])
     score_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
     feat_ms = float(np.mean([a.elapsed_time(b) for a, b in f_ev]))
@@ -235,15 +247,18 @@ def main():
     for _ in range(2):
         bs.predict_pcm(host, lengths)
     barrier()
+    w2 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         lab = bs.predict_pcm(host, lengths)
     e1.record()
     barrier()
+    w3 = time.perf_counter()
     e2e_ms = e0.elapsed_time(e1)
+    time.sleep(0.12)
     sampler.stop()
-    clocks = sampler.summary()
+    clocks = sampler.summary([(w0, w1 + 0.06), (w2, w3 + 0.06)])
     assert np.array_equal(lab.numpy(), labels_dev)
 
     t = torch.tensor([dev_ms, e2e_ms, score_ms, feat_ms], dtype=torch.float64, device="cuda")

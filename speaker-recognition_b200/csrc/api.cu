@@ -112,9 +112,9 @@ void pack_models_host(int S, int K, int D, const double *const *weights, const d
 				double c = weights[s][r] > 0.0 ? log2(weights[s][r]) : -1.0e30;
 				for (int d = 0; d < D; ++d) {
 					const double a = A0 / sg[d];
-					float *t = tile + (size_t)d * 64 + (m >> 1) * 4 + (m & 1) * 2;
+					float *t = tile + (size_t)d * 64 + (m >> 1) * 4 + (m & 1);   // chunk = [a0, a1, nb0, nb1]
 					t[0] = (float)a;
-					t[1] = (float)(-mu[d] * a);
+					t[2] = (float)(-mu[d] * a);
 					c -= log2(2.5066282746310002 * sg[d]);   // SQRT_2_PI, gmm.cc:22
 				}
 				c2 = (c < -1.0e30 || c != c) ? PAD_C2 : (float)c;

@@ -20,16 +20,15 @@ __global__ void __launch_bounds__(256) fma_loop(float *out, int iters, float a, 
 				for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
 		}
 	} else if (VARIANT == 1) {
-		float x[4] = {a, a + 1.f, a + 2.f, a + 3.f};
+		// x changes every repetition (it depends on the accumulators), so t cannot be hoisted out of the loop
 		for (int it = 0; it < iters; ++it) {
 #pragma unroll
 			for (int r = 0; r < 4; ++r)
 #pragma unroll
 				for (int i = 0; i < 16; ++i) {
-					const float t = fmaf(x[i & 3], a, b);
+					const float t = fmaf(acc[(i + 5) & 15], a, b);
 					acc[i] = fmaf(t, t, acc[i]);
 				}
-			x[0] += 1e-9f;
 		}
 	} else {
 		unsigned long long p[8], pa, pb;

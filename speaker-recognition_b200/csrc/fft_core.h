@@ -104,4 +104,100 @@ SRB_HD void power_unpack(const cpx *Z, float *P, int M, int batch, int p_stride,
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident building blocks of the fast MFCC path (M = 1024, at most 256 non-zero packed inputs):
+// the zero-padded 1024-point transform splits exactly into four 256-point transforms of pre-twiddled inputs,
+//     Z[4q + r] = sum_{n<256} (z[n] W_1024^{n r}) W_256^{n q},        r = 0..3, q = 0..255,
+// and each 256-point transform is two radix-16 steps held in registers (16 threads x 16 points) with one
+// transpose through shared memory in between.
+// ------------------------------------------------------------------------------------------------
+
+// forward 4-point DFT, outputs in natural order
+SRB_HD void dft4(cpx &a, cpx &b, cpx &c, cpx &d) {
+	const cpx apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d);
+	const cpx jbmd = cmulj_neg(csub(b, d));      // -i (b - d)
+	a = cadd(apc, bpd);
+	b = cadd(amc, jbmd);
+	c = csub(apc, bpd);
+	d = csub(amc, jbmd);
+}
+
+// forward 16-point DFT of v[0..15] into o[0..15] (natural order).  n = 4 n1 + n0, k = 4 k1 + k0:
+//   X[4k1 + k0] = sum_{n0} W4^{n0 k1} [ W16^{n0 k0} sum_{n1} x[4 n1 + n0] W4^{n1 k0} ]
+SRB_HD void dft16(const cpx *v, cpx *o) {
+	const float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f, R2 = 0.70710678118654752440f;
+	cpx t[4][4];   // t[n0][k0]
+#pragma unroll
+	for (int n0 = 0; n0 < 4; ++n0) {
+		cpx a = v[n0], b = v[n0 + 4], c = v[n0 + 8], d = v[n0 + 12];
+		dft4(a, b, c, d);
+		t[n0][0] = a;
+		t[n0][1] = b;
+		t[n0][2] = c;
+		t[n0][3] = d;
+	}
+	// twiddles W16^{n0 k0}: exponents 1,2,3 | 2,4,6 | 3,6,9
+	t[1][1] = cmul(t[1][1], cpx{C1, -S1});
+	t[1][2] = cmul(t[1][2], cpx{R2, -R2});
+	t[1][3] = cmul(t[1][3], cpx{S1, -C1});
+	t[2][1] = cmul(t[2][1], cpx{R2, -R2});
+	t[2][2] = cmulj_neg(t[2][2]);
+	t[2][3] = cmul(t[2][3], cpx{-R2, -R2});
+	t[3][1] = cmul(t[3][1], cpx{S1, -C1});
+	t[3][2] = cmul(t[3][2], cpx{-R2, -R2});
+	t[3][3] = cmul(t[3][3], cpx{-C1, S1});
+#pragma unroll
+	for (int k0 = 0; k0 < 4; ++k0) {
+		cpx a = t[0][k0], b = t[1][k0], c = t[2][k0], d = t[3][k0];
+		dft4(a, b, c, d);        // over n0 -> k1 = 0..3
+		o[0 + k0] = a;
+		o[4 + k0] = b;
+		o[8 + k0] = c;
+		o[12 + k0] = d;
+	}
+}
+
+constexpr int FAST_TSTRIDE = 17;        // padded row of the 16x16 transpose tile (complex elements)
+constexpr int FAST_PSTRIDE = 257;       // P'[r][q] rows: k = 4q + r, q <= 256 only for r == 0
+
+// step A of the 256-point sub-transform owned by (r, u): inputs z[u + 16 n2] (packed complex frame, zero for
+// n >= 256 by construction), first twiddle tw1[r][n] = W_1024^{n r}, radix-16 over n2, second twiddle
+// twA[q2][u] = W_256^{u q2}, result into the transpose tile T[u][q2].
+SRB_HD void fast_step_a(const cpx *z, const cpx *tw1, const cpx *twA, cpx *T, int r, int u) {
+	cpx in[16], out[16];
+#pragma unroll
+	for (int n2 = 0; n2 < 16; ++n2) {
+		const int n = u + 16 * n2;
+		const cpx zz = z[n];
+		in[n2] = (r == 0) ? zz : cmul(zz, tw1[(r - 1) * 256 + n]);
+	}
+	dft16(in, out);
+#pragma unroll
+	for (int q2 = 0; q2 < 16; ++q2) T[u * FAST_TSTRIDE + q2] = cmul(out[q2], twA[q2 * 16 + u]);
+}
+
+// step B: radix-16 over n1 of T[n1][u] -> Y_r[16 q1 + u], stored as Zs[r][16 q1 + u]
+SRB_HD void fast_step_b(const cpx *T, cpx *Zr, int u) {
+	cpx in[16], out[16];
+#pragma unroll
+	for (int n1 = 0; n1 < 16; ++n1) in[n1] = T[n1 * FAST_TSTRIDE + u];
+	dft16(in, out);
+#pragma unroll
+	for (int q1 = 0; q1 < 16; ++q1) Zr[16 * q1 + u] = out[q1];
+}
+
+// power spectrum of the real 2048-point transform from Zs[r][q] (Z[4q + r]); output permuted P'[r*257 + q]
+SRB_HD void fast_power_unpack(const cpx *Zs, float *Pp, const cpx *tw2, int worker, int n_workers) {
+	for (int k = worker; k <= 1024; k += n_workers) {
+		const int km = (1024 - k) & 1023;
+		const cpx zk = Zs[(k & 3) * 256 + ((k >> 2) & 255)];
+		cpx zc = Zs[(km & 3) * 256 + (km >> 2)];
+		zc.y = -zc.y;
+		const cpx e = cadd(zk, zc), o = csub(zk, zc);
+		const cpx wo = cmul(tw2[k], o);
+		const float yr = 0.5f * (e.x + wo.y), yi = 0.5f * (e.y - wo.x);
+		Pp[(k & 3) * FAST_PSTRIDE + (k >> 2)] = yr * yr + yi * yi;
+	}
+}
+
 }  // namespace srbfft

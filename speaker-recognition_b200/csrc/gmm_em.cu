@@ -154,10 +154,10 @@ __global__ void __launch_bounds__(EM_THREADS, 2) em_accumulate_kernel(const EmAr
 				for (int j = 0; j < 4; ++j) {
 					const float4 p = *reinterpret_cast<const float4 *>(pq + d * 64 + 16 * j);
 #pragma unroll
-					for (int f = 0; f < 8; ++f) {
-						const float t0 = fmaf(xv[f], p.x, p.y);
+					for (int f = 0; f < 8; ++f) {   // chunk = [a0, a1, nb0, nb1]
+						const float t0 = fmaf(xv[f], p.x, p.z);
 						a8[f][2 * j] = fmaf(t0, t0, a8[f][2 * j]);
-						const float t1 = fmaf(xv[f], p.z, p.w);
+						const float t1 = fmaf(xv[f], p.y, p.w);
 						a8[f][2 * j + 1] = fmaf(t1, t1, a8[f][2 * j + 1]);
 					}
 				}
@@ -343,9 +343,9 @@ __global__ void em_pack_kernel(const double *__restrict__ params, int K, int D, 
 			a = (float)ad;
 			nb = (float)(-mu * ad);
 		}
-		float *t = tiles + (size_t)tile * tileF + (size_t)d * 64 + (m >> 1) * 4 + (m & 1) * 2;
+		float *t = tiles + (size_t)tile * tileF + (size_t)d * 64 + (m >> 1) * 4 + (m & 1);   // chunk = [a0, a1, nb0, nb1]
 		t[0] = a;
-		t[1] = nb;
+		t[2] = nb;
 	}
 	if (idx < Kpad) {
 		const int r = idx, tile = r >> 5, m = r & 31;

@@ -7,7 +7,8 @@
 //
 //   mixture row r = s * Kpad + k            (speaker-major, K padded to a multiple of 32 rows)
 //   tile  = 32 consecutive rows             (never straddles a speaker)
-//   per tile, contiguous in HBM:  [D][16 chunks][a_{2c}, nb_{2c}, a_{2c+1}, nb_{2c+1}]  then  c2[32]
+//   per tile, contiguous in HBM:  [D][16 chunks][a_{2c}, a_{2c+1}, nb_{2c}, nb_{2c+1}]  then  c2[32]
+//       (one LDS.128 per chunk = the two 64-bit operand pairs of a packed fma.rn.f32x2)
 //       a   = sqrt(log2(e)/2) / sigma              (so that t = x*a + nb, t*t is the exponent in log2 units)
 //       nb  = -mean * a
 //       c2  = log2(w) - sum_d log2(sqrt(2 pi) sigma_d)      (padded rows: a = nb = 0, c2 = -1e30)

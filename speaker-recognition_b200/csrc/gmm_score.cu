@@ -21,8 +21,7 @@
 
 namespace srb {
 
-constexpr int SC_THREADS = 128;
-constexpr int SC_FT = 256;          // frames per CTA tile
+constexpr int SC_MAX_WARPS = 8;     // CTA = 4 warps x 64 frames (3 CTAs/SM) or 8 warps x 64 frames (2 CTAs/SM, <=128 registers)
 constexpr int SC_STAGES = 3;
 constexpr float LN2F = 0.69314718055994531f;
 constexpr float DENORM_LOG_MIN_F = -744.4400719213812f;   // log(4.94e-324): the reference's linear-domain sum is 0 below this
@@ -42,14 +41,34 @@ struct ScoreArgs {
 	int x_vec_ok;              // X rows are 16-B aligned and ld % 4 == 0
 };
 
-__global__ void __launch_bounds__(SC_THREADS, 3) gmm_score_kernel(const ScoreArgs A) {
+// packed fp32x2 FMA (SASS FFMA2, sm_100+): two lanes per instruction.  The scorer is issue-bound with scalar FFMA
+// (ncu r1: issue slots 88 % busy, FMA pipe 76 %); FFMA2 halves the FMA instruction count so that the LDS / MUFU /
+// ALU instructions of the loop and of the log-sum-exp epilogue no longer take issue slots away from the FMA pipe.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+	unsigned long long d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+
+template <bool PACKED, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kernel(const ScoreArgs A) {
+	constexpr int SC_THREADS = WARPS * 32;
+	constexpr int SC_FT = WARPS * 64;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int D = A.D;
 	const int tileF = 64 * D + 32;
 	float *xs = reinterpret_cast<float *>(smem_raw);                  // [D][256]
 	float *ps = xs + (size_t)D * SC_FT;                               // [STAGES][tileF]
 	uint64_t *bars = reinterpret_cast<uint64_t *>(ps + (size_t)SC_STAGES * tileF);
-	double *red = reinterpret_cast<double *>(bars + SC_STAGES);       // [2][4]
+	double *red = reinterpret_cast<double *>(bars + SC_STAGES);       // [2][WARPS]
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int g = lane >> 2, q = lane & 3;
@@ -114,8 +133,40 @@ __global__ void __launch_bounds__(SC_THREADS, 3) gmm_score_kernel(const ScoreArg
 		const float *pt = ps + (size_t)stage * tileF;
 
 		float acc[8][8];
-		{
-			const float *cp = pt + 64 * D;
+		const float *cp = pt + 64 * D;
+		const float *pq = pt + 4 * q;
+		if (PACKED) {
+			// acc2[f][j] = {acc of mixture 2(4j+q), acc of mixture 2(4j+q)+1}
+			unsigned long long acc2[8][4];
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const float2 c = *reinterpret_cast<const float2 *>(cp + 2 * (4 * j + q));
+				const unsigned long long c2 = pack2(-c.x, -c.y);
+#pragma unroll
+				for (int f = 0; f < 8; ++f) acc2[f][j] = c2;
+			}
+#pragma unroll 2
+			for (int d = 0; d < D; ++d) {
+				const float4 xa = *reinterpret_cast<const float4 *>(xbase + d * SC_FT);
+				const float4 xb = *reinterpret_cast<const float4 *>(xbase + d * SC_FT + 32);
+				const unsigned long long x2[8] = {pack2(xa.x, xa.x), pack2(xa.y, xa.y), pack2(xa.z, xa.z), pack2(xa.w, xa.w),
+				                                  pack2(xb.x, xb.x), pack2(xb.y, xb.y), pack2(xb.z, xb.z), pack2(xb.w, xb.w)};
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					// {a_2c, a_2c+1} and {nb_2c, nb_2c+1} arrive as two aligned 64-bit halves of one LDS.128
+					const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(pq + d * 64 + 16 * j);
+#pragma unroll
+					for (int f = 0; f < 8; ++f) {
+						const unsigned long long t2 = fma2(x2[f], p.x, p.y);
+						acc2[f][j] = fma2(t2, t2, acc2[f][j]);
+					}
+				}
+			}
+#pragma unroll
+			for (int f = 0; f < 8; ++f)
+#pragma unroll
+				for (int j = 0; j < 4; ++j) unpack2(acc2[f][j], acc[f][2 * j], acc[f][2 * j + 1]);
+		} else {
 #pragma unroll
 			for (int j = 0; j < 4; ++j) {
 				const float2 c = *reinterpret_cast<const float2 *>(cp + 2 * (4 * j + q));
@@ -125,22 +176,21 @@ __global__ void __launch_bounds__(SC_THREADS, 3) gmm_score_kernel(const ScoreArg
 					acc[f][2 * j + 1] = -c.y;
 				}
 			}
-		}
-		const float *pq = pt + 4 * q;
 #pragma unroll 2
-		for (int d = 0; d < D; ++d) {
-			const float4 xa = *reinterpret_cast<const float4 *>(xbase + d * SC_FT);
-			const float4 xb = *reinterpret_cast<const float4 *>(xbase + d * SC_FT + 32);
-			const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+			for (int d = 0; d < D; ++d) {
+				const float4 xa = *reinterpret_cast<const float4 *>(xbase + d * SC_FT);
+				const float4 xb = *reinterpret_cast<const float4 *>(xbase + d * SC_FT + 32);
+				const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				const float4 p = *reinterpret_cast<const float4 *>(pq + d * 64 + 16 * j);
+				for (int j = 0; j < 4; ++j) {
+					const float4 p = *reinterpret_cast<const float4 *>(pq + d * 64 + 16 * j);   // a0 a1 nb0 nb1
 #pragma unroll
-				for (int f = 0; f < 8; ++f) {
-					const float t0 = fmaf(xv[f], p.x, p.y);
-					acc[f][2 * j] = fmaf(t0, t0, acc[f][2 * j]);
-					const float t1 = fmaf(xv[f], p.z, p.w);
-					acc[f][2 * j + 1] = fmaf(t1, t1, acc[f][2 * j + 1]);
+					for (int f = 0; f < 8; ++f) {
+						const float t0 = fmaf(xv[f], p.x, p.z);
+						acc[f][2 * j] = fmaf(t0, t0, acc[f][2 * j]);
+						const float t1 = fmaf(xv[f], p.y, p.w);
+						acc[f][2 * j + 1] = fmaf(t1, t1, acc[f][2 * j + 1]);
+					}
 				}
 			}
 		}
@@ -188,13 +238,16 @@ __global__ void __launch_bounds__(SC_THREADS, 3) gmm_score_kernel(const ScoreArg
 			// sum over the 8 frame groups of the warp (lanes with equal q hold identical values)
 #pragma unroll
 			for (int off = 4; off <= 16; off <<= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-			if (lane == 0) red[(spk & 1) * 4 + warp] = local;
+			if (lane == 0) red[(spk & 1) * WARPS + warp] = local;
 		}
 		__syncthreads();   // every warp is done with this stage (and red[] is visible)
 		if (tid == 0) {
 			if (spk_done) {
-				const double *r = red + (spk & 1) * 4;
-				A.partial[(size_t)blockIdx.x * A.S + spk] = (r[0] + r[1]) + (r[2] + r[3]);
+				const double *r = red + (spk & 1) * WARPS;
+				double tot = 0.0;
+#pragma unroll
+				for (int w = 0; w < WARPS; ++w) tot += r[w];
+				A.partial[(size_t)blockIdx.x * A.S + spk] = tot;
 			}
 			const int nxt = it + SC_STAGES;
 			if (nxt < n_tiles) {
@@ -271,9 +324,10 @@ void score_tables_release() {
 	g_tables.clear();
 }
 
-static int get_table(const int *utt_off, int n_utt, int S, cudaStream_t st, TileTable **out) {
+static int get_table(const int *utt_off, int n_utt, int S, int FT, cudaStream_t st, TileTable **out) {
 	std::vector<int> key(utt_off, utt_off + n_utt + 1);
 	key.push_back(S);
+	key.push_back(FT);
 	for (auto &t : g_tables)
 		if (t.key == key) {
 			t.stamp = ++g_stamp;
@@ -293,7 +347,7 @@ static int get_table(const int *utt_off, int n_utt, int S, cudaStream_t st, Tile
 	for (int u = 0; u < n_utt; ++u) {
 		uts[u] = (int)ft.size();
 		const int b = utt_off[u], e = utt_off[u + 1];
-		for (int f = b; f < e; f += SC_FT) ft.push_back(make_int4(f, (e - f < SC_FT ? e - f : SC_FT), u, 0));
+		for (int f = b; f < e; f += FT) ft.push_back(make_int4(f, (e - f < FT ? e - f : FT), u, 0));
 	}
 	uts[n_utt] = (int)ft.size();
 	TileTable t;
@@ -333,11 +387,13 @@ static int choose_spk_per_chunk(int n_ftiles, int S, int ctas_per_wave) {
 	return best_spc;
 }
 
-static size_t score_smem_bytes(int D) {
-	return (size_t)D * SC_FT * 4 + (size_t)SC_STAGES * tile_floats(D) * 4 + SC_STAGES * 8 + 8 * 8;
+static size_t score_smem_bytes(int D, int FT) {
+	return (size_t)D * FT * 4 + (size_t)SC_STAGES * tile_floats(D) * 4 + SC_STAGES * 8 + 2 * SC_MAX_WARPS * 8;
 }
 
 static bool g_score_attr_set = false;
+static bool g_score_scalar = false;
+static int g_score_warps = 4;
 
 int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums,
                  float *d_frame_ll, int ldf, int *d_best, int clamp, int frame_log2, cudaStream_t st) {
@@ -348,16 +404,26 @@ int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const i
 	SRB_REQUIRE(n_utt >= 1, "score: no utterances");
 	for (int u = 0; u < n_utt; ++u) SRB_REQUIRE(utt_off[u + 1] >= utt_off[u], "score: utterance offsets not ascending");
 	Context &c = ctx();
-	TileTable *tt = nullptr;
-	if (get_table(utt_off, n_utt, pm.S, st, &tt)) return 1;
-	const size_t smem = score_smem_bytes(D);
 	if (!g_score_attr_set) {
-		SRB_CUDA(cudaFuncSetAttribute(gmm_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(gmm_score_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(gmm_score_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(gmm_score_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		const char *ev = getenv("SRB200_SCORE_SCALAR");     // A/B switches for profiling
+		g_score_scalar = ev && ev[0] == '1';
+		const char *ew = getenv("SRB200_SCORE_WARPS");
+		if (ew && ew[0] == '8') g_score_warps = 8;
+		if (ew && ew[0] == '4') g_score_warps = 4;
 		g_score_attr_set = true;
 	}
+	int warps = g_score_scalar ? 4 : g_score_warps;
+	if (score_smem_bytes(D, warps * 64) > 113 * 1024) warps = 4;   // 8-warp CTAs need two per SM
+	const int FT = warps * 64;
+	TileTable *tt = nullptr;
+	if (get_table(utt_off, n_utt, pm.S, FT, st, &tt)) return 1;
+	const size_t smem = score_smem_bytes(D, FT);
 	if (tt->n_ftiles > 0) {
 		int per_sm = (int)((227 * 1024) / (smem + 1024));
-		if (per_sm > 3) per_sm = 3;
+		if (per_sm > (warps == 4 ? 3 : 2)) per_sm = (warps == 4 ? 3 : 2);
 		if (per_sm < 1) per_sm = 1;
 		const int spc = choose_spk_per_chunk(tt->n_ftiles, pm.S, c.sm_count * per_sm);
 		ScoreArgs a;
@@ -376,7 +442,9 @@ int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const i
 		a.frame_log2 = frame_log2;
 		a.x_vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(dX) & 15) == 0);
 		dim3 grid(tt->n_ftiles, ceil_div(pm.S, spc));
-		gmm_score_kernel<<<grid, SC_THREADS, smem, st>>>(a);
+		if (g_score_scalar) gmm_score_kernel<false, 4><<<grid, 128, smem, st>>>(a);
+		else if (warps == 8) gmm_score_kernel<true, 8><<<grid, 256, smem, st>>>(a);
+		else gmm_score_kernel<true, 4><<<grid, 128, smem, st>>>(a);
 		SRB_CUDA(cudaGetLastError());
 	}
 	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, d_sums, d_best);

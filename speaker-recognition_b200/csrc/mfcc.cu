@@ -45,6 +45,11 @@ struct MfccPlan {
 	cpx *d_tw = nullptr, *d_tw2 = nullptr;
 	int *d_mel_ptr = nullptr, *d_mel_col = nullptr;
 	double *d_dct = nullptr;
+	// fast path (M == 1024, frame length <= 512): register-resident 4 x 256-point transforms
+	bool fast = false;
+	cpx *d_tw1 = nullptr, *d_twA = nullptr;
+	int *d_mel_colp = nullptr;
+	size_t smem_fast = 0;
 	std::vector<MfccShape> shapes;
 	uint64_t stamp = 0;
 };
@@ -63,6 +68,8 @@ struct MfccArgs {
 	const double *dct;
 	float *ceps;
 	double *partials;
+	const cpx *tw1, *twA;      // fast path tables
+	const int *mel_colp;       // mel columns permuted to the fast path's P'[r*257 + q] layout
 };
 
 __device__ __forceinline__ int find_segment(const int *__restrict__ start, int n, int x) {
@@ -180,6 +187,115 @@ __global__ void __launch_bounds__(MF_THREADS) mfcc_frames_kernel(const MfccArgs 
 		double s = 0.0, ss = 0.0;
 		for (int f = 0; f < nfr; ++f) {
 			const double c = (double)cep[f * nc + tid];
+			s += c;
+			ss = fma(c, c, ss);
+		}
+		A.partials[(size_t)blockIdx.x * 2 * nc + tid] = s;
+		A.partials[(size_t)blockIdx.x * 2 * nc + nc + tid] = ss;
+	}
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: FFT_SIZE = 2048 (M = 1024) and frame length <= 512, i.e. at most 256 non-zero packed inputs -- the
+// reference's default geometry at 16 kHz and 8 kHz.  The zero-padded transform is four 256-point transforms of
+// pre-twiddled inputs, each done by 16 threads x 16 points in registers (fft_core.h: fast_step_a/b), so a frame costs
+// two shared-memory round trips instead of five radix-4 passes, the pruned first pass disappears, and the mel sums are
+// computed by 8-lane groups.  CTA = 256 threads = 4 frames x (4 sub-transforms x 16 lanes).
+// ------------------------------------------------------------------------------------------------
+constexpr int MFF_NF = 4;
+constexpr int MFF_YLEN = 512;
+
+__global__ void __launch_bounds__(MF_THREADS, 2) mfcc_frames_fast_kernel(const MfccArgs A) {
+	extern __shared__ __align__(16) unsigned char mf_smem[];
+	const int tid = threadIdx.x;
+	const int L = A.L, nb = A.nb, nc = A.nc;
+	cpx *T = reinterpret_cast<cpx *>(mf_smem);                                   // [NF][4][16*17]   (later P'[NF][4*257] floats)
+	cpx *Zs = T + MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE;                        // [NF][4][256]
+	float *ybuf = reinterpret_cast<float *>(Zs + MFF_NF * 4 * 256);              // [NF][512]        (later logE / cep)
+	float *sbuf = ybuf + MFF_NF * MFF_YLEN;                                      // [(NF-1)*shift + L]
+
+	const int u_ = find_segment(A.cta_start, A.n_utt, blockIdx.x);
+	const int fbase = __ldg(A.frame_off + u_);
+	const int T_u = __ldg(A.frame_off + u_ + 1) - fbase;
+	const int fr0 = (blockIdx.x - __ldg(A.cta_start + u_)) * MFF_NF;
+	const int nfr = min(MFF_NF, T_u - fr0);
+	const long long s0 = A.smp_off[u_] + (long long)fr0 * A.shift;
+	const int span = (nfr - 1) * A.shift + L;
+
+	if (A.is_f32) {
+		const float *p = reinterpret_cast<const float *>(A.pcm) + s0;
+		for (int i = tid; i < span; i += MF_THREADS) sbuf[i] = __ldg(p + i);
+	} else {
+		const int16_t *p = reinterpret_cast<const int16_t *>(A.pcm) + s0;
+		for (int i = tid; i < span; i += MF_THREADS) sbuf[i] = (float)__ldg(p + i);
+	}
+	__syncthreads();
+	// window then pre-emphasis (MFCC.py:61-64) into ybuf; zeros beyond the frame and for absent frames
+	for (int t = tid; t < MFF_NF * MFF_YLEN; t += MF_THREADS) {
+		const int f = t >> 9, i = t & (MFF_YLEN - 1);
+		float y = 0.f;
+		if (f < nfr && i < L) {
+			const float *s = sbuf + f * A.shift;
+			y = __ldg(A.win + i) * s[i];
+			if (i > 0) y = fmaf(-__ldg(A.win2 + i), s[i - 1], y);
+		}
+		ybuf[t] = y;
+	}
+	__syncthreads();
+	const int f = tid >> 6, r = (tid >> 4) & 3, u = tid & 15;
+	cpx *Tfr = T + (f * 4 + r) * 16 * srbfft::FAST_TSTRIDE;
+	srbfft::fast_step_a(reinterpret_cast<const cpx *>(ybuf + f * MFF_YLEN), A.tw1, A.twA, Tfr, r, u);
+	__syncthreads();
+	srbfft::fast_step_b(Tfr, Zs + (f * 4 + r) * 256, u);
+	__syncthreads();
+	float *Pp = reinterpret_cast<float *>(T);                                    // [NF][4*257]
+	constexpr int PSTR = 4 * srbfft::FAST_PSTRIDE;
+	srbfft::fast_power_unpack(Zs + f * 4 * 256, Pp + f * PSTR, A.tw2, tid & 63, 64);
+	__syncthreads();
+
+	// mel + log: one 8-lane group per (frame, band), lanes stride the band's non-zeros, shuffle-reduce (deterministic)
+	float *logE = ybuf;                                                          // [NF][nb]
+	{
+		const int group = tid >> 3, l8 = tid & 7;
+		const int items = MFF_NF * nb;
+		for (int it = 0; it * 32 < items; ++it) {
+			const int item = it * 32 + group;
+			const bool valid = item < items;
+			const int ff = valid ? item / nb : 0, b = valid ? item - ff * nb : 0;
+			float e = 0.f;
+			if (valid) {
+				const float *Pf = Pp + ff * PSTR;
+				const int j1 = __ldg(A.mel_ptr + b + 1);
+				for (int j = __ldg(A.mel_ptr + b) + l8; j < j1; j += 8) e = fmaf(__ldg(A.mel_val + j), Pf[__ldg(A.mel_colp + j)], e);
+			}
+			e += __shfl_xor_sync(0xffffffffu, e, 4);
+			e += __shfl_xor_sync(0xffffffffu, e, 2);
+			e += __shfl_xor_sync(0xffffffffu, e, 1);
+			if (valid && l8 == 0) logE[item] = e > 0.f ? logf(e) : __ldg(A.logfloor + b);
+		}
+	}
+	__syncthreads();
+	float *cep = logE + MFF_NF * nb;                                             // [NF][nc]
+	for (int t = tid; t < MFF_NF * nc; t += MF_THREADS) {
+		const int ff = t / nc, i = t - ff * nc;
+		const double *dr = A.dct + (size_t)i * nb;
+		const float *le = logE + ff * nb;
+		double acc = 0.0;
+		for (int b = 0; b < nb; ++b) acc = fma(__ldg(dr + b), (double)le[b], acc);
+		const float c = (float)acc;
+		cep[t] = c;
+		if (ff < nfr) A.ceps[(size_t)(fbase + fr0 + ff) * A.CL + i] = c;
+	}
+	for (int t = tid; t < MFF_NF * (A.CL - nc); t += MF_THREADS) {
+		const int ff = t / (A.CL - nc), i = nc + t - ff * (A.CL - nc);
+		if (ff < nfr) A.ceps[(size_t)(fbase + fr0 + ff) * A.CL + i] = 0.f;
+	}
+	__syncthreads();
+	if (tid < nc) {
+		double s = 0.0, ss = 0.0;
+		for (int ff = 0; ff < nfr; ++ff) {
+			const double c = (double)cep[ff * nc + tid];
 			s += c;
 			ss = fma(c, c, ss);
 		}
@@ -330,6 +446,17 @@ static int build_tables(MfccPlan *p) {
 	std::vector<cpx> tw(M), tw2(M + 1);
 	for (int j = 0; j < M; ++j) tw[j] = cpx{(float)cos(-2.0 * M_PI * j / M), (float)sin(-2.0 * M_PI * j / M)};
 	for (int k = 0; k <= M; ++k) tw2[k] = cpx{(float)cos(-2.0 * M_PI * k / N), (float)sin(-2.0 * M_PI * k / N)};
+	if (p->fast) {
+		std::vector<cpx> tw1(3 * 256), twA(256);
+		for (int r = 1; r < 4; ++r)
+			for (int n = 0; n < 256; ++n)
+				tw1[(r - 1) * 256 + n] = cpx{(float)cos(-2.0 * M_PI * n * r / 1024), (float)sin(-2.0 * M_PI * n * r / 1024)};
+		for (int q2 = 0; q2 < 16; ++q2)
+			for (int u = 0; u < 16; ++u) twA[q2 * 16 + u] = cpx{(float)cos(-2.0 * M_PI * u * q2 / 256), (float)sin(-2.0 * M_PI * u * q2 / 256)};
+		std::vector<int> colp(col.size());
+		for (size_t j = 0; j < col.size(); ++j) colp[j] = (col[j] & 3) * srbfft::FAST_PSTRIDE + (col[j] >> 2);
+		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_colp, colp)) return 1;
+	}
 	if (to_device(&p->d_win, win) || to_device(&p->d_win2, win2) || to_device(&p->d_mel_ptr, ptr) ||
 	    to_device(&p->d_mel_col, col) || to_device(&p->d_mel_val, val) || to_device(&p->d_logfloor, logfloor) ||
 	    to_device(&p->d_dct, dct) || to_device(&p->d_tw, tw) || to_device(&p->d_tw2, tw2))
@@ -361,7 +488,8 @@ MfccPlan *mfcc_plan_create(int fs, double win_ms, double shift_ms, int nfft, int
 		delete p;
 		return nullptr;
 	}
-	p->NF = std::max(1, std::min(16, 4096 / p->M));
+	p->fast = (p->M == 1024 && p->L <= MFF_YLEN && n_filters + n_ceps <= MFF_YLEN);
+	p->NF = p->fast ? MFF_NF : std::max(1, std::min(16, 4096 / p->M));
 	// the log/cepstra scratch reuses one FFT buffer: NF*(nb+nc) floats must fit in NF*M*2 floats
 	if ((p->nb + p->nc) > 2 * p->M) {
 		set_error("mfcc: FFT_SIZE %d too small for %d filters", nfft, n_filters);
@@ -369,7 +497,9 @@ MfccPlan *mfcc_plan_create(int fs, double win_ms, double shift_ms, int nfft, int
 		return nullptr;
 	}
 	p->smem = (size_t)2 * p->NF * p->M * sizeof(cpx) + ((size_t)(p->NF - 1) * p->shift + p->L) * sizeof(float);
-	if (p->smem > 200 * 1024) {
+	p->smem_fast = (size_t)MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE * sizeof(cpx) + (size_t)MFF_NF * 4 * 256 * sizeof(cpx) +
+	               (size_t)MFF_NF * MFF_YLEN * sizeof(float) + ((size_t)(MFF_NF - 1) * p->shift + p->L) * sizeof(float);
+	if (p->smem > 200 * 1024 || (p->fast && p->smem_fast > 110 * 1024)) {
 		set_error("mfcc: frame shift %d too large for the shared-memory staging", p->shift);
 		delete p;
 		return nullptr;
@@ -378,7 +508,8 @@ MfccPlan *mfcc_plan_create(int fs, double win_ms, double shift_ms, int nfft, int
 		mfcc_plan_free(p);
 		return nullptr;
 	}
-	if (cudaFuncSetAttribute(mfcc_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+	if (cudaFuncSetAttribute(mfcc_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+	    cudaFuncSetAttribute(mfcc_frames_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
 		set_error("mfcc: cudaFuncSetAttribute failed");
 		mfcc_plan_free(p);
 		return nullptr;
@@ -409,6 +540,9 @@ void mfcc_plan_free(MfccPlan *p) {
 	cudaFree(p->d_mel_ptr);
 	cudaFree(p->d_mel_col);
 	cudaFree(p->d_dct);
+	cudaFree(p->d_tw1);
+	cudaFree(p->d_twA);
+	cudaFree(p->d_mel_colp);
 	delete p;
 }
 
@@ -507,7 +641,12 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.dct = p->d_dct;
 	a.ceps = s->d_ceps;
 	a.partials = s->d_partials;
-	mfcc_frames_kernel<<<s->n_cta, MF_THREADS, p->smem, st>>>(a);
+	a.tw1 = p->d_tw1;
+	a.twA = p->d_twA;
+	a.mel_colp = p->d_mel_colp;
+	static const bool force_generic = [] { const char *e = getenv("SRB200_MFCC_GENERIC"); return e && e[0] == '1'; }();
+	if (p->fast && !force_generic) mfcc_frames_fast_kernel<<<s->n_cta, MF_THREADS, p->smem_fast, st>>>(a);
+	else mfcc_frames_kernel<<<s->n_cta, MF_THREADS, p->smem, st>>>(a);
 	SRB_CUDA(cudaGetLastError());
 	if (cmvn) {
 		mfcc_stats_kernel<<<n_utt, 1024, 0, st>>>(s->d_partials, s->d_cta_start, s->d_frame_off, p->nc, s->d_stats);

@@ -59,6 +59,21 @@ class BatchScorer(object):
         self.h_best = torch.empty(B, dtype=torch.int32).pin_memory()
         self.B = B
         self._shape = key
+        # sub-batches for the end-to-end path: H2D of chunk c+1 overlaps the kernels of chunk c
+        self.chunks = []
+        n_chunks = 4 if B >= 8 else 1
+        bounds = [round(i * B / n_chunks) for i in range(n_chunks + 1)]
+        row0 = 0
+        for c in range(n_chunks):
+            u0, u1 = bounds[c], bounds[c + 1]
+            rel = (off[u0:u1 + 1] - off[u0]).tolist()
+            smp = (C.c_longlong * (u1 - u0 + 1))(*rel)
+            rows_c = int(self.L.srb200_mfcc_rows_total(self.ex._h, smp, u1 - u0, self.nd))
+            self.chunks.append(dict(u0=u0, u1=u1, s0=int(off[u0]), s1=int(off[u1]), smp=smp, row0=row0, rows=rows_c,
+                                    feat_off=(C.c_int * (u1 - u0 + 1))()))
+            row0 += rows_c
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.copy_events = [torch.cuda.Event() for _ in self.chunks]
 
     # ---- stages (each enqueues on the current torch stream) ----
     def upload(self, pcm_host):
@@ -81,12 +96,28 @@ class BatchScorer(object):
         self.score()
 
     def predict_pcm(self, pcm_host, lengths):
-        """end to end: pinned host PCM in, speaker indices (host int32 tensor, pinned) out"""
+        """end to end: pinned host PCM in, speaker indices (host int32 tensor, pinned) out.  The batch is cut into
+        sub-batches of utterances; the H2D copy of sub-batch c+1 (copy stream) overlaps the kernels of sub-batch c."""
+        torch = self.torch
         self._prepare(lengths)
-        self.upload(pcm_host)
-        self.step_device()
+        cur = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(cur)              # previous users of d_pcm are done
+        with torch.cuda.stream(self.copy_stream):
+            for c, ev in zip(self.chunks, self.copy_events):
+                self.d_pcm[c["s0"]:c["s1"]].copy_(pcm_host[c["s0"]:c["s1"]], non_blocking=True)
+                ev.record(self.copy_stream)
+        st = cur.cuda_stream
+        for c, ev in zip(self.chunks, self.copy_events):
+            cur.wait_event(ev)
+            nu = c["u1"] - c["u0"]
+            _lib.check(self.L.srb200_mfcc_extract_dev(self.ex._h, self.d_pcm.data_ptr() + 2 * c["s0"], c["smp"], nu, self.nd,
+                                                      self.d_feat.data_ptr() + 4 * self.ld * c["row0"], self.ld, c["feat_off"], st),
+                       "mfcc_extract_dev")
+            _lib.check(self.L.srb200_gmmset_score_dev(self.set_h, self.d_feat.data_ptr() + 4 * self.ld * c["row0"], self.ld, self.dim,
+                                                      c["feat_off"], nu, self.d_sums.data_ptr() + 8 * self.S * c["u0"], None, 0,
+                                                      self.d_best.data_ptr() + 4 * c["u0"], st), "gmmset_score_dev")
         self.h_best.copy_(self.d_best, non_blocking=True)
-        self.torch.cuda.current_stream().synchronize()
+        cur.synchronize()
         return self.h_best
 
     def predict(self, signals):

@@ -36,3 +36,30 @@ def test_enroll_train_predict_dump_load(tmp_path):
     m2 = ModelInterface.load(path)
     assert [m2.predict(16000, sig) for _, sig in tests] == names
     assert m.predict(16000, np.zeros(100, dtype=np.int16)) is None      # extractor exception -> None (interface.py:89-93)
+
+
+def test_batch_scorer_matches_per_utterance_path_and_oracle():
+    """pipeline.BatchScorer (device-resident, chunked H2D overlap) == per-utterance public API == float64 oracle argmax"""
+    from speaker_recognition_b200.feature import MFCC
+    from speaker_recognition_b200.gmm.pygmm import GMM
+    from speaker_recognition_b200.gmmset import GMMSet
+    from speaker_recognition_b200.pipeline import BatchScorer
+    S, K, D = 12, 32, 39
+    W, M, Sg = synth.models(S, K, D, seed0=1000)
+    gs = GMMSet(gmm_order=K)
+    for i in range(S):
+        gs.gmms.append(GMM(K).set_params(W[i], M[i], Sg[i]))
+        gs.y.append("s%d" % i)
+    lens = [40000, 9000, 33333, 2561 + 512, 70001, 12000, 8191, 25000, 16000, 48000]   # 10 utterances -> 4 ragged sub-batches
+    sigs = [synth.audio(n, seed=300 + i) for i, n in enumerate(lens)]
+    bs = BatchScorer(gs, fs=16000, nd=2)
+    labels = bs.predict(sigs)
+    sums = bs.d_sums.cpu().numpy()
+    for i, s in enumerate(sigs):
+        feat = MFCC.extract(16000, s, nd=2)
+        per_utt = np.array(gs.predict_one_scores(feat))
+        assert np.max(np.abs(per_utt - sums[i]) / np.abs(per_utt)) < 1e-5
+        ref_feat = mfcc_ref.extract39(16000, s)
+        ex = [gmm_ref.score_all(W[k], M[k], Sg[k], ref_feat, gmm_ref.MODE_LOGDOMAIN) for k in range(S)]
+        assert labels[i] == "s%d" % int(np.argmax(ex))
+        assert np.max(np.abs(np.array(ex) - sums[i]) / np.abs(np.array(ex))) < 2e-3     # features differ at 1e-4 -> sums at ~1e-3
