@@ -48,7 +48,7 @@ struct MfccPlan {
 	// fast path (M == 1024, frame length <= 512): register-resident 4 x 256-point transforms
 	bool fast = false;
 	cpx *d_tw1 = nullptr, *d_twA = nullptr;
-	int *d_mel_colp = nullptr;
+	int *d_mel_colp = nullptr, *d_mel_order = nullptr;
 	size_t smem_fast = 0;
 	std::vector<MfccShape> shapes;
 	uint64_t stamp = 0;
@@ -70,6 +70,7 @@ struct MfccArgs {
 	double *partials;
 	const cpx *tw1, *twA;      // fast path tables
 	const int *mel_colp;       // mel columns permuted to the fast path's P'[r*257 + q] layout
+	const int *mel_order;      // bands sorted by non-zero count, descending (balances the 8-lane groups)
 };
 
 __device__ __forceinline__ int find_segment(const int *__restrict__ start, int n, int x) {
@@ -254,7 +255,9 @@ __global__ void __launch_bounds__(MF_THREADS, 2) mfcc_frames_fast_kernel(const M
 	srbfft::fast_power_unpack(Zs + f * 4 * 256, Pp + f * PSTR, A.tw2, tid & 63, 64);
 	__syncthreads();
 
-	// mel + log: one 8-lane group per (frame, band), lanes stride the band's non-zeros, shuffle-reduce (deterministic)
+	// mel + log: one 8-lane group per (frame, band); lanes stride the band's non-zeros and shuffle-reduce in a fixed
+	// order (deterministic).  Items are visited in descending non-zero count (mel_order) so that the 32 groups of a
+	// round carry similar work: the phase costs ~nnz_total/256 iterations instead of the widest band per round.
 	float *logE = ybuf;                                                          // [NF][nb]
 	{
 		const int group = tid >> 3, l8 = tid & 7;
@@ -262,30 +265,51 @@ __global__ void __launch_bounds__(MF_THREADS, 2) mfcc_frames_fast_kernel(const M
 		for (int it = 0; it * 32 < items; ++it) {
 			const int item = it * 32 + group;
 			const bool valid = item < items;
-			const int ff = valid ? item / nb : 0, b = valid ? item - ff * nb : 0;
-			float e = 0.f;
+			const int ff = item & (MFF_NF - 1);
+			const int b = valid ? __ldg(A.mel_order + (item >> 2)) : 0;
+			float e0 = 0.f, e1 = 0.f;
 			if (valid) {
 				const float *Pf = Pp + ff * PSTR;
 				const int j1 = __ldg(A.mel_ptr + b + 1);
-				for (int j = __ldg(A.mel_ptr + b) + l8; j < j1; j += 8) e = fmaf(__ldg(A.mel_val + j), Pf[__ldg(A.mel_colp + j)], e);
+				int j = __ldg(A.mel_ptr + b) + l8;
+				for (; j + 8 < j1; j += 16) {
+					const float v0 = __ldg(A.mel_val + j), v1 = __ldg(A.mel_val + j + 8);
+					const int c0 = __ldg(A.mel_colp + j), c1 = __ldg(A.mel_colp + j + 8);
+					e0 = fmaf(v0, Pf[c0], e0);
+					e1 = fmaf(v1, Pf[c1], e1);
+				}
+				if (j < j1) e0 = fmaf(__ldg(A.mel_val + j), Pf[__ldg(A.mel_colp + j)], e0);
 			}
+			float e = e0 + e1;
 			e += __shfl_xor_sync(0xffffffffu, e, 4);
 			e += __shfl_xor_sync(0xffffffffu, e, 2);
 			e += __shfl_xor_sync(0xffffffffu, e, 1);
-			if (valid && l8 == 0) logE[item] = e > 0.f ? logf(e) : __ldg(A.logfloor + b);
+			if (valid && l8 == 0) logE[ff * nb + b] = e > 0.f ? logf(e) : __ldg(A.logfloor + b);
 		}
 	}
 	__syncthreads();
+	// DCT rows 1..n_ceps, float64 accumulate; each dot product is split over 4 lanes (fixed order -> deterministic)
 	float *cep = logE + MFF_NF * nb;                                             // [NF][nc]
-	for (int t = tid; t < MFF_NF * nc; t += MF_THREADS) {
-		const int ff = t / nc, i = t - ff * nc;
-		const double *dr = A.dct + (size_t)i * nb;
-		const float *le = logE + ff * nb;
-		double acc = 0.0;
-		for (int b = 0; b < nb; ++b) acc = fma(__ldg(dr + b), (double)le[b], acc);
-		const float c = (float)acc;
-		cep[t] = c;
-		if (ff < nfr) A.ceps[(size_t)(fbase + fr0 + ff) * A.CL + i] = c;
+	{
+		const int q4 = tid & 3, t4 = tid >> 2;
+		const int outs = MFF_NF * nc;
+		for (int base = 0; base < outs; base += MF_THREADS / 4) {
+			const int t = base + t4;
+			const bool valid = t < outs;
+			const int ff = valid ? t / nc : 0, i = valid ? t - ff * nc : 0;
+			const double *dr = A.dct + (size_t)i * nb;
+			const float *le = logE + ff * nb;
+			double acc = 0.0;
+			if (valid)
+				for (int b = q4; b < nb; b += 4) acc = fma(__ldg(dr + b), (double)le[b], acc);
+			acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+			acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+			if (valid && q4 == 0) {
+				const float c = (float)acc;
+				cep[t] = c;
+				if (ff < nfr) A.ceps[(size_t)(fbase + fr0 + ff) * A.CL + i] = c;
+			}
+		}
 	}
 	for (int t = tid; t < MFF_NF * (A.CL - nc); t += MF_THREADS) {
 		const int ff = t / (A.CL - nc), i = nc + t - ff * (A.CL - nc);
@@ -455,7 +479,11 @@ static int build_tables(MfccPlan *p) {
 			for (int u = 0; u < 16; ++u) twA[q2 * 16 + u] = cpx{(float)cos(-2.0 * M_PI * u * q2 / 256), (float)sin(-2.0 * M_PI * u * q2 / 256)};
 		std::vector<int> colp(col.size());
 		for (size_t j = 0; j < col.size(); ++j) colp[j] = (col[j] & 3) * srbfft::FAST_PSTRIDE + (col[j] >> 2);
-		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_colp, colp)) return 1;
+		std::vector<int> order(nb);
+		for (int b = 0; b < nb; ++b) order[b] = b;
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return (ptr[a + 1] - ptr[a]) > (ptr[b2 + 1] - ptr[b2]); });
+		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_colp, colp) || to_device(&p->d_mel_order, order))
+			return 1;
 	}
 	if (to_device(&p->d_win, win) || to_device(&p->d_win2, win2) || to_device(&p->d_mel_ptr, ptr) ||
 	    to_device(&p->d_mel_col, col) || to_device(&p->d_mel_val, val) || to_device(&p->d_logfloor, logfloor) ||
@@ -543,6 +571,7 @@ void mfcc_plan_free(MfccPlan *p) {
 	cudaFree(p->d_tw1);
 	cudaFree(p->d_twA);
 	cudaFree(p->d_mel_colp);
+	cudaFree(p->d_mel_order);
 	delete p;
 }
 
@@ -644,6 +673,7 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.tw1 = p->d_tw1;
 	a.twA = p->d_twA;
 	a.mel_colp = p->d_mel_colp;
+	a.mel_order = p->d_mel_order;
 	static const bool force_generic = [] { const char *e = getenv("SRB200_MFCC_GENERIC"); return e && e[0] == '1'; }();
 	if (p->fast && !force_generic) mfcc_frames_fast_kernel<<<s->n_cta, MF_THREADS, p->smem_fast, st>>>(a);
 	else mfcc_frames_kernel<<<s->n_cta, MF_THREADS, p->smem, st>>>(a);

@@ -260,3 +260,27 @@ def test_pickle_roundtrip_of_speaker_set(tmp_path):
     g2.after_pickle()
     assert g2.predict_one(X) == "p2"
     assert np.allclose(g2.predict_one_scores(X), before, rtol=1e-12)
+
+
+def test_dist_em_train_with_device_backend_single_rank():
+    """speaker_recognition_b200.dist.em_train + DeviceEM (the frame-sharded trainer, world size 1) vs the float64 oracle"""
+    import torch
+    from speaker_recognition_b200 import dist as sdist
+    K, D, n = 12, 20, 4000
+    wt, mt, st_ = synth.model(K, D, seed=61, floor_frac=0.0)
+    X = synth.draw(wt, mt, st_, n, seed=62)
+    w0 = np.ones(K) / K
+    m0 = X[np.random.default_rng(4).choice(n, K, replace=False)]
+    s0 = np.tile(X.std(axis=0, ddof=1), (K, 1))
+    g = make_gmm(w0, m0, s0)
+    ld = (D + 3) & ~3
+    Xd = torch.zeros((n, ld), dtype=torch.float32, device="cuda")
+    Xd[:, :D] = torch.from_numpy(X.astype(np.float32)).cuda()
+    iters, ll = sdist.em_train(sdist.DeviceEM(g, Xd, n, ld, D), n, 4, threshold=0.0)
+    assert iters == 4
+    w, m, s = w0, m0, s0
+    for _ in range(4):
+        w, m, s = gmm_ref.em_iteration(w, m, s, X)
+    gw, gm, gsg = g.get_params()
+    assert np.max(rel_err(gm, m)) < 5e-4 and np.max(np.abs(gsg - s) / s) < 5e-4 and np.max(np.abs(gw - w) / w) < 5e-4
+    assert abs(ll - gmm_ref.score_all(w, m, s, X)) < 1e-4 * abs(ll)

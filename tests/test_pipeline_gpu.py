@@ -63,3 +63,29 @@ def test_batch_scorer_matches_per_utterance_path_and_oracle():
         ex = [gmm_ref.score_all(W[k], M[k], Sg[k], ref_feat, gmm_ref.MODE_LOGDOMAIN) for k in range(S)]
         assert labels[i] == "s%d" % int(np.argmax(ex))
         assert np.max(np.abs(np.array(ex) - sums[i]) / np.abs(np.array(ex))) < 2e-3     # features differ at 1e-4 -> sums at ~1e-3
+
+
+def test_streaming_predictor_equals_window_predict():
+    """config-5 semantics: each tick's label == predict() on the trailing 1.5 s window (gui.py:179-190)"""
+    from speaker_recognition_b200.feature import MFCC
+    from speaker_recognition_b200.gmm.pygmm import GMM
+    from speaker_recognition_b200.gmmset import GMMSet
+    from speaker_recognition_b200.streaming import StreamingPredictor
+    S, K, D, B, hop = 6, 16, 39, 5, 400
+    W, M, Sg = synth.models(S, K, D, seed0=2000)
+    gs = GMMSet(gmm_order=K)
+    for i in range(S):
+        gs.gmms.append(GMM(K).set_params(W[i], M[i], Sg[i]))
+        gs.y.append(i)
+    sp = StreamingPredictor(gs, n_streams=B, fs=16000, window_s=1.5, nd=2)
+    n_ticks = 24000 // hop + 3
+    audio = np.stack([synth.audio(hop * n_ticks, seed=700 + b) for b in range(B)])
+    out = None
+    for t in range(n_ticks):
+        out = sp.push(audio[:, t * hop:(t + 1) * hop])
+        assert (out is None) == ((t + 1) * hop < 24000)
+    for b in range(B):
+        win = audio[b, hop * n_ticks - 24000:]
+        feat = MFCC.extract(16000, win, nd=2)
+        assert feat.shape == (90, 39)
+        assert int(out[b]) == int(np.argmax(gs.predict_one_scores(feat)))
