@@ -158,7 +158,9 @@ SRB_HD void dft16(const cpx *v, cpx *o) {
 }
 
 constexpr int FAST_TSTRIDE = 17;        // padded row of the 16x16 transpose tile (complex elements)
-constexpr int FAST_PSTRIDE = 257;       // P'[r][q] rows: k = 4q + r, q <= 256 only for r == 0
+constexpr int FAST_ZSTRIDE = 260;       // row stride of Zs[r][q] (complex): 260 = 4 mod 16 makes the 64-bit reads of
+                                        // Z[4q + r] by consecutive k conflict-free (16 lanes x 8 B = 16 distinct bank pairs)
+constexpr int FAST_PSTRIDE = 1028;      // power spectrum row (floats): bins 0..1024, natural order
 
 // step A of the 256-point sub-transform owned by (r, u): inputs z[u + 16 n2] (packed complex frame, zero for
 // n >= 256 by construction), first twiddle tw1[r][n] = W_1024^{n r}, radix-16 over n2, second twiddle
@@ -176,7 +178,7 @@ SRB_HD void fast_step_a(const cpx *z, const cpx *tw1, const cpx *twA, cpx *T, in
 	for (int q2 = 0; q2 < 16; ++q2) T[u * FAST_TSTRIDE + q2] = cmul(out[q2], twA[q2 * 16 + u]);
 }
 
-// step B: radix-16 over n1 of T[n1][u] -> Y_r[16 q1 + u], stored as Zs[r][16 q1 + u]
+// step B: radix-16 over n1 of T[n1][u] -> Y_r[16 q1 + u], stored as Zr[16 q1 + u] (Zr = Zs + r * FAST_ZSTRIDE)
 SRB_HD void fast_step_b(const cpx *T, cpx *Zr, int u) {
 	cpx in[16], out[16];
 #pragma unroll
@@ -186,18 +188,45 @@ SRB_HD void fast_step_b(const cpx *T, cpx *Zr, int u) {
 	for (int q1 = 0; q1 < 16; ++q1) Zr[16 * q1 + u] = out[q1];
 }
 
-// power spectrum of the real 2048-point transform from Zs[r][q] (Z[4q + r]); output permuted P'[r*257 + q]
-SRB_HD void fast_power_unpack(const cpx *Zs, float *Pp, const cpx *tw2, int worker, int n_workers) {
-	for (int k = worker; k <= 1024; k += n_workers) {
-		const int km = (1024 - k) & 1023;
-		const cpx zk = Zs[(k & 3) * 256 + ((k >> 2) & 255)];
-		cpx zc = Zs[(km & 3) * 256 + (km >> 2)];
-		zc.y = -zc.y;
-		const cpx e = cadd(zk, zc), o = csub(zk, zc);
-		const cpx wo = cmul(tw2[k], o);
-		const float yr = 0.5f * (e.x + wo.y), yi = 0.5f * (e.y - wo.x);
-		Pp[(k & 3) * FAST_PSTRIDE + (k >> 2)] = yr * yr + yi * yi;
+// one bin of the real 2048-point power spectrum from Zs[r][q] = Z[4q + r]; w = exp(-2 pi i k / 2048)
+SRB_HD float fast_power_bin(const cpx *Zs, int k, cpx w) {
+	const int km = (1024 - k) & 1023;
+	const cpx zk = Zs[(k & 3) * FAST_ZSTRIDE + ((k >> 2) & 255)];
+	cpx zc = Zs[(km & 3) * FAST_ZSTRIDE + (km >> 2)];
+	zc.y = -zc.y;
+	const cpx e = cadd(zk, zc), o = csub(zk, zc);
+	const cpx wo = cmul(w, o);
+	const float yr = 0.5f * (e.x + wo.y), yi = 0.5f * (e.y - wo.x);
+	return yr * yr + yi * yi;
+}
+
+// power spectrum P[0..1024] (natural order) of one frame by 64 workers: worker w owns k = w + 64 i, i = 0..15
+// (consecutive workers -> consecutive k: conflict-free shared-memory traffic), worker 0 also k = 1024.
+// The unpack twiddle exp(-2 pi i k/2048) = tw2[w] * exp(-2 pi i i/32): one table load per worker, 16 constants.
+SRB_HD void fast_power_unpack(const cpx *Zs, float *P, const cpx *tw2, int worker) {
+	const float W32[16][2] = {{1.f, -0.f},
+	                          {0.98078528040323044913f, -0.19509032201612826785f},
+	                          {0.92387953251128675613f, -0.38268343236508977173f},
+	                          {0.83146961230254523708f, -0.55557023301960222474f},
+	                          {0.70710678118654752440f, -0.70710678118654752440f},
+	                          {0.55557023301960222474f, -0.83146961230254523708f},
+	                          {0.38268343236508977173f, -0.92387953251128675613f},
+	                          {0.19509032201612826785f, -0.98078528040323044913f},
+	                          {0.f, -1.f},
+	                          {-0.19509032201612826785f, -0.98078528040323044913f},
+	                          {-0.38268343236508977173f, -0.92387953251128675613f},
+	                          {-0.55557023301960222474f, -0.83146961230254523708f},
+	                          {-0.70710678118654752440f, -0.70710678118654752440f},
+	                          {-0.83146961230254523708f, -0.55557023301960222474f},
+	                          {-0.92387953251128675613f, -0.38268343236508977173f},
+	                          {-0.98078528040323044913f, -0.19509032201612826785f}};
+	const cpx base = tw2[worker];
+#pragma unroll
+	for (int i = 0; i < 16; ++i) {
+		const cpx w = (i == 0) ? base : cmul(base, cpx{W32[i][0], W32[i][1]});
+		P[worker + 64 * i] = fast_power_bin(Zs, worker + 64 * i, w);
 	}
+	if (worker == 0) P[1024] = fast_power_bin(Zs, 1024, cpx{-1.f, 0.f});
 }
 
 }  // namespace srbfft

@@ -33,9 +33,22 @@ constexpr int EM_XS = 264;             // padded row stride of the x tile (float
 constexpr int EM_DP = 40;              // dims per pass of the phase-2 tile (4 dim groups x 10)
 constexpr int EM_GS = 36;              // padded row stride of a warp's gamma tile [64][32]
 constexpr int EM_FLUSH = 16;           // steps between float64 flushes
-constexpr int EM_ACC = 4 * 10 * 2 + 4; // per-thread outputs: 4 mixtures x 10 dims x {x, x^2} + 4 N_k
 constexpr float LN2F_EM = 0.69314718055994531f;
 constexpr float DENORM_LOG_MIN_EM = -744.4400719213812f;
+
+__device__ __forceinline__ unsigned long long em_pack2(float lo, float hi) {
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+	return r;
+}
+__device__ __forceinline__ void em_unpack2(unsigned long long v, float &lo, float &hi) {
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long em_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+	unsigned long long d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));   // SASS FFMA2: two fp32 FMAs per issue slot
+	return d;
+}
 
 struct EmArgs {
 	const float *X;
@@ -84,9 +97,13 @@ __global__ void __launch_bounds__(EM_THREADS, 2) em_accumulate_kernel(const EmAr
 	const int step0 = split * per;
 	const int step1 = min(n_steps_total, step0 + per);
 
-	float acc[EM_ACC];
+	// phase-2 accumulators: acc2[kk][j] = {sum gamma x, sum gamma x^2} for mixture 4kg+kk, dim 4j+dg; accn[kk] = sum gamma
+	unsigned long long acc2[4][10];
+	float accn[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-	for (int i = 0; i < EM_ACC; ++i) acc[i] = 0.f;
+	for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+		for (int j = 0; j < 10; ++j) acc2[kk][j] = 0ull;
 	double *my_part = A.partials + ((((size_t)split * 4 + warp) * A.n_ktiles + ktile) * 32) * 84;
 
 	mbar_wait(bar, 0);
@@ -140,27 +157,35 @@ __global__ void __launch_bounds__(EM_THREADS, 2) em_accumulate_kernel(const EmAr
 		// ---------------- phase 1: exponents of (64 frames of this warp) x (32 mixtures) ----------------
 		{
 			float a8[8][8];
-#pragma unroll
-			for (int f = 0; f < 8; ++f)
-#pragma unroll
-				for (int m = 0; m < 8; ++m) a8[f][m] = cneg[m];
-			const float *xbase = xs + warp * 64 + 4 * g;
-#pragma unroll 2
-			for (int d = 0; d < D; ++d) {
-				const float4 xa = *reinterpret_cast<const float4 *>(xbase + d * EM_XS);
-				const float4 xb = *reinterpret_cast<const float4 *>(xbase + d * EM_XS + 32);
-				const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+			{
+				unsigned long long a2[8][4];
 #pragma unroll
 				for (int j = 0; j < 4; ++j) {
-					const float4 p = *reinterpret_cast<const float4 *>(pq + d * 64 + 16 * j);
+					const unsigned long long c2 = em_pack2(cneg[2 * j], cneg[2 * j + 1]);
 #pragma unroll
-					for (int f = 0; f < 8; ++f) {   // chunk = [a0, a1, nb0, nb1]
-						const float t0 = fmaf(xv[f], p.x, p.z);
-						a8[f][2 * j] = fmaf(t0, t0, a8[f][2 * j]);
-						const float t1 = fmaf(xv[f], p.y, p.w);
-						a8[f][2 * j + 1] = fmaf(t1, t1, a8[f][2 * j + 1]);
+					for (int f = 0; f < 8; ++f) a2[f][j] = c2;
+				}
+				const float *xbase = xs + warp * 64 + 4 * g;
+#pragma unroll 2
+				for (int d = 0; d < D; ++d) {
+					const float4 xa = *reinterpret_cast<const float4 *>(xbase + d * EM_XS);
+					const float4 xb = *reinterpret_cast<const float4 *>(xbase + d * EM_XS + 32);
+					const unsigned long long x2[8] = {em_pack2(xa.x, xa.x), em_pack2(xa.y, xa.y), em_pack2(xa.z, xa.z), em_pack2(xa.w, xa.w),
+					                                  em_pack2(xb.x, xb.x), em_pack2(xb.y, xb.y), em_pack2(xb.z, xb.z), em_pack2(xb.w, xb.w)};
+#pragma unroll
+					for (int j = 0; j < 4; ++j) {
+						const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(pq + d * 64 + 16 * j);   // {a0,a1}, {nb0,nb1}
+#pragma unroll
+						for (int f = 0; f < 8; ++f) {
+							const unsigned long long t2 = em_fma2(x2[f], p.x, p.y);
+							a2[f][j] = em_fma2(t2, t2, a2[f][j]);
+						}
 					}
 				}
+#pragma unroll
+				for (int f = 0; f < 8; ++f)
+#pragma unroll
+					for (int j = 0; j < 4; ++j) em_unpack2(a2[f][j], a8[f][2 * j], a8[f][2 * j + 1]);
 			}
 			// gamma = 2^(-acc - lse2); park in the warp's tile gw[frame][mixture]
 #pragma unroll
@@ -189,10 +214,10 @@ __global__ void __launch_bounds__(EM_THREADS, 2) em_accumulate_kernel(const EmAr
 				if (dg == 0) {
 #pragma unroll
 					for (int i = 0; i < 4; ++i) {
-						acc[80] += gmm[i].x;
-						acc[81] += gmm[i].y;
-						acc[82] += gmm[i].z;
-						acc[83] += gmm[i].w;
+						accn[0] += gmm[i].x;
+						accn[1] += gmm[i].y;
+						accn[2] += gmm[i].z;
+						accn[3] += gmm[i].w;
 					}
 				}
 #pragma unroll
@@ -201,15 +226,11 @@ __global__ void __launch_bounds__(EM_THREADS, 2) em_accumulate_kernel(const EmAr
 					const float xv[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
 					for (int i = 0; i < 4; ++i) {
-						const float x1 = xv[i], x2 = xv[i] * xv[i];
-						acc[0 * 20 + 2 * j] = fmaf(gmm[i].x, x1, acc[0 * 20 + 2 * j]);
-						acc[0 * 20 + 2 * j + 1] = fmaf(gmm[i].x, x2, acc[0 * 20 + 2 * j + 1]);
-						acc[1 * 20 + 2 * j] = fmaf(gmm[i].y, x1, acc[1 * 20 + 2 * j]);
-						acc[1 * 20 + 2 * j + 1] = fmaf(gmm[i].y, x2, acc[1 * 20 + 2 * j + 1]);
-						acc[2 * 20 + 2 * j] = fmaf(gmm[i].z, x1, acc[2 * 20 + 2 * j]);
-						acc[2 * 20 + 2 * j + 1] = fmaf(gmm[i].z, x2, acc[2 * 20 + 2 * j + 1]);
-						acc[3 * 20 + 2 * j] = fmaf(gmm[i].w, x1, acc[3 * 20 + 2 * j]);
-						acc[3 * 20 + 2 * j + 1] = fmaf(gmm[i].w, x2, acc[3 * 20 + 2 * j + 1]);
+						const unsigned long long xx = em_pack2(xv[i], xv[i] * xv[i]);          // {x, x^2}
+						acc2[0][j] = em_fma2(em_pack2(gmm[i].x, gmm[i].x), xx, acc2[0][j]);
+						acc2[1][j] = em_fma2(em_pack2(gmm[i].y, gmm[i].y), xx, acc2[1][j]);
+						acc2[2][j] = em_fma2(em_pack2(gmm[i].z, gmm[i].z), xx, acc2[2][j]);
+						acc2[3][j] = em_fma2(em_pack2(gmm[i].w, gmm[i].w), xx, acc2[3][j]);
 					}
 				}
 			}
@@ -224,14 +245,15 @@ __global__ void __launch_bounds__(EM_THREADS, 2) em_accumulate_kernel(const EmAr
 #pragma unroll
 				for (int j = 0; j < 10; ++j) {
 					const int dd = 4 * j + dg;
-					rowp[2 * dd] += (double)acc[kk * 20 + 2 * j];
-					rowp[2 * dd + 1] += (double)acc[kk * 20 + 2 * j + 1];
-					acc[kk * 20 + 2 * j] = 0.f;
-					acc[kk * 20 + 2 * j + 1] = 0.f;
+					float sx, sxx;
+					em_unpack2(acc2[kk][j], sx, sxx);
+					rowp[2 * dd] += (double)sx;
+					rowp[2 * dd + 1] += (double)sxx;
+					acc2[kk][j] = 0ull;
 				}
 				if (dg == 0) {
-					rowp[80] += (double)acc[80 + kk];
-					acc[80 + kk] = 0.f;
+					rowp[80] += (double)accn[kk];
+					accn[kk] = 0.f;
 				}
 			}
 			since_flush = 0;

@@ -48,7 +48,7 @@ struct MfccPlan {
 	// fast path (M == 1024, frame length <= 512): register-resident 4 x 256-point transforms
 	bool fast = false;
 	cpx *d_tw1 = nullptr, *d_twA = nullptr;
-	int *d_mel_colp = nullptr, *d_mel_order = nullptr;
+	int *d_mel_order = nullptr;
 	size_t smem_fast = 0;
 	std::vector<MfccShape> shapes;
 	uint64_t stamp = 0;
@@ -69,7 +69,6 @@ struct MfccArgs {
 	float *ceps;
 	double *partials;
 	const cpx *tw1, *twA;      // fast path tables
-	const int *mel_colp;       // mel columns permuted to the fast path's P'[r*257 + q] layout
 	const int *mel_order;      // bands sorted by non-zero count, descending (balances the 8-lane groups)
 };
 
@@ -207,14 +206,13 @@ __global__ void __launch_bounds__(MF_THREADS) mfcc_frames_kernel(const MfccArgs 
 constexpr int MFF_NF = 4;
 constexpr int MFF_YLEN = 512;
 
-__global__ void __launch_bounds__(MF_THREADS, 2) mfcc_frames_fast_kernel(const MfccArgs A) {
+__global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const MfccArgs A) {
 	extern __shared__ __align__(16) unsigned char mf_smem[];
 	const int tid = threadIdx.x;
 	const int L = A.L, nb = A.nb, nc = A.nc;
-	cpx *T = reinterpret_cast<cpx *>(mf_smem);                                   // [NF][4][16*17]   (later P'[NF][4*257] floats)
-	cpx *Zs = T + MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE;                        // [NF][4][256]
-	float *ybuf = reinterpret_cast<float *>(Zs + MFF_NF * 4 * 256);              // [NF][512]        (later logE / cep)
-	float *sbuf = ybuf + MFF_NF * MFF_YLEN;                                      // [(NF-1)*shift + L]
+	cpx *T = reinterpret_cast<cpx *>(mf_smem);                                   // [NF][4][16*17]   (later P[NF][1028] floats)
+	cpx *Zs = T + MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE;                        // [NF][4][260]
+	float *ybuf = reinterpret_cast<float *>(Zs + MFF_NF * 4 * srbfft::FAST_ZSTRIDE);   // [NF][512]  (later logE / cep)
 
 	const int u_ = find_segment(A.cta_start, A.n_utt, blockIdx.x);
 	const int fbase = __ldg(A.frame_off + u_);
@@ -222,24 +220,25 @@ __global__ void __launch_bounds__(MF_THREADS, 2) mfcc_frames_fast_kernel(const M
 	const int fr0 = (blockIdx.x - __ldg(A.cta_start + u_)) * MFF_NF;
 	const int nfr = min(MFF_NF, T_u - fr0);
 	const long long s0 = A.smp_off[u_] + (long long)fr0 * A.shift;
-	const int span = (nfr - 1) * A.shift + L;
 
-	if (A.is_f32) {
-		const float *p = reinterpret_cast<const float *>(A.pcm) + s0;
-		for (int i = tid; i < span; i += MF_THREADS) sbuf[i] = __ldg(p + i);
-	} else {
-		const int16_t *p = reinterpret_cast<const int16_t *>(A.pcm) + s0;
-		for (int i = tid; i < span; i += MF_THREADS) sbuf[i] = (float)__ldg(p + i);
-	}
-	__syncthreads();
-	// window then pre-emphasis (MFCC.py:61-64) into ybuf; zeros beyond the frame and for absent frames
+	// window then pre-emphasis (MFCC.py:61-64) straight from global memory (each sample is touched by at most four
+	// (frame, tap) pairs of this CTA: L1 serves the repeats); zeros beyond the frame and for absent frames
 	for (int t = tid; t < MFF_NF * MFF_YLEN; t += MF_THREADS) {
 		const int f = t >> 9, i = t & (MFF_YLEN - 1);
 		float y = 0.f;
 		if (f < nfr && i < L) {
-			const float *s = sbuf + f * A.shift;
-			y = __ldg(A.win + i) * s[i];
-			if (i > 0) y = fmaf(-__ldg(A.win2 + i), s[i - 1], y);
+			const long long g = s0 + (long long)f * A.shift + i;
+			float sc, sp = 0.f;
+			if (A.is_f32) {
+				const float *p = reinterpret_cast<const float *>(A.pcm);
+				sc = __ldg(p + g);
+				if (i > 0) sp = __ldg(p + g - 1);
+			} else {
+				const int16_t *p = reinterpret_cast<const int16_t *>(A.pcm);
+				sc = (float)__ldg(p + g);
+				if (i > 0) sp = (float)__ldg(p + g - 1);
+			}
+			y = fmaf(-__ldg(A.win2 + i), sp, __ldg(A.win + i) * sc);
 		}
 		ybuf[t] = y;
 	}
@@ -248,16 +247,17 @@ __global__ void __launch_bounds__(MF_THREADS, 2) mfcc_frames_fast_kernel(const M
 	cpx *Tfr = T + (f * 4 + r) * 16 * srbfft::FAST_TSTRIDE;
 	srbfft::fast_step_a(reinterpret_cast<const cpx *>(ybuf + f * MFF_YLEN), A.tw1, A.twA, Tfr, r, u);
 	__syncthreads();
-	srbfft::fast_step_b(Tfr, Zs + (f * 4 + r) * 256, u);
+	srbfft::fast_step_b(Tfr, Zs + (f * 4 + r) * srbfft::FAST_ZSTRIDE, u);
 	__syncthreads();
-	float *Pp = reinterpret_cast<float *>(T);                                    // [NF][4*257]
-	constexpr int PSTR = 4 * srbfft::FAST_PSTRIDE;
-	srbfft::fast_power_unpack(Zs + f * 4 * 256, Pp + f * PSTR, A.tw2, tid & 63, 64);
+	float *P = reinterpret_cast<float *>(T);                                     // [NF][1028], natural bin order
+	constexpr int PSTR = srbfft::FAST_PSTRIDE;
+	srbfft::fast_power_unpack(Zs + f * 4 * srbfft::FAST_ZSTRIDE, P + f * PSTR, A.tw2, tid & 63);
 	__syncthreads();
 
-	// mel + log: one 8-lane group per (frame, band); lanes stride the band's non-zeros and shuffle-reduce in a fixed
-	// order (deterministic).  Items are visited in descending non-zero count (mel_order) so that the 32 groups of a
-	// round carry similar work: the phase costs ~nnz_total/256 iterations instead of the widest band per round.
+	// mel + log: one 8-lane group per (frame, band).  The filters are triangles, so a band's non-zeros are a contiguous
+	// run of bins starting at mel_col[ptr[b]] (checked on the host): the lanes read consecutive P values (no column
+	// look-up) and shuffle-reduce in a fixed order (deterministic).  Items are visited in descending non-zero count
+	// (mel_order) so that the 32 groups of a round carry similar work.
 	float *logE = ybuf;                                                          // [NF][nb]
 	{
 		const int group = tid >> 3, l8 = tid & 7;
@@ -267,20 +267,21 @@ __global__ void __launch_bounds__(MF_THREADS, 2) mfcc_frames_fast_kernel(const M
 			const bool valid = item < items;
 			const int ff = item & (MFF_NF - 1);
 			const int b = valid ? __ldg(A.mel_order + (item >> 2)) : 0;
-			float e0 = 0.f, e1 = 0.f;
+			float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
 			if (valid) {
-				const float *Pf = Pp + ff * PSTR;
-				const int j1 = __ldg(A.mel_ptr + b + 1);
-				int j = __ldg(A.mel_ptr + b) + l8;
-				for (; j + 8 < j1; j += 16) {
-					const float v0 = __ldg(A.mel_val + j), v1 = __ldg(A.mel_val + j + 8);
-					const int c0 = __ldg(A.mel_colp + j), c1 = __ldg(A.mel_colp + j + 8);
-					e0 = fmaf(v0, Pf[c0], e0);
-					e1 = fmaf(v1, Pf[c1], e1);
+				const int j0 = __ldg(A.mel_ptr + b), n = __ldg(A.mel_ptr + b + 1) - j0;
+				const float *v = A.mel_val + j0;
+				const float *Pb = P + ff * PSTR + (n > 0 ? __ldg(A.mel_col + j0) : 0);
+				int i = l8;
+				for (; i + 24 < n; i += 32) {
+					e0 = fmaf(__ldg(v + i), Pb[i], e0);
+					e1 = fmaf(__ldg(v + i + 8), Pb[i + 8], e1);
+					e2 = fmaf(__ldg(v + i + 16), Pb[i + 16], e2);
+					e3 = fmaf(__ldg(v + i + 24), Pb[i + 24], e3);
 				}
-				if (j < j1) e0 = fmaf(__ldg(A.mel_val + j), Pf[__ldg(A.mel_colp + j)], e0);
+				for (; i < n; i += 8) e0 = fmaf(__ldg(v + i), Pb[i], e0);
 			}
-			float e = e0 + e1;
+			float e = (e0 + e1) + (e2 + e3);
 			e += __shfl_xor_sync(0xffffffffu, e, 4);
 			e += __shfl_xor_sync(0xffffffffu, e, 2);
 			e += __shfl_xor_sync(0xffffffffu, e, 1);
@@ -470,6 +471,10 @@ static int build_tables(MfccPlan *p) {
 	std::vector<cpx> tw(M), tw2(M + 1);
 	for (int j = 0; j < M; ++j) tw[j] = cpx{(float)cos(-2.0 * M_PI * j / M), (float)sin(-2.0 * M_PI * j / M)};
 	for (int k = 0; k <= M; ++k) tw2[k] = cpx{(float)cos(-2.0 * M_PI * k / N), (float)sin(-2.0 * M_PI * k / N)};
+	// the fast path reads each band as one contiguous run of bins; true for triangular filters, verified here
+	for (int b = 0; b < nb && p->fast; ++b)
+		for (int j = ptr[b] + 1; j < ptr[b + 1]; ++j)
+			if (col[j] != col[j - 1] + 1) p->fast = false;
 	if (p->fast) {
 		std::vector<cpx> tw1(3 * 256), twA(256);
 		for (int r = 1; r < 4; ++r)
@@ -477,13 +482,10 @@ static int build_tables(MfccPlan *p) {
 				tw1[(r - 1) * 256 + n] = cpx{(float)cos(-2.0 * M_PI * n * r / 1024), (float)sin(-2.0 * M_PI * n * r / 1024)};
 		for (int q2 = 0; q2 < 16; ++q2)
 			for (int u = 0; u < 16; ++u) twA[q2 * 16 + u] = cpx{(float)cos(-2.0 * M_PI * u * q2 / 256), (float)sin(-2.0 * M_PI * u * q2 / 256)};
-		std::vector<int> colp(col.size());
-		for (size_t j = 0; j < col.size(); ++j) colp[j] = (col[j] & 3) * srbfft::FAST_PSTRIDE + (col[j] >> 2);
 		std::vector<int> order(nb);
 		for (int b = 0; b < nb; ++b) order[b] = b;
 		std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return (ptr[a + 1] - ptr[a]) > (ptr[b2 + 1] - ptr[b2]); });
-		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_colp, colp) || to_device(&p->d_mel_order, order))
-			return 1;
+		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_order, order)) return 1;
 	}
 	if (to_device(&p->d_win, win) || to_device(&p->d_win2, win2) || to_device(&p->d_mel_ptr, ptr) ||
 	    to_device(&p->d_mel_col, col) || to_device(&p->d_mel_val, val) || to_device(&p->d_logfloor, logfloor) ||
@@ -525,8 +527,8 @@ MfccPlan *mfcc_plan_create(int fs, double win_ms, double shift_ms, int nfft, int
 		return nullptr;
 	}
 	p->smem = (size_t)2 * p->NF * p->M * sizeof(cpx) + ((size_t)(p->NF - 1) * p->shift + p->L) * sizeof(float);
-	p->smem_fast = (size_t)MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE * sizeof(cpx) + (size_t)MFF_NF * 4 * 256 * sizeof(cpx) +
-	               (size_t)MFF_NF * MFF_YLEN * sizeof(float) + ((size_t)(MFF_NF - 1) * p->shift + p->L) * sizeof(float);
+	p->smem_fast = (size_t)MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE * sizeof(cpx) + (size_t)MFF_NF * 4 * srbfft::FAST_ZSTRIDE * sizeof(cpx) +
+	               (size_t)MFF_NF * MFF_YLEN * sizeof(float);
 	if (p->smem > 200 * 1024 || (p->fast && p->smem_fast > 110 * 1024)) {
 		set_error("mfcc: frame shift %d too large for the shared-memory staging", p->shift);
 		delete p;
@@ -570,7 +572,6 @@ void mfcc_plan_free(MfccPlan *p) {
 	cudaFree(p->d_dct);
 	cudaFree(p->d_tw1);
 	cudaFree(p->d_twA);
-	cudaFree(p->d_mel_colp);
 	cudaFree(p->d_mel_order);
 	delete p;
 }
@@ -672,7 +673,6 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.partials = s->d_partials;
 	a.tw1 = p->d_tw1;
 	a.twA = p->d_twA;
-	a.mel_colp = p->d_mel_colp;
 	a.mel_order = p->d_mel_order;
 	static const bool force_generic = [] { const char *e = getenv("SRB200_MFCC_GENERIC"); return e && e[0] == '1'; }();
 	if (p->fast && !force_generic) mfcc_frames_fast_kernel<<<s->n_cta, MF_THREADS, p->smem_fast, st>>>(a);

@@ -31,8 +31,8 @@ extern "C" int emul_power_spectrum(const float *y, int N, int batch, int n_worke
 }
 
 // replay of the fast path (M = 1024, <= 256 non-zero packed inputs): y = real frames [batch][2048] with zeros
-// beyond 512; Pp = permuted power spectrum [batch][4*257]
-extern "C" void emul_fast_power_spectrum(const float *y, int batch, float *Pp) {
+// beyond 512; P = power spectrum [batch][FAST_PSTRIDE], natural order
+extern "C" void emul_fast_power_spectrum(const float *y, int batch, float *P) {
 	const int N = 2048, M = 1024;
 	std::vector<cpx> tw1(3 * 256), twA(256), tw2(M + 1);
 	for (int r = 1; r < 4; ++r)
@@ -41,12 +41,12 @@ extern "C" void emul_fast_power_spectrum(const float *y, int batch, float *Pp) {
 		for (int u = 0; u < 16; ++u) twA[q2 * 16 + u] = cpx{(float)std::cos(-2.0 * M_PI * u * q2 / 256), (float)std::sin(-2.0 * M_PI * u * q2 / 256)};
 	for (int k = 0; k <= M; ++k) tw2[k] = cpx{(float)std::cos(-2.0 * M_PI * k / N), (float)std::sin(-2.0 * M_PI * k / N)};
 	for (int b = 0; b < batch; ++b) {
-		std::vector<cpx> z(256), T(4 * 16 * FAST_TSTRIDE), Zs(4 * 256);
+		std::vector<cpx> z(256), T(4 * 16 * FAST_TSTRIDE), Zs(4 * FAST_ZSTRIDE);
 		for (int n = 0; n < 256; ++n) z[n] = cpx{y[(size_t)b * N + 2 * n], y[(size_t)b * N + 2 * n + 1]};
 		for (int r = 0; r < 4; ++r)
 			for (int u = 0; u < 16; ++u) fast_step_a(z.data(), tw1.data(), twA.data(), T.data() + r * 16 * FAST_TSTRIDE, r, u);
 		for (int r = 0; r < 4; ++r)
-			for (int u = 0; u < 16; ++u) fast_step_b(T.data() + r * 16 * FAST_TSTRIDE, Zs.data() + r * 256, u);
-		for (int w = 0; w < 64; ++w) fast_power_unpack(Zs.data(), Pp + (size_t)b * 4 * FAST_PSTRIDE, tw2.data(), w, 64);
+			for (int u = 0; u < 16; ++u) fast_step_b(T.data() + r * 16 * FAST_TSTRIDE, Zs.data() + r * FAST_ZSTRIDE, u);
+		for (int w = 0; w < 64; ++w) fast_power_unpack(Zs.data(), P + (size_t)b * FAST_PSTRIDE, tw2.data(), w);
 	}
 }

@@ -34,3 +34,21 @@ def test_power_spectrum_matches_numpy(emul, N, workers):
     emul.emul_power_spectrum(y.ctypes.data_as(fp), N, batch, workers, P.ctypes.data_as(fp))
     ref = np.abs(np.fft.fft(y.astype(np.float64), axis=1)[:, : N // 2 + 1]) ** 2
     assert np.max(np.abs(P - ref) / ref.max(axis=1, keepdims=True)) < 2e-6
+
+
+def test_fast_path_power_spectrum_matches_numpy(emul):
+    """the register-resident fast path (4 x 256-point transforms of the zero-padded 2048-point frame, fft_core.h
+    fast_step_a / fast_step_b / fast_power_unpack) replayed thread by thread"""
+    rng = np.random.default_rng(5)
+    batch = 5
+    y = np.zeros((batch, 2048), np.float32)
+    y[:, :512] = (rng.standard_normal((batch, 512)) * 3000).astype(np.float32)
+    y[1, 300:512] = 0           # shorter frame (8 kHz geometry)
+    y[2, :] = 0                 # digital silence
+    P = np.zeros((batch, 1028), np.float32)
+    fp = C.POINTER(C.c_float)
+    emul.emul_fast_power_spectrum(y.ctypes.data_as(fp), batch, P.ctypes.data_as(fp))
+    ref = np.abs(np.fft.fft(y.astype(np.float64), axis=1)[:, :1025]) ** 2
+    scale = np.maximum(ref.max(axis=1, keepdims=True), 1e-30)
+    assert np.max(np.abs(P[:, :1025] - ref) / scale) < 2e-6
+    assert np.all(P[2, :1025] == 0)
