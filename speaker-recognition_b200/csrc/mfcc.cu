@@ -48,7 +48,7 @@ struct MfccPlan {
 	// fast path (M == 1024, frame length <= 512): register-resident 4 x 256-point transforms
 	bool fast = false;
 	cpx *d_tw1 = nullptr, *d_twA = nullptr;
-	int *d_mel_order = nullptr;
+	int4 *d_mel_desc = nullptr;
 	size_t smem_fast = 0;
 	std::vector<MfccShape> shapes;
 	uint64_t stamp = 0;
@@ -69,7 +69,7 @@ struct MfccArgs {
 	float *ceps;
 	double *partials;
 	const cpx *tw1, *twA;      // fast path tables
-	const int *mel_order;      // bands sorted by non-zero count, descending (balances the 8-lane groups)
+	const int4 *mel_desc;      // fast path: per band, by descending non-zero count: {band, first nz, count, first bin}
 };
 
 __device__ __forceinline__ int find_segment(const int *__restrict__ start, int n, int x) {
@@ -222,25 +222,35 @@ __global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const M
 	const long long s0 = A.smp_off[u_] + (long long)fr0 * A.shift;
 
 	// window then pre-emphasis (MFCC.py:61-64) straight from global memory (each sample is touched by at most four
-	// (frame, tap) pairs of this CTA: L1 serves the repeats); zeros beyond the frame and for absent frames
-	for (int t = tid; t < MFF_NF * MFF_YLEN; t += MF_THREADS) {
-		const int f = t >> 9, i = t & (MFF_YLEN - 1);
-		float y = 0.f;
-		if (f < nfr && i < L) {
-			const long long g = s0 + (long long)f * A.shift + i;
-			float sc, sp = 0.f;
-			if (A.is_f32) {
-				const float *p = reinterpret_cast<const float *>(A.pcm);
-				sc = __ldg(p + g);
-				if (i > 0) sp = __ldg(p + g - 1);
-			} else {
-				const int16_t *p = reinterpret_cast<const int16_t *>(A.pcm);
-				sc = (float)__ldg(p + g);
-				if (i > 0) sp = (float)__ldg(p + g - 1);
+	// (frame, tap) pairs of this CTA: L1 serves the repeats); zeros beyond the frame and for absent frames.
+	// Fully unrolled with the loads hoisted so the 16 global reads of a thread are in flight together.
+	{
+		float sc[8], sp[8];
+#pragma unroll
+		for (int it = 0; it < 8; ++it) {
+			const int ff = it >> 1, i = tid + ((it & 1) << 8);
+			sc[it] = 0.f;
+			sp[it] = 0.f;
+			if (ff < nfr && i < L) {
+				const long long g = s0 + (long long)ff * A.shift + i;
+				if (A.is_f32) {
+					const float *p = reinterpret_cast<const float *>(A.pcm);
+					sc[it] = __ldg(p + g);
+					if (i > 0) sp[it] = __ldg(p + g - 1);
+				} else {
+					const int16_t *p = reinterpret_cast<const int16_t *>(A.pcm);
+					sc[it] = (float)__ldg(p + g);
+					if (i > 0) sp[it] = (float)__ldg(p + g - 1);
+				}
 			}
-			y = fmaf(-__ldg(A.win2 + i), sp, __ldg(A.win + i) * sc);
 		}
-		ybuf[t] = y;
+		const float w0 = tid < L ? __ldg(A.win + tid) : 0.f, w1 = tid + 256 < L ? __ldg(A.win + tid + 256) : 0.f;
+		const float v0 = tid < L ? __ldg(A.win2 + tid) : 0.f, v1 = tid + 256 < L ? __ldg(A.win2 + tid + 256) : 0.f;
+#pragma unroll
+		for (int it = 0; it < 8; ++it) {
+			const float w = (it & 1) ? w1 : w0, v = (it & 1) ? v1 : v0;
+			ybuf[(it >> 1) * MFF_YLEN + tid + ((it & 1) << 8)] = fmaf(-v, sp[it], w * sc[it]);
+		}
 	}
 	__syncthreads();
 	const int f = tid >> 6, r = (tid >> 4) & 3, u = tid & 15;
@@ -262,30 +272,36 @@ __global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const M
 	{
 		const int group = tid >> 3, l8 = tid & 7;
 		const int items = MFF_NF * nb;
-		for (int it = 0; it * 32 < items; ++it) {
-			const int item = it * 32 + group;
-			const bool valid = item < items;
-			const int ff = item & (MFF_NF - 1);
-			const int b = valid ? __ldg(A.mel_order + (item >> 2)) : 0;
-			float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-			if (valid) {
-				const int j0 = __ldg(A.mel_ptr + b), n = __ldg(A.mel_ptr + b + 1) - j0;
-				const float *v = A.mel_val + j0;
-				const float *Pb = P + ff * PSTR + (n > 0 ? __ldg(A.mel_col + j0) : 0);
-				int i = l8;
-				for (; i + 24 < n; i += 32) {
-					e0 = fmaf(__ldg(v + i), Pb[i], e0);
-					e1 = fmaf(__ldg(v + i + 8), Pb[i + 8], e1);
-					e2 = fmaf(__ldg(v + i + 16), Pb[i + 16], e2);
-					e3 = fmaf(__ldg(v + i + 24), Pb[i + 24], e3);
-				}
-				for (; i < n; i += 8) e0 = fmaf(__ldg(v + i), Pb[i], e0);
+		// mel_desc[rank] = {band, first non-zero j0, count n, first bin c0}: one 128-bit load per item, and two items of
+		// a group are kept in flight (independent chains) to overlap the load / shuffle latencies
+		for (int it = 0; it * 64 < items; ++it) {
+			const int itemA = it * 64 + group, itemB = itemA + 32;
+			const bool vA = itemA < items, vB = itemB < items;
+			const int4 dA = vA ? __ldg(A.mel_desc + (itemA >> 2)) : make_int4(0, 0, 0, 0);
+			const int4 dB = vB ? __ldg(A.mel_desc + (itemB >> 2)) : make_int4(0, 0, 0, 0);
+			const float *vAp = A.mel_val + dA.y, *vBp = A.mel_val + dB.y;
+			const float *PA = P + (itemA & (MFF_NF - 1)) * PSTR + dA.w, *PB = P + (itemB & (MFF_NF - 1)) * PSTR + dB.w;
+			float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+			const int nA = dA.z, nB = dB.z, nmax = nA > nB ? nA : nB;
+			for (int i = l8; i < nmax; i += 16) {
+				const float va0 = i < nA ? __ldg(vAp + i) : 0.f, va1 = i + 8 < nA ? __ldg(vAp + i + 8) : 0.f;
+				const float vb0 = i < nB ? __ldg(vBp + i) : 0.f, vb1 = i + 8 < nB ? __ldg(vBp + i + 8) : 0.f;
+				const float pa0 = i < nA ? PA[i] : 0.f, pa1 = i + 8 < nA ? PA[i + 8] : 0.f;
+				const float pb0 = i < nB ? PB[i] : 0.f, pb1 = i + 8 < nB ? PB[i + 8] : 0.f;
+				a0 = fmaf(va0, pa0, a0);
+				a1 = fmaf(va1, pa1, a1);
+				b0 = fmaf(vb0, pb0, b0);
+				b1 = fmaf(vb1, pb1, b1);
 			}
-			float e = (e0 + e1) + (e2 + e3);
-			e += __shfl_xor_sync(0xffffffffu, e, 4);
-			e += __shfl_xor_sync(0xffffffffu, e, 2);
-			e += __shfl_xor_sync(0xffffffffu, e, 1);
-			if (valid && l8 == 0) logE[ff * nb + b] = e > 0.f ? logf(e) : __ldg(A.logfloor + b);
+			float ea = a0 + a1, eb = b0 + b1;
+			ea += __shfl_xor_sync(0xffffffffu, ea, 4);
+			eb += __shfl_xor_sync(0xffffffffu, eb, 4);
+			ea += __shfl_xor_sync(0xffffffffu, ea, 2);
+			eb += __shfl_xor_sync(0xffffffffu, eb, 2);
+			ea += __shfl_xor_sync(0xffffffffu, ea, 1);
+			eb += __shfl_xor_sync(0xffffffffu, eb, 1);
+			if (vA && l8 == 0) logE[(itemA & (MFF_NF - 1)) * nb + dA.x] = ea > 0.f ? logf(ea) : __ldg(A.logfloor + dA.x);
+			if (vB && l8 == 1) logE[(itemB & (MFF_NF - 1)) * nb + dB.x] = eb > 0.f ? logf(eb) : __ldg(A.logfloor + dB.x);
 		}
 	}
 	__syncthreads();
@@ -485,7 +501,12 @@ static int build_tables(MfccPlan *p) {
 		std::vector<int> order(nb);
 		for (int b = 0; b < nb; ++b) order[b] = b;
 		std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return (ptr[a + 1] - ptr[a]) > (ptr[b2 + 1] - ptr[b2]); });
-		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_order, order)) return 1;
+		std::vector<int4> desc(nb);
+		for (int rk = 0; rk < nb; ++rk) {
+			const int b = order[rk], n = ptr[b + 1] - ptr[b];
+			desc[rk] = make_int4(b, ptr[b], n, n > 0 ? col[ptr[b]] : 0);
+		}
+		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_desc, desc)) return 1;
 	}
 	if (to_device(&p->d_win, win) || to_device(&p->d_win2, win2) || to_device(&p->d_mel_ptr, ptr) ||
 	    to_device(&p->d_mel_col, col) || to_device(&p->d_mel_val, val) || to_device(&p->d_logfloor, logfloor) ||
@@ -572,7 +593,7 @@ void mfcc_plan_free(MfccPlan *p) {
 	cudaFree(p->d_dct);
 	cudaFree(p->d_tw1);
 	cudaFree(p->d_twA);
-	cudaFree(p->d_mel_order);
+	cudaFree(p->d_mel_desc);
 	delete p;
 }
 
@@ -673,7 +694,7 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.partials = s->d_partials;
 	a.tw1 = p->d_tw1;
 	a.twA = p->d_twA;
-	a.mel_order = p->d_mel_order;
+	a.mel_desc = p->d_mel_desc;
 	static const bool force_generic = [] { const char *e = getenv("SRB200_MFCC_GENERIC"); return e && e[0] == '1'; }();
 	if (p->fast && !force_generic) mfcc_frames_fast_kernel<<<s->n_cta, MF_THREADS, p->smem_fast, st>>>(a);
 	else mfcc_frames_kernel<<<s->n_cta, MF_THREADS, p->smem, st>>>(a);
