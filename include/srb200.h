@@ -145,6 +145,31 @@ int srb200_mfcc_extract_dev(srb200_mfcc *plan, const int16_t *d_pcm, const long 
                             float *d_feat, int ld, int *feat_off, void *stream);
 long long srb200_mfcc_rows_total(srb200_mfcc *plan, const long long *smp_off, int n_utt, int nd);
 
+/* ------------------------------------------------------------------------------------------------
+ * LPC features (replaces LPCExtractor.extract, src/feature/LPC.py:40-57: per frame, coefficients 1..n_lpc of the
+ * autocorrelation-method linear predictor, i.e. scikits.talkbox lpc(frame, n_lpc)[0][1:]; same window and
+ * pre-emphasis as the MFCC front-end).  The frame geometry (fs, win_length_ms, win_shift_ms, pre-emphasis) is taken
+ * from the plan; n_lpc <= 31.  One output row per frame, no normalisation (the reference applies none).
+ * ---------------------------------------------------------------------------------------------- */
+int srb200_lpc_extract_i16(srb200_mfcc *plan, const int16_t *pcm, long long n_samples, int n_lpc, double *out, int *rows_out);
+int srb200_lpc_extract_f32(srb200_mfcc *plan, const float *pcm, long long n_samples, int n_lpc, double *out, int *rows_out);
+int srb200_lpc_extract_f64(srb200_mfcc *plan, const double *pcm, long long n_samples, int n_lpc, double *out, int *rows_out);
+/* device PCM for B utterances; writes columns [col_off, col_off + n_lpc) of d_feat rows (row = frame, packed utterance
+ * after utterance): call after srb200_mfcc_extract_dev(nd = 0) on the same buffer to build mix_feature = MFCC || LPC
+ * (src/feature/__init__.py:25-30) without leaving the device. */
+int srb200_lpc_extract_dev(srb200_mfcc *plan, const int16_t *d_pcm, const long long *smp_off, int n_utt, int n_lpc,
+                           float *d_feat, int ld, int col_off, int *feat_off, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Energy-based silence removal (replaces remove_silence, src/filters/silence.py:11-50).  Integer arithmetic:
+ * results are bit-exact with the reference.  frame_duration = 0.02, frame_shift = 0.01, perc = 0.15 are the
+ * reference defaults.  out must hold n_samples elements; *n_out receives the kept length.
+ * ---------------------------------------------------------------------------------------------- */
+int srb200_remove_silence_i16(int fs, const int16_t *pcm, long long n_samples, double frame_duration, double frame_shift, double perc,
+                              int16_t *out, long long *n_out);
+int srb200_remove_silence_u8(int fs, const uint8_t *pcm, long long n_samples, double frame_duration, double frame_shift, double perc,
+                             uint8_t *out, long long *n_out);
+
 #ifdef __cplusplus
 }
 #endif

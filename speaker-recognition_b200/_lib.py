@@ -81,6 +81,12 @@ PROTOTYPES = {
     "srb200_mfcc_extract_f64": (_ci, [_vp, _dp, _cll, _ci, _ci, _dp, _ip]),
     "srb200_mfcc_extract_dev": (_ci, [_vp, _vp, _llp, _ci, _ci, _vp, _ci, _ip, _vp]),
     "srb200_mfcc_rows_total": (_cll, [_vp, _llp, _ci, _ci]),
+    "srb200_lpc_extract_i16": (_ci, [_vp, _i16p, _cll, _ci, _dp, _ip]),
+    "srb200_lpc_extract_f32": (_ci, [_vp, _fp, _cll, _ci, _dp, _ip]),
+    "srb200_lpc_extract_f64": (_ci, [_vp, _dp, _cll, _ci, _dp, _ip]),
+    "srb200_lpc_extract_dev": (_ci, [_vp, _vp, _llp, _ci, _ci, _vp, _ci, _ci, _ip, _vp]),
+    "srb200_remove_silence_i16": (_ci, [_ci, _i16p, _cll, _cd, _cd, _cd, _i16p, _llp]),
+    "srb200_remove_silence_u8": (_ci, [_ci, C.POINTER(C.c_uint8), _cll, _cd, _cd, _cd, C.POINTER(C.c_uint8), _llp]),
 }
 
 

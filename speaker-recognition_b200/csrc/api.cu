@@ -908,4 +908,96 @@ int srb200_mfcc_extract_dev(srb200_mfcc *h, const int16_t *d_pcm, const long lon
 	return launch_mfcc(h->plan, d_pcm, 0, smp_off, n_utt, nd, 1, d_feat, ld, feat_off, (cudaStream_t)stream);
 }
 
+
+// ---- LPC ----
+static int lpc_extract_host(srb200_mfcc *h, const void *pcm, int kind, long long n, int n_lpc, double *out, int *rows_out) {
+	SRB_REQUIRE(h && pcm && out, "lpc_extract: null argument");
+	SRB_REQUIRE(n > 0 && n < (1LL << 31), "lpc_extract: bad sample count %lld", n);
+	Context &c = ctx();
+	if (c.init()) return 1;
+	const size_t esz = kind == 0 ? 2 : 4;
+	if (c.h_pcm.ensure((size_t)n * esz) || c.d_pcm.ensure((size_t)n * esz)) return 1;
+	if (kind == 2) {
+		float *dst = c.h_pcm.as<float>();
+		const double *srcp = (const double *)pcm;
+		for (long long i = 0; i < n; ++i) dst[i] = (float)srcp[i];
+	} else
+		memcpy(c.h_pcm.p, pcm, (size_t)n * esz);
+	SRB_CUDA(cudaMemcpyAsync(c.d_pcm.p, c.h_pcm.p, (size_t)n * esz, cudaMemcpyHostToDevice, c.stream));
+	const int rows = srb200_mfcc_num_frames(h, n);
+	SRB_REQUIRE(rows >= 1, "lpc_extract: signal shorter than one frame");
+	const int ld = (n_lpc + 3) & ~3;
+	const long long smp_off[2] = {0, n};
+	int feat_off[2];
+	if (c.d_feat.ensure((size_t)rows * ld * sizeof(float))) return 1;
+	SRB_CUDA(cudaMemsetAsync(c.d_feat.p, 0, (size_t)rows * ld * sizeof(float), c.stream));
+	if (launch_lpc_for_plan(h->plan, c.d_pcm.p, kind != 0, smp_off, 1, n_lpc, c.d_feat.as<float>(), ld, 0, feat_off, c.stream)) return 1;
+	if (c.h_out.ensure((size_t)rows * ld * sizeof(float))) return 1;
+	SRB_CUDA(cudaMemcpyAsync(c.h_out.p, c.d_feat.p, (size_t)rows * ld * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+	SRB_CUDA(cudaStreamSynchronize(c.stream));
+	const float *src = c.h_out.as<float>();
+	for (int r = 0; r < rows; ++r)
+		for (int j = 0; j < n_lpc; ++j) out[(size_t)r * n_lpc + j] = (double)src[(size_t)r * ld + j];
+	if (rows_out) *rows_out = rows;
+	return 0;
+}
+int srb200_lpc_extract_i16(srb200_mfcc *h, const int16_t *pcm, long long n, int n_lpc, double *out, int *rows_out) {
+	API_ENTER();
+	return lpc_extract_host(h, pcm, 0, n, n_lpc, out, rows_out);
+}
+int srb200_lpc_extract_f32(srb200_mfcc *h, const float *pcm, long long n, int n_lpc, double *out, int *rows_out) {
+	API_ENTER();
+	return lpc_extract_host(h, pcm, 1, n, n_lpc, out, rows_out);
+}
+int srb200_lpc_extract_f64(srb200_mfcc *h, const double *pcm, long long n, int n_lpc, double *out, int *rows_out) {
+	API_ENTER();
+	return lpc_extract_host(h, pcm, 2, n, n_lpc, out, rows_out);
+}
+int srb200_lpc_extract_dev(srb200_mfcc *h, const int16_t *d_pcm, const long long *smp_off, int n_utt, int n_lpc, float *d_feat, int ld,
+                           int col_off, int *feat_off, void *stream) {
+	API_ENTER();
+	SRB_REQUIRE(h && d_pcm && smp_off && d_feat, "lpc_extract_dev: null argument");
+	return launch_lpc_for_plan(h->plan, d_pcm, 0, smp_off, n_utt, n_lpc, d_feat, ld, col_off, feat_off, (cudaStream_t)stream);
+}
+
+
+// ---- silence removal ----
+static int remove_silence_host(int fs, const void *pcm, int is_u8, long long n, double frame_duration, double frame_shift, double perc,
+                               void *out, long long *n_out) {
+	SRB_REQUIRE(pcm && out && n_out, "remove_silence: null argument");
+	SRB_REQUIRE(n >= 1 && n < (1LL << 40), "remove_silence: bad sample count %lld", n);
+	Context &c = ctx();
+	if (c.init()) return 1;
+	const int frame_len = (int)(frame_duration * fs), shift_len = (int)(frame_shift * fs);     // silence.py:23-24
+	SRB_REQUIRE(frame_len >= 1 && shift_len >= 1, "remove_silence: frame length/shift below one sample at fs=%d", fs);
+	const size_t esz = is_u8 ? 1 : 2;
+	const size_t nb = (size_t)((n + 1023) / 1024), nseg = (size_t)(n / shift_len + 2);
+	if (c.h_pcm.ensure((size_t)n * esz) || c.d_pcm.ensure((size_t)n * esz) || c.d_out.ensure((size_t)n * esz) ||
+	    c.d_misc.ensure(((size_t)n + 1 + nb + 2) * sizeof(long long) + nseg * sizeof(longlong3) + 64))
+		return 1;
+	memcpy(c.h_pcm.p, pcm, (size_t)n * esz);
+	SRB_CUDA(cudaMemcpyAsync(c.d_pcm.p, c.h_pcm.p, (size_t)n * esz, cudaMemcpyHostToDevice, c.stream));
+	long long *d_ps = c.d_misc.as<long long>();
+	long long *d_block = d_ps + n + 1;
+	long long *d_counts = d_block + nb;
+	longlong3 *d_segs = reinterpret_cast<longlong3 *>(d_counts + 2);
+	if (launch_remove_silence(c.d_pcm.p, is_u8, n, frame_len, shift_len, perc, d_ps, d_block, d_segs, d_counts, c.d_out.p, c.stream)) return 1;
+	long long counts[2] = {0, 0};
+	SRB_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, c.stream));
+	SRB_CUDA(cudaStreamSynchronize(c.stream));
+	if (counts[1] > 0) SRB_CUDA(cudaMemcpy(out, c.d_out.p, (size_t)counts[1] * esz, cudaMemcpyDeviceToHost));
+	*n_out = counts[1];
+	return 0;
+}
+int srb200_remove_silence_i16(int fs, const int16_t *pcm, long long n, double frame_duration, double frame_shift, double perc, int16_t *out,
+                              long long *n_out) {
+	API_ENTER();
+	return remove_silence_host(fs, pcm, 0, n, frame_duration, frame_shift, perc, out, n_out);
+}
+int srb200_remove_silence_u8(int fs, const uint8_t *pcm, long long n, double frame_duration, double frame_shift, double perc, uint8_t *out,
+                             long long *n_out) {
+	API_ENTER();
+	return remove_silence_host(fs, pcm, 1, n, frame_duration, frame_shift, perc, out, n_out);
+}
+
 }  // extern "C"

@@ -35,4 +35,15 @@ int mfcc_n_ceps(const MfccPlan *p);
 int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp_off, int n_utt, int nd, int cmvn,
                 float *d_feat, int ld, int *feat_off, cudaStream_t st);
 
+// ---- lpc.cu (driven through the MFCC plan, which owns the frame geometry and the float64 window) ----
+int launch_lpc(const double *d_win, const double *d_win2, int L, int shift, const void *d_pcm, int is_f32, const long long *d_smp_off,
+               const int *d_frame_off, int n_utt, int frames_total, int order, float *d_out, int ld, int col_off, cudaStream_t st);
+// features = LPC coefficients 1..order of every frame, written to columns [col_off, col_off+order) of d_out rows
+int launch_lpc_for_plan(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp_off, int n_utt, int order, float *d_out,
+                        int ld, int col_off, int *feat_off, cudaStream_t st);
+
+// ---- silence.cu ----
+int launch_remove_silence(const void *d_pcm, int is_u8, long long n, int frame_len, int shift_len, double perc, long long *d_ps,
+                          long long *d_block, longlong3 *d_segs, long long *d_counts, void *d_out, cudaStream_t st);
+
 }  // namespace srb

@@ -45,6 +45,7 @@ struct MfccPlan {
 	cpx *d_tw = nullptr, *d_tw2 = nullptr;
 	int *d_mel_ptr = nullptr, *d_mel_col = nullptr;
 	double *d_dct = nullptr;
+	double *d_win_d = nullptr, *d_win2_d = nullptr;   // float64 window / pre-emphasised window (LPC path)
 	// fast path (M == 1024, frame length <= 512): register-resident 4 x 256-point transforms
 	bool fast = false;
 	cpx *d_tw1 = nullptr, *d_twA = nullptr;
@@ -422,10 +423,13 @@ static int build_tables(MfccPlan *p) {
 	std::vector<float> win(L), win2(L);
 	std::vector<double> w(L);
 	for (int i = 0; i < L; ++i) w[i] = 0.54 - 0.46 * cos(2 * M_PI / L * (i + 0.5));
+	std::vector<double> w2(L);
 	for (int i = 0; i < L; ++i) {
 		win[i] = (float)w[i];
 		win2[i] = i > 0 ? (float)(p->pre * w[i - 1]) : 0.f;
+		w2[i] = i > 0 ? p->pre * w[i - 1] : 0.0;
 	}
+	if (to_device(&p->d_win_d, w) || to_device(&p->d_win2_d, w2)) return 1;
 	// mel filterbank, MFCC.py:81-105
 	const double f0 = 700.0 / p->fs;
 	const int fn2 = N / 2;
@@ -591,6 +595,8 @@ void mfcc_plan_free(MfccPlan *p) {
 	cudaFree(p->d_mel_ptr);
 	cudaFree(p->d_mel_col);
 	cudaFree(p->d_dct);
+	cudaFree(p->d_win_d);
+	cudaFree(p->d_win2_d);
 	cudaFree(p->d_tw1);
 	cudaFree(p->d_twA);
 	cudaFree(p->d_mel_desc);
@@ -708,6 +714,19 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	mfcc_norm_kernel<<<blocks, 256, 0, st>>>(s->d_ceps, p->CL, s->d_stats, s->d_frame_off, s->d_feat_off, n_utt, p->nc, nd, cmvn,
 	                                        d_feat, ld, total);
 	SRB_CUDA(cudaGetLastError());
+	if (feat_off) memcpy(feat_off, s->feat_off.data(), sizeof(int) * (n_utt + 1));
+	return 0;
+}
+
+int launch_lpc_for_plan(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp_off, int n_utt, int order, float *d_out,
+                        int ld, int col_off, int *feat_off, cudaStream_t st) {
+	SRB_REQUIRE(p != nullptr, "lpc: null plan");
+	SRB_REQUIRE(n_utt >= 1, "lpc: no utterances");
+	MfccShape *s = nullptr;
+	if (get_shape(p, smp_off, n_utt, 0, st, &s)) return 1;      // nd = 0: one output row per frame
+	if (launch_lpc(p->d_win_d, p->d_win2_d, p->L, p->shift, d_pcm, is_f32, s->d_smp_off, s->d_frame_off, n_utt, s->frames_total, order,
+	               d_out, ld, col_off, st))
+		return 1;
 	if (feat_off) memcpy(feat_off, s->feat_off.data(), sizeof(int) * (n_utt + 1));
 	return 0;
 }

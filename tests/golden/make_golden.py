@@ -142,6 +142,50 @@ def gen_gmm():
     print("gmm_ref.npz keys:", len(flat))
 
 
+def gen_lpc():
+    """LPC: the reference's feature path (src/feature/LPC.py:46-57) with its talkbox call replaced by the reference repo's
+    own prototype of the same algorithm, src/lpcc/lpc_jp.py:13-66 (autocorr + LevinsonDurbin), exec'd from the tree.
+    (talkbox itself is third-party and absent; lpc_jp.py imports it and pylab at module level, so only the two function
+    definitions are compiled out of the file's AST.)"""
+    import ast
+    MFCC, _ = load_reference_mfcc()
+    with open(os.path.join(REF, "src/lpcc/lpc_jp.py")) as f:
+        src = f.read()
+    src = src[:src.index('if __name__ == "__main__":')]          # the script part below is Python 2 (print statements)
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("autocorr", "LevinsonDurbin")]
+    assert len(keep) == 2
+    ns = {"np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "ref:lpcc/lpc_jp.py", "exec"), ns)
+    flat = {}
+    for name, fs, n, seed, kw in [("lpc_16k", 16000, 12000, 31, dict(win_length_ms=32, win_shift_ms=16, n_lpc=15, pre_emphasis_coef=0.95)),
+                                  ("lpc_8k_o10", 8000, 5000, 32, dict(win_length_ms=32, win_shift_ms=16, n_lpc=10, pre_emphasis_coef=0.95))]:
+        sig = synth.audio(n, seed=seed, fs=fs)
+        flen = int(float(kw["win_length_ms"]) / 1000 * fs)
+        fshift = int(float(kw["win_shift_ms"]) / 1000 * fs)
+        window = MFCC.hamming(flen)
+        x = np.asarray(sig, dtype=float)
+        frames = (len(x) - flen) // fshift + 1                      # LPC.py:47
+        out = []
+        for f in range(frames):
+            frame = x[f * fshift: f * fshift + flen] * window       # LPC.py:50-51
+            frame[1:] -= frame[:-1] * kw["pre_emphasis_coef"]       # LPC.py:53
+            r = ns["autocorr"](frame, kw["n_lpc"] + 1)
+            a, _e = ns["LevinsonDurbin"](r, kw["n_lpc"])
+            out.append(a[1:])                                       # LPC.py:41-42  lpc[1:]
+        flat[name + "/fs"] = np.int64(fs)
+        flat[name + "/signal"] = sig
+        flat[name + "/out"] = np.array(out)
+        flat[name + "/kwargs"] = np.array(repr(kw))
+    np.savez_compressed(os.path.join(HERE, "lpc_ref.npz"), **flat)
+    print("lpc_ref.npz:", {k: v.shape for k, v in flat.items() if k.endswith("/out")})
+
+
 if __name__ == "__main__":
-    gen_mfcc()
-    gen_gmm()
+    which = sys.argv[1:] or ["mfcc", "gmm", "lpc"]
+    if "mfcc" in which:
+        gen_mfcc()
+    if "gmm" in which:
+        gen_gmm()
+    if "lpc" in which:
+        gen_lpc()

@@ -156,3 +156,15 @@ def test_live_shipped_model_text_load_agrees(golden_gmm):
     w, m, s = gmm_ref.load_model("/root/reference/src/gui/model/ubm.mixture-32.utt-300.model")
     c = golden_gmm.case("ubm32")
     assert np.array_equal(w, c["w"]) and np.array_equal(m, c["mean"]) and np.array_equal(s, c["sigma"])
+
+
+@pytest.mark.parametrize("case", ["lpc_16k", "lpc_8k_o10"])
+def test_lpc_oracle_matches_reference_prototype_fixture(case):
+    """oracle/lpc_ref.py (talkbox's published algorithm) vs the fixture produced by the reference repo's own prototype
+    src/lpcc/lpc_jp.py (autocorr + LevinsonDurbin) on the reference's LPC framing (LPC.py:46-57)"""
+    from oracle import lpc_ref
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lpc_ref.npz"))
+    kw = ast.literal_eval(str(z[case + "/kwargs"]))
+    got = lpc_ref.extract(int(z[case + "/fs"]), z[case + "/signal"], **kw)
+    assert got.shape == z[case + "/out"].shape
+    assert np.max(np.abs(got - z[case + "/out"])) < 1e-11

@@ -1,5 +1,7 @@
 """End-to-end drop-in test: the reference's facade (ModelInterface.enroll/train/predict, src/gui/interface.py) on
 synthetic speakers, with the float64 oracle pipeline as the checker for the predicted labels."""
+import os
+
 import numpy as np
 import pytest
 
@@ -89,3 +91,26 @@ def test_streaming_predictor_equals_window_predict():
         feat = MFCC.extract(16000, win, nd=2)
         assert feat.shape == (90, 39)
         assert int(out[b]) == int(np.argmax(gs.predict_one_scores(feat)))
+
+
+def test_cli_enroll_and_predict(tmp_path, capsys):
+    """speaker-recognition.py -t enroll / -t predict on wav files written to disk (src/speaker-recognition.py:52-90)"""
+    from scipy.io import wavfile
+    from speaker_recognition_b200 import cli
+    names = ["alice", "bert", "carol"]
+    for i, nm in enumerate(names):
+        d = tmp_path / "train" / nm
+        d.mkdir(parents=True)
+        for k in range(2):
+            wavfile.write(str(d / ("%d.wav" % k)), 16000, speaker_audio(i + 10, 4, k))
+    test_dir = tmp_path / "test"
+    test_dir.mkdir()
+    for i, nm in enumerate(names):
+        wavfile.write(str(test_dir / ("%s_x.wav" % nm)), 16000, speaker_audio(i + 10, 4, 1)[4000:52000])
+    model = str(tmp_path / "model.out")
+    cli.main(["-t", "enroll", "-i", "%s/train/*" % tmp_path, "-m", model])
+    out = cli.task_predict(str(test_dir / "*.wav"), model)
+    assert len(out) == 3
+    for f, label in out:
+        assert os.path.basename(f).split("_")[0] == label
+    assert "->" in capsys.readouterr().out
