@@ -277,8 +277,14 @@ def main():
         flops_alg = 3.0 * DIM * T * S_SPK * K_MIX                   # survey convention: sub, mul, mul-add per dim
         fma_issued = 2.0 * DIM * T * S_SPK * K_MIX                   # what the kernel issues: 2 FFMA per (frame, mixture, dim)
         sec = score_ms * 1e-3
+        traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tpath):
+            tj = json.load(open(tpath)).get("gmm_score_kernel", {})
+            if tj.get("utts") == B and tj.get("speakers") == S_SPK and tj.get("mixtures") == K_MIX:
+                traffic = tj.get("dram_bytes")
         roofline = {"bound": "hbm", "kernel": "gmm_score_kernel", "achieved": bytes_alg / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": bytes_alg / sec / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": bytes_alg / sec / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "ms_per_launch": score_ms, "algorithmic_bytes": bytes_alg,
                     "note": "scoring is bound by the fp32 FMA pipe (~2700 flop/B at C2), not HBM; see roofline_fma"}
         fma = {"bound": "fp32_fma", "kernel": "gmm_score_kernel", "unit": "TFLOP/s",

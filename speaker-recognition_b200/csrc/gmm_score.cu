@@ -12,7 +12,9 @@
 //   log2 p(x) = log2 sum_k 2^(-acc_k)    via an online max/sum over 32-row mixture tiles
 // One CTA = 128 threads = 4 warps owns a tile of 256 frames (x tile transposed in shared memory for the whole
 // CTA lifetime) and walks the packed parameter tiles of its speaker chunk, which a single elected thread streams
-// with cp.async.bulk (TMA engine) into a 3-stage mbarrier ring.  Each thread keeps an 8-frame x 8-mixture
+// with cp.async.bulk (TMA engine) into a 3-stage full/empty mbarrier ring (no CTA-wide barrier in the tile loop: warps
+// drift by up to two tiles, which keeps the FMA pipe of every SM sub-partition busy while a sibling warp is in its
+// log-sum-exp epilogue).  Each thread keeps an 8-frame x 8-mixture
 // register tile: per dimension 2 LDS.128 (frames) + 4 LDS.128 (broadcast parameters) feed 128 FFMA.
 // The kernel is bound by the fp32 FMA pipe (2*D FFMA per frame-mixture pair); HBM traffic is the x tile once
 // and the parameters from L2 (DESIGN.md "roofline").
@@ -67,8 +69,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 	const int tileF = 64 * D + 32;
 	float *xs = reinterpret_cast<float *>(smem_raw);                  // [D][256]
 	float *ps = xs + (size_t)D * SC_FT;                               // [STAGES][tileF]
-	uint64_t *bars = reinterpret_cast<uint64_t *>(ps + (size_t)SC_STAGES * tileF);
-	double *red = reinterpret_cast<double *>(bars + SC_STAGES);       // [2][WARPS]
+	uint64_t *bars = reinterpret_cast<uint64_t *>(ps + (size_t)SC_STAGES * tileF);   // full[STAGES] then empty[STAGES]
+	uint64_t *empty = bars + SC_STAGES;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int g = lane >> 2, q = lane & 3;
@@ -81,7 +83,10 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 	const uint32_t tile_bytes = (uint32_t)tileF * 4u;
 
 	if (tid == 0) {
-		for (int s = 0; s < SC_STAGES; ++s) mbar_init(&bars[s], 1);
+		for (int s = 0; s < SC_STAGES; ++s) {
+			mbar_init(&bars[s], 1);
+			mbar_init(&empty[s], WARPS);
+		}
 		fence_mbar_init();
 	}
 	__syncthreads();
@@ -235,24 +240,22 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 				m_run[f] = -3.0e38f;
 				s_run[f] = 0.f;
 			}
-			// sum over the 8 frame groups of the warp (lanes with equal q hold identical values)
+			// sum over the 8 frame groups of the warp (lanes with equal q hold identical values); one partial per warp
 #pragma unroll
 			for (int off = 4; off <= 16; off <<= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-			if (lane == 0) red[(spk & 1) * WARPS + warp] = local;
+			if (lane == 0) A.partial[((size_t)blockIdx.x * A.S + spk) * WARPS + warp] = local;
 		}
-		__syncthreads();   // every warp is done with this stage (and red[] is visible)
-		if (tid == 0) {
-			if (spk_done) {
-				const double *r = red + (spk & 1) * WARPS;
-				double tot = 0.0;
-#pragma unroll
-				for (int w = 0; w < WARPS; ++w) tot += r[w];
-				A.partial[(size_t)blockIdx.x * A.S + spk] = tot;
-			}
-			const int nxt = it + SC_STAGES;
+		// this warp is done with the stage: release it; the elected producer refills the stage of the PREVIOUS tile
+		// (which every warp has left by now, so the wait below almost never blocks) with the tile two ahead
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&empty[stage]);
+		if (tid == 0 && it >= 1) {
+			const int prev = it - 1, nxt = prev + SC_STAGES;
 			if (nxt < n_tiles) {
-				mbar_expect_tx(&bars[stage], tile_bytes);
-				bulk_g2s(ps + (size_t)stage * tileF, gt0 + (size_t)nxt * tileF, tile_bytes, &bars[stage]);
+				const int pstg = prev % SC_STAGES;
+				mbar_wait(&empty[pstg], (uint32_t)((prev / SC_STAGES) & 1));
+				mbar_expect_tx(&bars[pstg], tile_bytes);
+				bulk_g2s(ps + (size_t)pstg * tileF, gt0 + (size_t)nxt * tileF, tile_bytes, &bars[pstg]);
 			}
 		}
 		if (spk_done) {
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 }
 
 // sums[u][s] = sum over the frame tiles of utterance u (deterministic order); best[u] = first argmax_s
-__global__ void score_reduce_kernel(const double *__restrict__ partial, const int *__restrict__ utt_tile_start, int S,
+__global__ void score_reduce_kernel(const double *__restrict__ partial, const int *__restrict__ utt_tile_start, int S, int parts,
                                     double *__restrict__ sums, int *__restrict__ best) {
 	const int u = blockIdx.x;
 	const int t0 = utt_tile_start[u], t1 = utt_tile_start[u + 1];
@@ -273,7 +276,8 @@ __global__ void score_reduce_kernel(const double *__restrict__ partial, const in
 	int besti = 0x7fffffff;
 	for (int s = threadIdx.x; s < S; s += blockDim.x) {
 		double acc = 0.0;
-		for (int t = t0; t < t1; ++t) acc += partial[(size_t)t * S + s];
+		for (int t = t0; t < t1; ++t)
+			for (int w = 0; w < parts; ++w) acc += partial[((size_t)t * S + s) * parts + w];
 		sums[(size_t)u * S + s] = acc;
 		if (acc > bestv) {   // strict: keeps the first maximum within a thread's ascending s sequence
 			bestv = acc;
@@ -357,7 +361,7 @@ static int get_table(const int *utt_off, int n_utt, int S, int FT, cudaStream_t 
 	const size_t nft = ft.size() ? ft.size() : 1;
 	SRB_CUDA(cudaMalloc(&t.d_ftiles, nft * sizeof(int4)));
 	SRB_CUDA(cudaMalloc(&t.d_utt_tile_start, (size_t)(n_utt + 1) * sizeof(int)));
-	SRB_CUDA(cudaMalloc(&t.d_partial, nft * (size_t)S * sizeof(double)));
+	SRB_CUDA(cudaMalloc(&t.d_partial, nft * (size_t)S * SC_MAX_WARPS * sizeof(double)));
 	if (!ft.empty()) SRB_CUDA(cudaMemcpyAsync(t.d_ftiles, ft.data(), ft.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
 	SRB_CUDA(cudaMemcpyAsync(t.d_utt_tile_start, uts.data(), uts.size() * sizeof(int), cudaMemcpyHostToDevice, st));
 	SRB_CUDA(cudaStreamSynchronize(st));   // the source vectors die with this scope
@@ -388,7 +392,7 @@ static int choose_spk_per_chunk(int n_ftiles, int S, int ctas_per_wave) {
 }
 
 static size_t score_smem_bytes(int D, int FT) {
-	return (size_t)D * FT * 4 + (size_t)SC_STAGES * tile_floats(D) * 4 + SC_STAGES * 8 + 2 * SC_MAX_WARPS * 8;
+	return (size_t)D * FT * 4 + (size_t)SC_STAGES * tile_floats(D) * 4 + 2 * SC_STAGES * 8;
 }
 
 static bool g_score_attr_set = false;
@@ -447,7 +451,7 @@ int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const i
 		else gmm_score_kernel<true, 4><<<grid, 128, smem, st>>>(a);
 		SRB_CUDA(cudaGetLastError());
 	}
-	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, d_sums, d_best);
+	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, warps, d_sums, d_best);
 	SRB_CUDA(cudaGetLastError());
 	return 0;
 }

@@ -66,7 +66,7 @@ def test_reference_edge_cases():
     raw = MFCC.get_mfcc_extractor(16000).extract(s, cmvn=False)
     assert np.max(rel_err(raw, raw_ref)) < TOL
     assert np.max(rel_err(MFCC.extract(16000, s), mfcc_ref.extract(16000, s))) < TOL
-    assert mix_feature((16000, synth.audio(8000, 1))).shape[1] == 13
+    assert mix_feature((16000, synth.audio(8000, 1))).shape[1] == 13 + 15      # MFCC || LPC
 
 
 def test_full_size_properties_config2():

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import gmm_ref, mfcc_ref
+from oracle import gmm_ref, lpc_ref, mfcc_ref
 from speaker_recognition_b200 import synth
 from speaker_recognition_b200.interface import ModelInterface
 
@@ -30,7 +30,7 @@ def test_enroll_train_predict_dump_load(tmp_path):
     assert preds == names
     # the float64 oracle (reference arithmetic) agrees on every label given the same trained models
     for (nm, sig), pred in zip(tests, preds):
-        feat = mfcc_ref.extract(16000, sig)
+        feat = np.concatenate((mfcc_ref.extract(16000, sig), lpc_ref.extract(16000, sig)), axis=1)   # mix_feature
         sc = [gmm_ref.score_all(*g.get_params(), feat, gmm_ref.MODE_LOGDOMAIN) for g in m.gmmset.gmms]
         assert m.gmmset.y[int(np.argmax(sc))] == pred
     path = str(tmp_path / "model.out")

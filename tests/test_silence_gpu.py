@@ -14,8 +14,9 @@ def gated(n, seed, fs=16000):
     s = synth.audio(n, seed=seed, fs=fs).astype(np.int64)
     rng = np.random.default_rng(seed)
     for _ in range(6):
-        a = int(rng.integers(0, n - 4000))
-        s[a:a + int(rng.integers(500, 4000))] //= int(rng.choice([1000, 40, 7]))
+        w = max(8, min(4000, n // 8))
+        a = int(rng.integers(0, n - w))
+        s[a:a + int(rng.integers(w // 8, w))] //= int(rng.choice([1000, 40, 7]))
     return s.astype(np.int16)
 
 
