@@ -74,7 +74,7 @@ def summarize_launches(tag, path):
     agg = defaultdict(list)
     for r in rows[1:]:
         agg[r[ki]].append(float(r[vi].replace(",", "")))
-    ours = {k: v for k, v in agg.items() if "srb::" in k}
+    ours = {k: v for k, v in agg.items() if "fma_loop" not in k and "at::" not in k and "elementwise" not in k}
     tot = sum(sum(v) for v in ours.values()) or 1.0
     lines = ["# launch list: ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)", ""]
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):

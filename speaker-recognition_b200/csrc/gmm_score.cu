@@ -33,13 +33,15 @@ struct ScoreArgs {
 	const float *X;
 	int ld, D;
 	const float *tiles;        // packed parameter tiles
-	int tiles_per_model, S, spk_per_chunk;
+	int tiles_per_model, S, spk_per_chunk, n_chunks;
 	const int4 *ftiles;        // per frame tile: {first frame, frame count, utterance, 0}
 	float *frame_ll;           // optional [S][ldf]
 	int ldf;
 	double *partial;           // [n_frame_tiles][S]
 	int clamp;
 	int frame_log2;            // frame_ll receives the unclamped log2-domain value (E-step normaliser) instead of ln
+	int stagger_cycles;        // first-wave CTAs of the same SM start this many cycles apart (see kernel)
+	int n_sm;
 	int x_vec_ok;              // X rows are 16-B aligned and ld % 4 == 0
 };
 
@@ -74,9 +76,13 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int g = lane >> 2, q = lane & 3;
-	const int4 ft = A.ftiles[blockIdx.x];
+	// 1-D grid, speaker chunk fastest: CTAs that share a frame tile are launched back to back, so the tile's features
+	// are read from HBM once and served from L2 to the other chunks (ncu r1 with the opposite order: 474 MB of DRAM
+	// reads per launch against 104 MB algorithmic)
+	const int ftile = blockIdx.x / A.n_chunks;
+	const int4 ft = A.ftiles[ftile];
 	const int f0 = ft.x, nf = ft.y;
-	const int s_begin = blockIdx.y * A.spk_per_chunk;
+	const int s_begin = (blockIdx.x - ftile * A.n_chunks) * A.spk_per_chunk;
 	const int s_end = min(A.S, s_begin + A.spk_per_chunk);
 	const int n_tiles = (s_end - s_begin) * A.tiles_per_model;
 	const float *gt0 = A.tiles + (size_t)s_begin * A.tiles_per_model * tileF;
@@ -122,6 +128,21 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 	}
 	__syncthreads();
 
+	// De-phase the CTAs that share an SM.  Every CTA does identical work at identical speed, so without this the warps
+	// co-resident on an SM sub-partition (warp w of each of the 3 CTAs) march in lockstep: all of them sit in the
+	// log-sum-exp epilogue at the same time and the FMA pipe idles for that quarter of every tile (ncu r1: pipe 77 %
+	// busy, top stall math-pipe throttle).  Block b of the first wave lands on SM b % n_sm in slot b / n_sm; slot s
+	// waits s thirds of a tile period once, later CTAs inherit the stagger from the CTAs they replace.
+	if (A.stagger_cycles > 0) {
+		const int lin = blockIdx.x;
+		if (lin < 3 * A.n_sm) {
+			const long long wait = (long long)(lin / A.n_sm) * A.stagger_cycles;
+			const long long t0 = clock64();
+			while (clock64() - t0 < wait) {
+			}
+		}
+	}
+
 	// thread's 8 frames: {warp*64 + 4g + i} and {warp*64 + 32 + 4g + i}, i = 0..3
 	const float *xbase = xs + warp * 64 + 4 * g;
 	float m_run[8], s_run[8];
@@ -143,15 +164,25 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 		if (PACKED) {
 			// acc2[f][j] = {acc of mixture 2(4j+q), acc of mixture 2(4j+q)+1}
 			unsigned long long acc2[8][4];
+			{   // d = 0 peeled: the accumulators start as fma(t, t, -c2) instead of being initialised by 64 moves
+				const float4 xa = *reinterpret_cast<const float4 *>(xbase);
+				const float4 xb = *reinterpret_cast<const float4 *>(xbase + 32);
+				const unsigned long long x2[8] = {pack2(xa.x, xa.x), pack2(xa.y, xa.y), pack2(xa.z, xa.z), pack2(xa.w, xa.w),
+				                                  pack2(xb.x, xb.x), pack2(xb.y, xb.y), pack2(xb.z, xb.z), pack2(xb.w, xb.w)};
 #pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				const float2 c = *reinterpret_cast<const float2 *>(cp + 2 * (4 * j + q));
-				const unsigned long long c2 = pack2(-c.x, -c.y);
+				for (int j = 0; j < 4; ++j) {
+					const float2 c = *reinterpret_cast<const float2 *>(cp + 2 * (4 * j + q));
+					const unsigned long long c2 = pack2(-c.x, -c.y);
+					const ulonglong2 p = *reinterpret_cast<const ulonglong2 *>(pq + 16 * j);
 #pragma unroll
-				for (int f = 0; f < 8; ++f) acc2[f][j] = c2;
+					for (int f = 0; f < 8; ++f) {
+						const unsigned long long t2 = fma2(x2[f], p.x, p.y);
+						acc2[f][j] = fma2(t2, t2, c2);
+					}
+				}
 			}
 #pragma unroll 2
-			for (int d = 0; d < D; ++d) {
+			for (int d = 1; d < D; ++d) {
 				const float4 xa = *reinterpret_cast<const float4 *>(xbase + d * SC_FT);
 				const float4 xb = *reinterpret_cast<const float4 *>(xbase + d * SC_FT + 32);
 				const unsigned long long x2[8] = {pack2(xa.x, xa.x), pack2(xa.y, xa.y), pack2(xa.z, xa.z), pack2(xa.w, xa.w),
@@ -229,7 +260,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 					s = s * ex2_approx(m - M) + so * ex2_approx(mo - M);
 					m = M;
 				}
-				const float l2 = m + log2f(s);
+				const float l2 = m + lg2_approx(s);    // s in [1, K]: absolute error of lg2.approx < 3e-7, |log-likelihood| ~ 50
 				float ll = l2 * LN2F;
 				if (A.clamp && !(ll >= DENORM_LOG_MIN_F)) ll = SAFE_LOG_FLOOR_F;
 				const int fr = warp * 64 + 4 * g + (f & 3) + ((f >> 2) << 5);
@@ -243,7 +274,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 			// sum over the 8 frame groups of the warp (lanes with equal q hold identical values); one partial per warp
 #pragma unroll
 			for (int off = 4; off <= 16; off <<= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-			if (lane == 0) A.partial[((size_t)blockIdx.x * A.S + spk) * WARPS + warp] = local;
+			if (lane == 0) A.partial[((size_t)ftile * A.S + spk) * WARPS + warp] = local;
 		}
 		// this warp is done with the stage: release it; the elected producer refills the stage of the PREVIOUS tile
 		// (which every warp has left by now, so the wait below almost never blocks) with the tile two ahead
@@ -398,6 +429,7 @@ static size_t score_smem_bytes(int D, int FT) {
 static bool g_score_attr_set = false;
 static bool g_score_scalar = false;
 static int g_score_warps = 4;
+static bool g_score_stagger = false;   // measured: no effect (fair-share scheduling pulls co-resident warps back into lockstep)
 
 int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums,
                  float *d_frame_ll, int ldf, int *d_best, int clamp, int frame_log2, cudaStream_t st) {
@@ -417,6 +449,8 @@ int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const i
 		const char *ew = getenv("SRB200_SCORE_WARPS");
 		if (ew && ew[0] == '8') g_score_warps = 8;
 		if (ew && ew[0] == '4') g_score_warps = 4;
+		const char *es = getenv("SRB200_SCORE_STAGGER");
+		if (es && es[0] == '1') g_score_stagger = true;
 		g_score_attr_set = true;
 	}
 	int warps = g_score_scalar ? 4 : g_score_warps;
@@ -444,8 +478,12 @@ int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const i
 		a.partial = tt->d_partial;
 		a.clamp = clamp;
 		a.frame_log2 = frame_log2;
+		a.stagger_cycles = g_score_stagger ? 140 * D : 0;     // ~ one third of a tile period (3 warps x D x 64 FFMA2 x 2 cycles)
+		a.n_sm = c.sm_count;
 		a.x_vec_ok = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(dX) & 15) == 0);
-		dim3 grid(tt->n_ftiles, ceil_div(pm.S, spc));
+		a.n_chunks = ceil_div(pm.S, spc);
+		SRB_REQUIRE((long long)a.n_chunks * tt->n_ftiles < (1LL << 31), "score: grid too large");
+		dim3 grid((unsigned)(a.n_chunks * tt->n_ftiles));
 		if (g_score_scalar) gmm_score_kernel<false, 4><<<grid, 128, smem, st>>>(a);
 		else if (warps == 8) gmm_score_kernel<true, 8><<<grid, 256, smem, st>>>(a);
 		else gmm_score_kernel<true, 4><<<grid, 128, smem, st>>>(a);
