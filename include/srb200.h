@@ -72,6 +72,13 @@ int srb200_get_device(void);
 int srb200_set_compat_clamp(int mode);
 int srb200_get_compat_clamp(void);
 
+/* scoring arithmetic route.  0 (default): fp32 FMA kernel, 2e-7 relative per frame.  1: tensor-core kernel (tcgen05, 3xTF32
+ * with fp32 accumulation in TMEM): the expanded-square GEMM form, measured 3.7e-5 worst per-frame relative error on
+ * sigma-floor models -- inside the 1e-4 parity bound, identical argmax -- and several times faster.  EM training always
+ * uses route 0.  The environment variable SRB200_SCORE_TC=1 selects route 1 when this is never called. */
+int srb200_set_score_path(int path);
+int srb200_get_score_path(void);
+
 int srb200_gmm_set_params(GMM *gmm, int nr_mixture, int dim, const double *weights, const double *means, const double *sigmas); /* means,sigmas [K*D]; sigma = std-dev (gmm.hh:31) */
 int srb200_gmm_get_params(GMM *gmm, double *weights, double *means, double *sigmas);
 int srb200_gmm_dump_precise(GMM *gmm, const char *model_file, int digits);   /* same text format, `digits` significant digits (17 = lossless) */

@@ -87,9 +87,58 @@ int Context::init() {
 
 void PackedModels::release() {
 	if (d_tiles) cudaFree(d_tiles);
+	if (d_tc) cudaFree(d_tc);
 	d_tiles = nullptr;
+	d_tc = nullptr;
+	h_tc.clear();
 	bytes = 0;
 	S = 0;
+}
+
+// Tensor-core weight images (gmm_score_tc.cuh).  Row r of speaker s holds W = [-a^2 (D), -2 a nb (D), C, 0-pad] with
+// a = sqrt(log2e/2)/sigma, nb = -mean a, C = log2 w - sum log2(sqrt(2pi) sigma) - sum nb^2; each value is split into a
+// TF32-representable hi part and the fp32 remainder lo.  Speakers are padded to 32 / 64 / multiples of 128 rows.
+void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *const *weights, const double *const *means,
+                         const double *const *sigmas, const int *Ks) {
+	const int Kp = ((2 * D + 1 + 7) / 8) * 8;
+	const int cols = K <= 32 ? 32 : (K <= 64 ? 64 : ((K + 127) / 128) * 128);
+	const long long rows_total = (long long)S * cols;
+	const int blocks = (int)((rows_total + 63) / 64);
+	const size_t bf = (size_t)2 * 64 * Kp;
+	pm.h_tc.assign((size_t)blocks * bf, 0.f);
+	pm.tc_Kp = Kp;
+	pm.tc_cols_per_spk = cols;
+	pm.tc_blocks_total = blocks;
+	const double A0 = 0.84932180028801904272;
+	auto put = [&](long long row, int k, double w) {
+		const int blk = (int)(row / 64), r = (int)(row % 64);
+		const float wf = (float)w;
+		uint32_t u;
+		memcpy(&u, &wf, 4);
+		u &= ~0x1FFFu;
+		float hi;
+		memcpy(&hi, &u, 4);
+		const float lo = (float)(w - (double)hi);
+		const size_t off = (size_t)(k >> 2) * (64 / 8) * 32 + (size_t)(r >> 3) * 32 + (r & 7) * 4 + (k & 3);
+		pm.h_tc[(size_t)blk * bf + off] = hi;
+		pm.h_tc[(size_t)blk * bf + (size_t)64 * Kp + off] = lo;
+	};
+	for (long long row = 0; row < (long long)blocks * 64; ++row) {
+		const int s = (int)(row / cols), k = (int)(row % cols);
+		if (s < S && k < Ks[s]) {
+			const double *mu = means[s] + (size_t)k * D, *sg = sigmas[s] + (size_t)k * D;
+			double C = weights[s][k] > 0.0 ? log2(weights[s][k]) : -1.0e30;
+			for (int d = 0; d < D; ++d) {
+				const double a = A0 / sg[d], nb = -mu[d] * a;
+				put(row, d, -a * a);
+				put(row, D + d, -2.0 * a * nb);
+				C -= log2(2.5066282746310002 * sg[d]) + nb * nb;
+			}
+			put(row, 2 * D, (C < -1.0e30 || C != C) ? -1.0e30 : C);
+		} else {
+			put(row, 2 * D, -1.0e30);      // padded row: exp2 underflows to exactly 0
+		}
+	}
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -187,6 +236,11 @@ int gmm_ensure_packed(GMM *g) {
 	const double *w = g->weights.data(), *m = g->means.data(), *s = g->sigmas.data();
 	pack_models_host(1, K, D, &w, &m, &s, &K, host, &Kpad);
 	if (upload_packed(g->packed, 1, K, D, host, Kpad, ctx().stream)) return 1;
+	if (g->packed.d_tc) {
+		cudaFree(g->packed.d_tc);
+		g->packed.d_tc = nullptr;
+	}
+	pack_models_tc_host(g->packed, 1, K, D, &w, &m, &s, &K);
 	g->packed_valid = true;
 	return 0;
 }
@@ -319,7 +373,7 @@ static int stage_frames(const RowSrc &src, int n, int dim, int *ld_out) {
 }
 
 // scores n staged frames against pm; returns sums[S] and optionally per-frame values for model 0
-static int score_staged(const PackedModels &pm, int n, int ld, int dim, double *sums, float *frame_out_host) {
+static int score_staged(PackedModels &pm, int n, int ld, int dim, double *sums, float *frame_out_host) {
 	Context &c = ctx();
 	const int S = pm.S;
 	if (c.d_sums.ensure((size_t)S * sizeof(double)) || c.h_out.ensure(std::max((size_t)S * sizeof(double), (size_t)n * sizeof(float)))) return 1;
@@ -534,6 +588,13 @@ int srb200_set_compat_clamp(int mode) {
 	return 0;
 }
 int srb200_get_compat_clamp(void) { return ctx().compat_clamp; }
+int srb200_set_score_path(int path) {
+	API_ENTER();
+	SRB_REQUIRE(path == 0 || path == 1, "score path must be 0 (fp32 FMA) or 1 (tcgen05 3xTF32)");
+	ctx().score_path = path;
+	return 0;
+}
+int srb200_get_score_path(void) { return ctx().score_path; }
 
 GMM *new_gmm(int nr_mixture, int covariance_type) {
 	API_ENTER();
@@ -773,6 +834,7 @@ srb200_gmmset *srb200_gmmset_create(GMM *const *models, int n_models) {
 		delete set;
 		return nullptr;
 	}
+	pack_models_tc_host(set->packed, n_models, K, D, w.data(), m.data(), s.data(), Ks.data());
 	set->S = n_models;
 	set->D = D;
 	set->K = K;

@@ -28,6 +28,10 @@ struct PackedModels {             // device-resident packed parameters of S mode
 	int S = 0, K = 0, Kpad = 0, D = 0, tiles_per_model = 0;
 	float *d_tiles = nullptr;     // S * tiles_per_model * tile_floats(D)
 	size_t bytes = 0;
+	// tensor-core path (gmm_score_tc.cuh): weight images [blocks][hi|lo][64*Kp], built on the host with the FMA tiles
+	std::vector<float> h_tc;      // host image, uploaded on first use
+	float *d_tc = nullptr;
+	int tc_Kp = 0, tc_cols_per_spk = 0, tc_blocks_total = 0;
 	void release();
 };
 
@@ -35,6 +39,9 @@ struct PackedModels {             // device-resident packed parameters of S mode
 void pack_models_host(int S, int K, int D, const double *const *weights, const double *const *means,
                       const double *const *sigmas, const int *Ks, std::vector<float> &out, int *Kpad_out);
 int upload_packed(PackedModels &pm, int S, int K, int D, const std::vector<float> &host, int Kpad, cudaStream_t st);
+// host-side build of the tensor-core weight images into pm.h_tc (no device work)
+void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *const *weights, const double *const *means,
+                         const double *const *sigmas, const int *Ks);
 
 }  // namespace srb
 

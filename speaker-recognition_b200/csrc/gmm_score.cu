@@ -342,6 +342,7 @@ struct TileTable {
 	int4 *d_ftiles = nullptr;
 	int *d_utt_tile_start = nullptr;
 	double *d_partial = nullptr;
+	float *d_Aimg = nullptr;         // tensor-core route: feature images, allocated on first use
 	uint64_t stamp = 0;
 };
 static std::vector<TileTable> g_tables;
@@ -351,6 +352,7 @@ static void free_table(TileTable &t) {
 	if (t.d_ftiles) cudaFree(t.d_ftiles);
 	if (t.d_utt_tile_start) cudaFree(t.d_utt_tile_start);
 	if (t.d_partial) cudaFree(t.d_partial);
+	if (t.d_Aimg) cudaFree(t.d_Aimg);
 	t = TileTable();
 }
 
@@ -431,7 +433,7 @@ static bool g_score_scalar = false;
 static int g_score_warps = 4;
 static bool g_score_stagger = false;   // measured: no effect (fair-share scheduling pulls co-resident warps back into lockstep)
 
-int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums,
+int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums,
                  float *d_frame_ll, int ldf, int *d_best, int clamp, int frame_log2, cudaStream_t st) {
 	SRB_REQUIRE(pm.S > 0 && pm.d_tiles != nullptr, "score: empty model set");
 	SRB_REQUIRE(D == pm.D, "score: feature dim %d != model dim %d", D, pm.D);
@@ -452,6 +454,22 @@ int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const i
 		const char *es = getenv("SRB200_SCORE_STAGGER");
 		if (es && es[0] == '1') g_score_stagger = true;
 		g_score_attr_set = true;
+	}
+	// ---- arithmetic route: tcgen05 3xTF32 (explicit opt-in) or fp32 FMA ----
+	int path = c.score_path;
+	if (path < 0) {
+		const char *et = getenv("SRB200_SCORE_TC");
+		path = (et && et[0] == '1') ? 1 : 0;
+	}
+	if (path == 1 && !frame_log2 && tc_supported(pm, D)) {
+		TileTable *tt = nullptr;
+		if (get_table(utt_off, n_utt, pm.S, 128, st, &tt)) return 1;
+		if (tt->n_ftiles > 0 && tt->d_Aimg == nullptr)
+			SRB_CUDA(cudaMalloc(&tt->d_Aimg, (size_t)tt->n_ftiles * 2 * 128 * pm.tc_Kp * sizeof(float)));
+		if (launch_score_tc(pm, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_Aimg, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;
+		score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, 4, d_sums, d_best);
+		SRB_CUDA(cudaGetLastError());
+		return 0;
 	}
 	int warps = g_score_scalar ? 4 : g_score_warps;
 	if (score_smem_bytes(D, warps * 64) > 113 * 1024) warps = 4;   // 8-warp CTAs need two per SM

@@ -1,0 +1,274 @@
+// gmm_score_tc.cuh -- tensor-core (tcgen05, kind::tf32) diagonal-GMM scorer for sm_100a: kernel + operand layouts.
+//
+// Same quantity as gmm_score.cu (log2 p(x) per frame and speaker, per-utterance sums), different arithmetic route:
+// the Mahalanobis term is expanded,
+//     l2_k(x) = C_k + sum_d [ (-a_kd^2) x_d^2 + (-2 a_kd nb_kd) x_d ],     C_k = c2_k - sum_d nb_kd^2,
+// i.e. a GEMM  L[frames x rows] = PHI[frames x Kp] . W[rows x Kp]^T  with PHI = [x^2, x, 1, 0-pad], Kp = 8*ceil((2D+1)/8),
+// run on the 5th-generation tensor cores as 3xTF32 (hi*hi + hi*lo + lo*hi; fp32 accumulate in TMEM).  Measured on B200
+// against float64 (experiments/tf32_numerics.py, C2-shaped models incl. sigma-floor entries): max per-frame
+// |LL - LL64| / max(1,|LL64|) = 3.7e-5 -- inside the 1e-4 bound, argmax identical -- versus 2e-7 for the FMA kernel,
+// which therefore stays the default; this path is selected explicitly (SRB200_SCORE_TC=1 / srb200_set_score_path).
+//
+// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0  producer: cp.async.bulk of the pre-imaged operand blocks into shared memory (A: one 128-frame tile, hi|lo,
+//           resident for the whole unit; B: 64-row blocks, hi|lo, 2-stage ring), completion on mbarriers
+//   warp 1  MMA issuer: one elected lane issues 3 passes x Kp/8 tcgen05.mma (M=128, N=64, K=8) per B block into one of
+//           four 64-column TMEM accumulator slots, tcgen05.commit -> mbarriers (frees the B stage, publishes the slot)
+//   warps 2-5  epilogue: thread = frame row (TMEM lane), tcgen05.ld 64 columns, online log2-sum-exp2 across the blocks
+//           of a speaker, clamp / per-frame output / warp-reduced per-(tile, speaker) partial sums
+// Operands are K-major in the no-swizzle canonical layout (8-row x 16-byte core matrices; LBO = byte stride between
+// K-adjacent core matrices, SBO = 128 B between 8-row groups), verified by experiments/tc_gemm_test.cu; the images are
+// written to HBM in exactly the shared-memory order, so every load is ONE contiguous bulk copy.
+#pragma once
+#include "common.cuh"
+
+namespace srb {
+
+constexpr int TC_M = 128;            // frames per tile (TMEM lanes)
+constexpr int TC_NB = 64;            // mixture rows per B block / accumulator slot
+constexpr int TC_SLOTS = 4;          // TMEM accumulator slots (4 x 64 = 256 columns)
+constexpr int TC_BSTAGES = 2;
+constexpr int TC_THREADS = 192;      // producer warp, MMA warp, 4 epilogue warps
+constexpr float TC_LN2 = 0.69314718055994531f;
+
+// floats per image block
+__host__ __device__ static inline size_t tc_a_tile_floats(int Kp) { return (size_t)2 * TC_M * Kp; }    // hi | lo
+__host__ __device__ static inline size_t tc_b_block_floats(int Kp) { return (size_t)2 * TC_NB * Kp; }
+// element (row r, k) of one part (hi or lo) of an image with `rows` rows: K-groups outermost
+__host__ __device__ static inline size_t tc_img_off(int rows, int r, int k) {
+	return (size_t)(k >> 2) * (rows / 8) * 32 + (size_t)(r >> 3) * 32 + (r & 7) * 4 + (k & 3);
+}
+
+struct TcArgs {
+	const float *A;            // [n_tiles][2][TC_M*Kp] feature images
+	const float *B;            // [n_blocks_total][2][TC_NB*Kp] weight images (speaker-major, rows padded)
+	const int4 *ftiles;        // per frame tile: {first frame, frame count, utterance, 0}
+	int n_ftiles;
+	int Kp;
+	int S;                     // speakers
+	int blocks_per_spk;        // 64-row blocks per speaker (rows padded to a multiple of 64) -- or, when seg < 64:
+	int seg;                   // columns per speaker inside a block (32 or 64) when a speaker is smaller than a block
+	int n_blocks_total;
+	int n_chunks;              // the block range is cut into n_chunks contiguous chunks (whole speakers each)
+	int spk_per_chunk;
+	float *frame_ll;           // optional [S][ldf]
+	int ldf;
+	double *partial;           // [n_ftiles][S][4]
+	int clamp, frame_log2;
+};
+
+namespace tc {
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+	uint64_t d = 0;
+	d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+	d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+	d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+	d |= (uint64_t)1 << 46;      // sm_100 descriptor version; layout_type (bits 61-63) = 0: no swizzle
+	return d;
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+	    "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t *bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ld32(uint32_t taddr, float *v) {
+	uint32_t r[32];
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+	    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+	    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+	      "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+	      "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+	      "=r"(r[31])
+	    : "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// bounded wait: a broken pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void wait(uint64_t *bar, uint32_t parity) {
+	long long spins = 0;
+	while (!mbar_try_wait(bar, parity)) {
+		if (++spins > 400000000LL) __trap();
+	}
+}
+
+}  // namespace tc
+
+// online log2-sum-exp2 update with 32 new values (one chunk of accumulator columns) for one frame
+__device__ __forceinline__ void tc_lse_update(const float *v, float &m_run, float &s_run) {
+	float mx = v[0];
+#pragma unroll
+	for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+	const float m_new = fmaxf(m_run, mx);
+	float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+	for (int i = 0; i < 32; i += 4) {
+		s0 += ex2_approx(v[i] - m_new);
+		s1 += ex2_approx(v[i + 1] - m_new);
+		s2 += ex2_approx(v[i + 2] - m_new);
+		s3 += ex2_approx(v[i + 3] - m_new);
+	}
+	s_run = fmaf(s_run, ex2_approx(m_run - m_new), (s0 + s1) + (s2 + s3));
+	m_run = m_new;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArgs A) {
+	extern __shared__ __align__(1024) unsigned char tc_smem[];
+	const int Kp = A.Kp;
+	const uint32_t a_part_bytes = (uint32_t)TC_M * Kp * 4, b_part_bytes = (uint32_t)TC_NB * Kp * 4;
+	float *sA = reinterpret_cast<float *>(tc_smem);                                  // hi | lo
+	float *sB = sA + tc_a_tile_floats(Kp);                                           // [stages][hi | lo]
+	uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TC_BSTAGES * tc_b_block_floats(Kp));
+	uint64_t *full_a = bars, *empty_a = bars + 1;
+	uint64_t *full_b = bars + 2, *empty_b = full_b + TC_BSTAGES;
+	uint64_t *tm_full = empty_b + TC_BSTAGES, *tm_empty = tm_full + TC_SLOTS;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + TC_SLOTS);
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	if (tid == 0) {
+		mbar_init(full_a, 1);
+		mbar_init(empty_a, 1);
+		for (int s = 0; s < TC_BSTAGES; ++s) {
+			mbar_init(&full_b[s], 1);
+			mbar_init(&empty_b[s], 1);
+		}
+		for (int s = 0; s < TC_SLOTS; ++s) {
+			mbar_init(&tm_full[s], 1);
+			mbar_init(&tm_empty[s], 4);      // one arrival per epilogue warp
+		}
+		fence_mbar_init();
+	}
+	if (warp == 1) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_SLOTS * TC_NB)));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+	}
+	tc::fence_before();
+	__syncthreads();
+	tc::fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	// work units: (frame tile, chunk of whole speakers); unit u -> tile u / n_chunks, chunk u % n_chunks
+	const int n_units = A.n_ftiles * A.n_chunks;
+	const int blocks_per_chunk_full = (A.seg >= TC_NB) ? A.spk_per_chunk * A.blocks_per_spk : (A.spk_per_chunk * A.seg + TC_NB - 1) / TC_NB;
+
+	if (warp == 0) {
+		// ======================= producer =======================
+		if (lane == 0) {
+			uint32_t it_b = 0, it_a = 0;
+			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it_a) {
+				const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
+				const int blk0 = chunk * blocks_per_chunk_full;
+				const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
+				tc::wait(empty_a, (it_a & 1) ^ 1);
+				mbar_expect_tx(full_a, 2 * a_part_bytes);
+				bulk_g2s(sA, A.A + (size_t)tile * tc_a_tile_floats(Kp), 2 * a_part_bytes, full_a);
+				for (int b = blk0; b < blk1; ++b, ++it_b) {
+					const int st = it_b % TC_BSTAGES;
+					tc::wait(&empty_b[st], ((it_b / TC_BSTAGES) & 1) ^ 1);
+					mbar_expect_tx(&full_b[st], 2 * b_part_bytes);
+					bulk_g2s(sB + (size_t)st * tc_b_block_floats(Kp), A.B + (size_t)b * tc_b_block_floats(Kp), 2 * b_part_bytes, &full_b[st]);
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ======================= MMA issuer =======================
+		if (lane == 0) {
+			// instruction descriptor: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9 / 10-12 = 2), both K-major, N>>3 at bit 17, M>>4 at bit 24
+			const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NB >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+			const uint32_t lbo_a = (TC_M / 8) * 128, lbo_b = (TC_NB / 8) * 128, sbo = 128;
+			const int ksteps = Kp / 8;
+			uint32_t it_b = 0, it_a = 0, it_s = 0;
+			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it_a) {
+				const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
+				const int blk0 = chunk * blocks_per_chunk_full;
+				const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
+				tc::wait(full_a, it_a & 1);
+				const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + a_part_bytes;
+				for (int b = blk0; b < blk1; ++b, ++it_b, ++it_s) {
+					const int st = it_b % TC_BSTAGES, slot = it_s % TC_SLOTS;
+					tc::wait(&tm_empty[slot], ((it_s / TC_SLOTS) & 1) ^ 1);
+					tc::wait(&full_b[st], (it_b / TC_BSTAGES) & 1);
+					tc::fence_after();
+					const uint32_t b_hi = smem_u32(sB + (size_t)st * tc_b_block_floats(Kp)), b_lo = b_hi + b_part_bytes;
+					const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TC_NB);
+					uint32_t acc = 0;
+					// 3xTF32: hi*hi, hi*lo, lo*hi (small terms last would be marginally better; the order is irrelevant at fp32 accumulate)
+					for (int pass = 0; pass < 3; ++pass) {
+						const uint32_t pa = pass == 2 ? a_lo : a_hi, pb = pass == 1 ? b_lo : b_hi;
+						for (int k = 0; k < ksteps; ++k) {
+							tc::mma_tf32(d_tmem, tc::make_desc(pa + k * 2 * lbo_a, lbo_a, sbo), tc::make_desc(pb + k * 2 * lbo_b, lbo_b, sbo), idesc, acc);
+							acc = 1;
+						}
+					}
+					tc::commit(&empty_b[st]);       // the B stage may be refilled once these MMAs have read it
+					tc::commit(&tm_full[slot]);     // ... and the accumulator slot is complete
+				}
+				tc::commit(empty_a);                // the A tile may be replaced
+			}
+		}
+	} else {
+		// ======================= epilogue (4 warps; thread = frame row) =======================
+		const int q = warp & 3;                       // TMEM lane quarter this warp may access
+		const int row = q * 32 + lane;                // frame within the tile
+		uint32_t it_s = 0;
+		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+			const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
+			const int blk0 = chunk * blocks_per_chunk_full;
+			const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
+			const int4 ft = A.ftiles[tile];
+			const bool valid = row < ft.y;
+			float m_run = -3.0e38f, s_run = 0.f;
+			int col_in_spk = 0;                       // columns of the current speaker consumed so far
+			int spk = chunk * A.spk_per_chunk;
+			const int cols_per_spk = (A.seg >= TC_NB) ? A.blocks_per_spk * TC_NB : A.seg;
+			for (int b = blk0; b < blk1; ++b, ++it_s) {
+				const int slot = it_s % TC_SLOTS;
+				tc::wait(&tm_full[slot], (it_s / TC_SLOTS) & 1);
+				tc::fence_after();
+				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * TC_NB);
+#pragma unroll 1
+				for (int half = 0; half < 2; ++half) {
+					float v[32];
+					tc::ld32(taddr + half * 32, v);
+					tc_lse_update(v, m_run, s_run);
+					col_in_spk += 32;
+					if (col_in_spk == cols_per_spk) {
+						if (spk < A.S) {
+							const float l2 = m_run + lg2_approx(s_run);
+							float ll = l2 * TC_LN2;
+							if (A.clamp && !(ll >= -744.4400719213812f)) ll = -34.538776394910684f;
+							double local = valid ? (double)ll : 0.0;
+							if (valid && A.frame_ll != nullptr) A.frame_ll[(size_t)spk * A.ldf + ft.x + row] = A.frame_log2 ? l2 : ll;
+#pragma unroll
+							for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+							if (lane == 0) A.partial[((size_t)tile * A.S + spk) * 4 + q] = local;
+						}
+						m_run = -3.0e38f;
+						s_run = 0.f;
+						col_in_spk = 0;
+						++spk;
+					}
+				}
+				tc::fence_before();
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&tm_empty[slot]);
+			}
+		}
+	}
+	tc::fence_before();
+	__syncthreads();
+	if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_SLOTS * TC_NB)));
+}
+
+}  // namespace srb

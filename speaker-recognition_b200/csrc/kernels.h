@@ -7,9 +7,14 @@ namespace srb {
 // ---- gmm_score.cu ----
 // dX [n_total][ld] fp32 on device; utt_off[n_utt+1] HOST frame offsets; d_sums [n_utt][S] float64;
 // d_frame_ll optional [S][ldf]; d_best optional [n_utt].
-int launch_score(const PackedModels &pm, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums,
+int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums,
                  float *d_frame_ll, int ldf, int *d_best, int clamp, int frame_log2, cudaStream_t st);
 void score_tables_release();
+
+// ---- gmm_score_tc.cu: tensor-core route (tcgen05, 3xTF32) ----
+bool tc_supported(const PackedModels &pm, int D);
+int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, float *d_Aimg, double *d_partial,
+                    float *d_frame_ll, int ldf, int clamp, int frame_log2, cudaStream_t st);
 
 // ---- gmm_em.cu ----
 // stats (float64): [K] N_k | [K*D] sum g x | [K*D] sum g x^2 | [1] sum log p | [1] frames used

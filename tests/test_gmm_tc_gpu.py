@@ -1,0 +1,103 @@
+"""GPU parity tests of the tensor-core scoring route (csrc/gmm_score_tc.cuh: tcgen05 kind::tf32, 3xTF32, TMEM accumulators)
+against the float64 oracle and against the default fp32-FMA route.  Bound: the north_star's 1e-4 * max(1, |ref|) per frame,
+identical argmax; this route's measured worst case on sigma-floor models is ~4e-5 (the FMA route: ~2e-7)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import gmm_ref
+from speaker_recognition_b200 import _lib, synth
+from speaker_recognition_b200.gmm.pygmm import GMM
+from speaker_recognition_b200.gmmset import GMMSet
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture()
+def tc_route():
+    L = _lib.lib()
+    _lib.check(L.srb200_set_score_path(1))
+    yield L
+    _lib.check(L.srb200_set_score_path(0))
+
+
+def build_set(S, K, D, seed0=1000, floor_frac=0.01):
+    W, M, Sg = synth.models(S, K, D, seed0=seed0, floor_frac=floor_frac)
+    gs = GMMSet(gmm_order=K)
+    for i in range(S):
+        gs.gmms.append(GMM(K).set_params(W[i], M[i], Sg[i]))
+        gs.y.append(i)
+    return gs, W, M, Sg
+
+
+@pytest.mark.parametrize("S,K,D,T", [(3, 128, 39, 1000), (5, 32, 39, 300), (4, 10, 13, 129), (2, 64, 26, 128), (3, 256, 39, 500),
+                                     (1, 512, 39, 257), (7, 100, 34, 640), (2, 40, 50, 200)])
+def test_tc_route_matches_oracle_per_frame_and_sums(tc_route, S, K, D, T):
+    gs, W, M, Sg = build_set(S, K, D, seed0=3000 + S * 7 + K)
+    X = synth.draw(W[S // 2], M[S // 2], Sg[S // 2], T, seed=K + T)
+    sums = np.array(gs.predict_one_scores(X))
+    for i in range(S):
+        exact = gmm_ref.score(W[i], M[i], Sg[i], X, gmm_ref.MODE_LOGDOMAIN)
+        got = gs.gmms[i].score(X)                        # per-frame values through the single-model entry point
+        assert np.max(rel_err(got, exact)) < TOL
+        assert abs(sums[i] - exact.sum()) < 2e-5 * abs(exact.sum())
+    assert int(np.argmax(sums)) == S // 2
+
+
+def test_tc_route_real_parameter_models_and_clamp(tc_route, golden_gmm):
+    for tag in ("ubm32", "ubm64", "ubm256"):
+        c = golden_gmm.case(tag)
+        g = GMM(len(c["w"])).set_params(c["w"], c["mean"], c["sigma"])
+        got = g.score(c["X"])
+        exact = gmm_ref.score(c["w"], c["mean"], c["sigma"], c["X"], gmm_ref.MODE_LOGDOMAIN)
+        assert np.max(rel_err(got, exact)) < TOL
+        assert abs(g.score_all(c["X"]) - float(c["score_all"])) < 1e-5 * abs(float(c["score_all"]))
+    c, u = golden_gmm.case("ubm32"), golden_gmm.case("underflow")
+    g = GMM(32).set_params(c["w"], c["mean"], c["sigma"])
+    got = g.score(u["X"])
+    exact = gmm_ref.score(c["w"], c["mean"], c["sigma"], u["X"], gmm_ref.MODE_LOGDOMAIN)
+    deep = exact < gmm_ref.DENORM_LOG_MIN - 5.0
+    assert deep.sum() > 3 and np.allclose(got[deep], gmm_ref.SAFE_LOG_FLOOR, atol=1e-5)      # safe_log clamp (gmm.cc:34-38)
+    dom = exact > -600
+    assert np.max(rel_err(got[dom], exact[dom])) < TOL
+
+
+def test_tc_route_equals_fma_route_on_batched_utterances(tc_route):
+    """device entry point with several ragged utterances: both routes give the same sums (to the TC route's accuracy) and argmax"""
+    import ctypes as C
+    import torch
+    L = tc_route
+    S, K, D = 9, 128, 39
+    gs, W, M, Sg = build_set(S, K, D)
+    lens = [700, 129, 1, 2048, 333]
+    X = np.concatenate([synth.draw(W[i % S], M[i % S], Sg[i % S], n, seed=50 + i) for i, n in enumerate(lens)])
+    Xd = torch.zeros((len(X), 40), dtype=torch.float32, device="cuda")
+    Xd[:, :D] = torch.from_numpy(X.astype(np.float32)).cuda()
+    off = (C.c_int * (len(lens) + 1))(*np.concatenate([[0], np.cumsum(lens)]).tolist())
+    res = []
+    for path in (1, 0):
+        _lib.check(L.srb200_set_score_path(path))
+        sums = torch.zeros((len(lens), S), dtype=torch.float64, device="cuda")
+        best = torch.zeros(len(lens), dtype=torch.int32, device="cuda")
+        _lib.check(L.srb200_gmmset_score_dev(gs._ensure_set(), Xd.data_ptr(), 40, D, off, len(lens), sums.data_ptr(), None, 0,
+                                             best.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        res.append((sums.cpu().numpy(), best.cpu().numpy()))
+    _lib.check(L.srb200_set_score_path(1))
+    assert np.max(np.abs(res[0][0] - res[1][0]) / np.abs(res[1][0])) < 2e-5
+    assert np.array_equal(res[0][1], res[1][1])
+    assert list(res[0][1]) == [i % S for i in range(len(lens))]
+
+
+def test_tc_route_full_size_config2(tc_route):
+    S, K, D, T = 100, 128, 39, 10000
+    gs, W, M, Sg = build_set(S, K, D)
+    X = synth.draw(W[37], M[37], Sg[37], T, seed=5)
+    scores = np.array(gs.predict_one_scores(X))
+    assert int(np.argmax(scores)) == 37
+    a, b = np.array(gs.predict_one_scores(X[:3333])), np.array(gs.predict_one_scores(X[3333:]))
+    assert np.max(np.abs((a + b) - scores) / np.abs(scores)) < 1e-9                       # additivity
+    for i in (0, 37, 99):
+        ex = gmm_ref.score_all(W[i], M[i], Sg[i], X[:1000], gmm_ref.MODE_LOGDOMAIN)
+        assert abs(gs.gmms[i].score_all(X[:1000]) - ex) < 2e-5 * abs(ex)
