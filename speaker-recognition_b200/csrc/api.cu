@@ -88,9 +88,12 @@ int Context::init() {
 void PackedModels::release() {
 	if (d_tiles) cudaFree(d_tiles);
 	if (d_tc) cudaFree(d_tc);
+	if (d_tc_hard) cudaFree(d_tc_hard);
 	d_tiles = nullptr;
 	d_tc = nullptr;
+	d_tc_hard = nullptr;
 	h_tc.clear();
+	h_tc_hard.clear();
 	bytes = 0;
 	S = 0;
 }
@@ -110,6 +113,12 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 	pm.tc_cols_per_spk = cols;
 	pm.tc_blocks_total = blocks;
 	const double A0 = 0.84932180028801904272;
+	constexpr int HMAX = 191;                    // = TC_HMAX (gmm_score_tc.cuh)
+	double HARD_SIGMA = 0.1;                     // = TC_HARD_SIGMA
+	if (const char *eh = getenv("SRB200_TC_HARD_SIGMA")) HARD_SIGMA = atof(eh);   // experiments: 0 disables the add-back list
+	pm.h_tc_hard.assign((size_t)blocks * 4 * (1 + HMAX), 0);
+	std::vector<int> n_hard(blocks, 0), n_first(blocks, 0);
+	bool overflow = false;
 	auto put = [&](long long row, int k, double w) {
 		const int blk = (int)(row / 64), r = (int)(row % 64);
 		const float wf = (float)w;
@@ -123,21 +132,48 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 		pm.h_tc[(size_t)blk * bf + off] = hi;
 		pm.h_tc[(size_t)blk * bf + (size_t)64 * Kp + off] = lo;
 	};
-	for (long long row = 0; row < (long long)blocks * 64; ++row) {
+	for (long long row = 0; row < (long long)blocks * 64; ++row) {     // rows ascend, so each block's list is sorted by column
 		const int s = (int)(row / cols), k = (int)(row % cols);
 		if (s < S && k < Ks[s]) {
 			const double *mu = means[s] + (size_t)k * D, *sg = sigmas[s] + (size_t)k * D;
 			double C = weights[s][k] > 0.0 ? log2(weights[s][k]) : -1.0e30;
 			for (int d = 0; d < D; ++d) {
 				const double a = A0 / sg[d], nb = -mu[d] * a;
-				put(row, d, -a * a);
-				put(row, D + d, -2.0 * a * nb);
-				C -= log2(2.5066282746310002 * sg[d]) + nb * nb;
+				C -= log2(2.5066282746310002 * sg[d]);
+				if (sg[d] < HARD_SIGMA) {
+					// kept out of the GEMM (its three ~1e3 terms would cancel): exact add-back entry for the epilogue
+					const int blk = (int)(row / 64), col = (int)(row % 64);
+					if (n_hard[blk] >= HMAX) {
+						overflow = true;
+						continue;
+					}
+					int *e = pm.h_tc_hard.data() + ((size_t)blk * (1 + HMAX) + 1 + n_hard[blk]) * 4;
+					const float af = (float)a, nbf = (float)nb;
+					e[0] = col;
+					e[1] = ((D + d) >> 2) * (128 / 8) * 32 + ((D + d) & 3);   // K-group part of tc_img_off(128, row, D + d)
+					memcpy(&e[2], &af, 4);
+					memcpy(&e[3], &nbf, 4);
+					++n_hard[blk];
+					if (col < 32) ++n_first[blk];
+				} else {
+					put(row, d, -a * a);
+					put(row, D + d, -2.0 * a * nb);
+					C -= nb * nb;
+				}
 			}
 			put(row, 2 * D, (C < -1.0e30 || C != C) ? -1.0e30 : C);
 		} else {
 			put(row, 2 * D, -1.0e30);      // padded row: exp2 underflows to exactly 0
 		}
+	}
+	for (int b = 0; b < blocks; ++b) {
+		int *h = pm.h_tc_hard.data() + (size_t)b * (1 + HMAX) * 4;
+		h[0] = n_first[b];
+		h[1] = n_hard[b];
+	}
+	if (overflow) {      // too many tiny-sigma entries for the sparse list: this model set stays on the FMA route
+		pm.h_tc.clear();
+		pm.h_tc_hard.clear();
 	}
 }
 

@@ -30,7 +30,9 @@ struct PackedModels {             // device-resident packed parameters of S mode
 	size_t bytes = 0;
 	// tensor-core path (gmm_score_tc.cuh): weight images [blocks][hi|lo][64*Kp], built on the host with the FMA tiles
 	std::vector<float> h_tc;      // host image, uploaded on first use
+	std::vector<int> h_tc_hard;   // per block: 4*(1+HMAX) ints (header + hard entries), see gmm_score_tc.cuh
 	float *d_tc = nullptr;
+	int *d_tc_hard = nullptr;
 	int tc_Kp = 0, tc_cols_per_spk = 0, tc_blocks_total = 0;
 	void release();
 };

@@ -42,7 +42,10 @@ __global__ void tc_prep_features_kernel(const float *__restrict__ X, int ld, int
 
 static bool g_tc_attr = false;
 
-size_t tc_smem_bytes(int Kp) { return (tc_a_tile_floats(Kp) + TC_BSTAGES * tc_b_block_floats(Kp)) * sizeof(float) + 256; }
+size_t tc_smem_bytes(int Kp) {
+	// operand tiles + 14 mbarriers + TMEM slot word + pair-merge buffer [128] float2 + staged hard entries [8][32] int4
+	return (tc_a_tile_floats(Kp) + TC_BSTAGES * tc_b_block_floats(Kp)) * sizeof(float) + 128 + TC_M * 8 + 8 * 32 * 16 + 64;
+}
 
 bool tc_supported(const PackedModels &pm, int D) {
 	return !pm.h_tc.empty() && pm.tc_Kp == ((2 * D + 1 + 7) / 8) * 8 && tc_smem_bytes(pm.tc_Kp) <= 227 * 1024 - 1024;
@@ -57,6 +60,8 @@ int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4
 	if (pm.d_tc == nullptr) {
 		SRB_CUDA(cudaMalloc(&pm.d_tc, pm.h_tc.size() * sizeof(float)));
 		SRB_CUDA(cudaMemcpyAsync(pm.d_tc, pm.h_tc.data(), pm.h_tc.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+		SRB_CUDA(cudaMalloc(&pm.d_tc_hard, pm.h_tc_hard.size() * sizeof(int)));
+		SRB_CUDA(cudaMemcpyAsync(pm.d_tc_hard, pm.h_tc_hard.data(), pm.h_tc_hard.size() * sizeof(int), cudaMemcpyHostToDevice, st));
 		SRB_CUDA(cudaStreamSynchronize(st));
 	}
 	if (!g_tc_attr) {
@@ -92,6 +97,8 @@ int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4
 	a.partial = d_partial;
 	a.clamp = clamp;
 	a.frame_log2 = frame_log2;
+	a.D = D;
+	a.hard = reinterpret_cast<const int4 *>(pm.d_tc_hard);
 	const long long units = (long long)n_ftiles * n_chunks;
 	const int grid = (int)std::min<long long>(units, c.sm_count);
 	gmm_score_tc_kernel<<<grid, TC_THREADS, tc_smem_bytes(Kp), st>>>(a);

@@ -8,14 +8,19 @@
 // against float64 (experiments/tf32_numerics.py, C2-shaped models incl. sigma-floor entries): max per-frame
 // |LL - LL64| / max(1,|LL64|) = 3.7e-5 -- inside the 1e-4 bound, argmax identical -- versus 2e-7 for the FMA kernel,
 // which therefore stays the default; this path is selected explicitly (SRB200_SCORE_TC=1 / srb200_set_score_path).
+// The residual error of the expanded form comes from dimensions with a tiny sigma (the trainer's floor 0.0316): their three
+// terms are ~1e3 each and cancel.  Those (row, dim) entries are therefore left out of W and C and added back EXACTLY in the
+// epilogue, t = a x + nb, l2 -= t*t, from a per-block sparse list (about 1 % of the entries in the synthetic configs);
+// with that the route measures ~1e-6 per frame.
 //
 // Structure (one persistent CTA per SM, 192 threads, warp-specialised):
 //   warp 0  producer: cp.async.bulk of the pre-imaged operand blocks into shared memory (A: one 128-frame tile, hi|lo,
 //           resident for the whole unit; B: 64-row blocks, hi|lo, 2-stage ring), completion on mbarriers
 //   warp 1  MMA issuer: one elected lane issues 3 passes x Kp/8 tcgen05.mma (M=128, N=64, K=8) per B block into one of
 //           four 64-column TMEM accumulator slots, tcgen05.commit -> mbarriers (frees the B stage, publishes the slot)
-//   warps 2-5  epilogue: thread = frame row (TMEM lane), tcgen05.ld 64 columns, online log2-sum-exp2 across the blocks
-//           of a speaker, clamp / per-frame output / warp-reduced per-(tile, speaker) partial sums
+//   warps 2-9  epilogue: thread = frame row (TMEM lane); the two warps of a lane quarter take the column halves 0-31 / 32-63 of
+//           every block (tcgen05.ld 32 columns), each keeps an online log2-sum-exp2 over its half of the speaker's rows, the pair
+//           merges at the end of a speaker through shared memory; clamp / per-frame output / per-(tile, speaker) partial sums
 // Operands are K-major in the no-swizzle canonical layout (8-row x 16-byte core matrices; LBO = byte stride between
 // K-adjacent core matrices, SBO = 128 B between 8-row groups), verified by experiments/tc_gemm_test.cu; the images are
 // written to HBM in exactly the shared-memory order, so every load is ONE contiguous bulk copy.
@@ -27,9 +32,11 @@ namespace srb {
 constexpr int TC_M = 128;            // frames per tile (TMEM lanes)
 constexpr int TC_NB = 64;            // mixture rows per B block / accumulator slot
 constexpr int TC_SLOTS = 4;          // TMEM accumulator slots (4 x 64 = 256 columns)
-constexpr int TC_BSTAGES = 2;
-constexpr int TC_THREADS = 192;      // producer warp, MMA warp, 4 epilogue warps
+constexpr int TC_BSTAGES = 3;
+constexpr int TC_THREADS = 320;      // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter: column halves)
 constexpr float TC_LN2 = 0.69314718055994531f;
+constexpr int TC_HMAX = 191;         // capacity of a block's hard-entry list (+1 header = 192 int4 = 3 KB)
+constexpr double TC_HARD_SIGMA = 0.1;   // dims with sigma below this are kept out of the GEMM and added back exactly
 
 // floats per image block
 __host__ __device__ static inline size_t tc_a_tile_floats(int Kp) { return (size_t)2 * TC_M * Kp; }    // hi | lo
@@ -55,6 +62,9 @@ struct TcArgs {
 	int ldf;
 	double *partial;           // [n_ftiles][S][4]
 	int clamp, frame_log2;
+	int D;
+	const int4 *hard;          // [n_blocks_total][1 + TC_HMAX]: header {n_first_half, n_total, 0, 0}, then entries sorted by
+	                           // column: {column in block, image offset of the feature x_dim (K-group part), float bits of a, of nb}
 };
 
 namespace tc {
@@ -72,6 +82,17 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
 	    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
 	    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
 	    "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+// descriptor passed as (lo, hi) words: only the low word (start address field) changes between k-steps, by one 32-bit add
+template <int ACC>
+__device__ __forceinline__ void mma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+	asm volatile(
+	    "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+	    "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+	    "setp.ne.b32 p, %6, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+	    "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
 	    : "memory");
 }
 __device__ __forceinline__ void commit(uint64_t *bar) {
@@ -134,18 +155,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 	uint64_t *full_b = bars + 2, *empty_b = full_b + TC_BSTAGES;
 	uint64_t *tm_full = empty_b + TC_BSTAGES, *tm_empty = tm_full + TC_SLOTS;
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + TC_SLOTS);
+	int4 *ent_s = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(bars) + 128);   // [8 warps][32] staged hard entries (16-B aligned)
+	float2 *ms_x = reinterpret_cast<float2 *>(ent_s + 8 * 32);                       // [128] (m, s) of the upper-half warps
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	if (tid == 0) {
 		mbar_init(full_a, 1);
-		mbar_init(empty_a, 1);
+		mbar_init(empty_a, 9);           // MMA commit + the eight epilogue warps (they read x from the A tile)
 		for (int s = 0; s < TC_BSTAGES; ++s) {
 			mbar_init(&full_b[s], 1);
 			mbar_init(&empty_b[s], 1);
 		}
 		for (int s = 0; s < TC_SLOTS; ++s) {
 			mbar_init(&tm_full[s], 1);
-			mbar_init(&tm_empty[s], 4);      // one arrival per epilogue warp
+			mbar_init(&tm_empty[s], 8);      // one arrival per epilogue warp
 		}
 		fence_mbar_init();
 	}
@@ -202,13 +225,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 					tc::fence_after();
 					const uint32_t b_hi = smem_u32(sB + (size_t)st * tc_b_block_floats(Kp)), b_lo = b_hi + b_part_bytes;
 					const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TC_NB);
-					uint32_t acc = 0;
-					// 3xTF32: hi*hi, hi*lo, lo*hi (small terms last would be marginally better; the order is irrelevant at fp32 accumulate)
+					// 3xTF32: hi*hi, hi*lo, lo*hi.  The issuing thread is the critical resource (ncu: the first version spent ~100
+					// cycles per MMA building descriptors against 32 cycles of tensor-pipe time), so descriptors are two constant
+					// words; only the 14-bit start-address field in the low word advances, by one add per operand per k-step.
+					const uint32_t dA_hi = (uint32_t)(sbo >> 4) | (1u << 14), dB_hi = dA_hi;            // SBO | version bit 46
+					const uint32_t stepA = (2 * lbo_a) >> 4, stepB = (2 * lbo_b) >> 4;
+#pragma unroll 1
 					for (int pass = 0; pass < 3; ++pass) {
 						const uint32_t pa = pass == 2 ? a_lo : a_hi, pb = pass == 1 ? b_lo : b_hi;
-						for (int k = 0; k < ksteps; ++k) {
-							tc::mma_tf32(d_tmem, tc::make_desc(pa + k * 2 * lbo_a, lbo_a, sbo), tc::make_desc(pb + k * 2 * lbo_b, lbo_b, sbo), idesc, acc);
-							acc = 1;
+						uint32_t da = ((pa >> 4) & 0x3FFF) | ((lbo_a >> 4) << 16);
+						uint32_t db = ((pb >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
+						int k = 0;
+						if (pass == 0) {
+							tc::mma_tf32_lohi<0>(d_tmem, da, dA_hi, db, dB_hi, idesc);     // first MMA of the block overwrites the slot
+							da += stepA;
+							db += stepB;
+							k = 1;
+						}
+#pragma unroll 2
+						for (; k < ksteps; ++k) {
+							tc::mma_tf32_lohi<1>(d_tmem, da, dA_hi, db, dB_hi, idesc);
+							da += stepA;
+							db += stepB;
 						}
 					}
 					tc::commit(&empty_b[st]);       // the B stage may be refilled once these MMAs have read it
@@ -218,9 +256,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 			}
 		}
 	} else {
-		// ======================= epilogue (4 warps; thread = frame row) =======================
-		const int q = warp & 3;                       // TMEM lane quarter this warp may access
+		// ======================= epilogue (8 warps; thread = frame row, warp pair = column halves) =======================
+		const int ew = warp - 2;                      // 0..7
+		const int q = warp & 3;                       // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+		const int half = ew >> 2;                     // ew 0-3 -> warps 2-5 (q = 2,3,0,1) take columns 0-31, ew 4-7 -> warps 6-9 take 32-63
 		const int row = q * 32 + lane;                // frame within the tile
+		int4 *my_ent = ent_s + ew * 32;
 		uint32_t it_s = 0;
 		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
 			const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
@@ -229,41 +270,102 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 			const int4 ft = A.ftiles[tile];
 			const bool valid = row < ft.y;
 			float m_run = -3.0e38f, s_run = 0.f;
-			int col_in_spk = 0;                       // columns of the current speaker consumed so far
+			int col_in_spk = 0;                       // columns of the current speaker consumed so far (by the pair)
 			int spk = chunk * A.spk_per_chunk;
 			const int cols_per_spk = (A.seg >= TC_NB) ? A.blocks_per_spk * TC_NB : A.seg;
 			for (int b = blk0; b < blk1; ++b, ++it_s) {
 				const int slot = it_s % TC_SLOTS;
+				const int4 *hl = A.hard + (size_t)b * (1 + TC_HMAX);
+				const int4 hdr = __ldg(hl);
+				const int e0 = half == 0 ? 0 : hdr.x, e1 = half == 0 ? hdr.x : hdr.y;
+				// stage this warp's share of the block's hard entries (prefetched before the accumulator is ready)
+				int4 mine = (e0 + lane < e1) ? __ldg(hl + 1 + e0 + lane) : make_int4(0, 0, 0, 0);
 				tc::wait(&tm_full[slot], (it_s / TC_SLOTS) & 1);
 				tc::fence_after();
-				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * TC_NB);
-#pragma unroll 1
-				for (int half = 0; half < 2; ++half) {
-					float v[32];
-					tc::ld32(taddr + half * 32, v);
-					tc_lse_update(v, m_run, s_run);
-					col_in_spk += 32;
-					if (col_in_spk == cols_per_spk) {
-						if (spk < A.S) {
-							const float l2 = m_run + lg2_approx(s_run);
-							float ll = l2 * TC_LN2;
-							if (A.clamp && !(ll >= -744.4400719213812f)) ll = -34.538776394910684f;
-							double local = valid ? (double)ll : 0.0;
-							if (valid && A.frame_ll != nullptr) A.frame_ll[(size_t)spk * A.ldf + ft.x + row] = A.frame_log2 ? l2 : ll;
-#pragma unroll
-							for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-							if (lane == 0) A.partial[((size_t)tile * A.S + spk) * 4 + q] = local;
-						}
-						m_run = -3.0e38f;
-						s_run = 0.f;
-						col_in_spk = 0;
-						++spk;
-					}
-				}
+				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * TC_NB + half * 32);
+				float v[32];
+				tc::ld32(taddr, v);
+				// the accumulator columns are in registers: release the slot right away
 				tc::fence_before();
 				__syncwarp();
 				if (lane == 0) mbar_arrive(&tm_empty[slot]);
+				// exact add-back of the (row, dim) entries kept out of the GEMM: the list is uniform across the warp, staged in
+				// shared memory 32 entries at a time and read back as broadcasts; the column switch is a uniform jump, v[] stays
+				// in registers
+#pragma unroll 1
+				for (int eb = e0; eb < e1; eb += 32) {
+					if (eb > e0) mine = (eb + lane < e1) ? __ldg(hl + 1 + eb + lane) : make_int4(0, 0, 0, 0);
+					__syncwarp();
+					my_ent[lane] = mine;
+					__syncwarp();
+					const int cnt = min(32, e1 - eb);
+					// software-pipelined: the entry and feature loads of entry j+1 are issued before the math / jump of entry j
+					const float *xrow = sA + (size_t)(row >> 3) * 32 + (row & 7) * 4;          // row part of the image offset
+					int4 en = my_ent[0];
+					float xh = xrow[en.y], xl = xrow[(size_t)TC_M * Kp + en.y];
+#pragma unroll 1
+					for (int j = 0; j < cnt; ++j) {
+						const int4 cur = en;
+						const float x = xh + xl;                                      // hi + lo is the fp32 feature exactly
+						if (j + 1 < cnt) {
+							en = my_ent[j + 1];
+							xh = xrow[en.y];
+							xl = xrow[(size_t)TC_M * Kp + en.y];
+						}
+						const float t = fmaf(x, __int_as_float(cur.z), __int_as_float(cur.w));
+						const float corr = t * t;
+						switch (cur.x & 31) {
+#define SRB_TC_CASE(c) case c: v[c] -= corr; break;
+							SRB_TC_CASE(0) SRB_TC_CASE(1) SRB_TC_CASE(2) SRB_TC_CASE(3) SRB_TC_CASE(4) SRB_TC_CASE(5) SRB_TC_CASE(6) SRB_TC_CASE(7)
+							SRB_TC_CASE(8) SRB_TC_CASE(9) SRB_TC_CASE(10) SRB_TC_CASE(11) SRB_TC_CASE(12) SRB_TC_CASE(13) SRB_TC_CASE(14) SRB_TC_CASE(15)
+							SRB_TC_CASE(16) SRB_TC_CASE(17) SRB_TC_CASE(18) SRB_TC_CASE(19) SRB_TC_CASE(20) SRB_TC_CASE(21) SRB_TC_CASE(22) SRB_TC_CASE(23)
+							SRB_TC_CASE(24) SRB_TC_CASE(25) SRB_TC_CASE(26) SRB_TC_CASE(27) SRB_TC_CASE(28) SRB_TC_CASE(29) SRB_TC_CASE(30) SRB_TC_CASE(31)
+#undef SRB_TC_CASE
+						}
+					}
+				}
+				// column segmentation: cols_per_spk >= 64 -> this warp's 32 columns belong to one speaker; cols_per_spk == 32 ->
+				// the lower-half warp holds speaker 2b', the upper-half warp speaker 2b'+1 (no merge needed)
+				tc_lse_update(v, m_run, s_run);
+				col_in_spk += TC_NB;
+				const bool spk_done = (cols_per_spk >= TC_NB) ? (col_in_spk == cols_per_spk) : true;
+				if (spk_done) {
+					float m = m_run, sacc = s_run;
+					int my_spk = spk;
+					bool writer = true;
+					if (cols_per_spk >= TC_NB) {
+						// merge the pair: the upper-half warp hands its (m, s) to the lower-half warp of the same lane quarter
+						if (half == 1) ms_x[row] = make_float2(m, sacc);
+						asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+						if (half == 0) {
+							const float2 o = ms_x[row];
+							const float M = fmaxf(m, o.x);
+							sacc = sacc * ex2_approx(m - M) + o.y * ex2_approx(o.x - M);
+							m = M;
+						}
+						asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // ms_x may be overwritten for the next speaker
+						writer = (half == 0);
+					} else {
+						my_spk = spk + half;                 // two 32-column speakers per block
+					}
+					if (writer && my_spk < A.S) {
+						const float l2 = m + lg2_approx(sacc);
+						float ll = l2 * TC_LN2;
+						if (A.clamp && !(ll >= -744.4400719213812f)) ll = -34.538776394910684f;
+						if (valid && A.frame_ll != nullptr) A.frame_ll[(size_t)my_spk * A.ldf + ft.x + row] = A.frame_log2 ? l2 : ll;
+						float local = valid ? ll : 0.f;
+#pragma unroll
+						for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+						if (lane == 0) A.partial[((size_t)tile * A.S + my_spk) * 4 + q] = (double)local;
+					}
+					m_run = -3.0e38f;
+					s_run = 0.f;
+					col_in_spk = 0;
+					spk += (cols_per_spk >= TC_NB) ? 1 : 2;
+				}
 			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(empty_a);      // this warp no longer needs the unit's A tile
 		}
 	}
 	tc::fence_before();

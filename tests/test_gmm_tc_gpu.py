@@ -97,7 +97,7 @@ def test_tc_route_full_size_config2(tc_route):
     scores = np.array(gs.predict_one_scores(X))
     assert int(np.argmax(scores)) == 37
     a, b = np.array(gs.predict_one_scores(X[:3333])), np.array(gs.predict_one_scores(X[3333:]))
-    assert np.max(np.abs((a + b) - scores) / np.abs(scores)) < 1e-9                       # additivity
+    assert np.max(np.abs((a + b) - scores) / np.abs(scores)) < 1e-7      # additivity (per-tile partials are fp32 warp sums here)
     for i in (0, 37, 99):
         ex = gmm_ref.score_all(W[i], M[i], Sg[i], X[:1000], gmm_ref.MODE_LOGDOMAIN)
         assert abs(gs.gmms[i].score_all(X[:1000]) - ex) < 2e-5 * abs(ex)
