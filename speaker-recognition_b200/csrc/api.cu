@@ -7,6 +7,7 @@
 #include <algorithm>
 #include "../../include/srb200.h"
 #include "kernels.h"
+#include "gmm_score_tc_layout.h"
 
 namespace srb {
 
@@ -104,23 +105,24 @@ void PackedModels::release() {
 void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *const *weights, const double *const *means,
                          const double *const *sigmas, const int *Ks) {
 	const int Kp = ((2 * D + 1 + 7) / 8) * 8;
-	const int cols = K <= 32 ? 32 : (K <= 64 ? 64 : ((K + 127) / 128) * 128);
+	const int NB = TC_NB;
+	const int cols = K <= 32 ? 32 : (K <= 64 ? 64 : ((K + NB - 1) / NB) * NB);
 	const long long rows_total = (long long)S * cols;
-	const int blocks = (int)((rows_total + 63) / 64);
-	const size_t bf = (size_t)2 * 64 * Kp;
+	const int blocks = (int)((rows_total + NB - 1) / NB);
+	const size_t bf = tc_b_block_floats(Kp);
 	pm.h_tc.assign((size_t)blocks * bf, 0.f);
 	pm.tc_Kp = Kp;
 	pm.tc_cols_per_spk = cols;
 	pm.tc_blocks_total = blocks;
 	const double A0 = 0.84932180028801904272;
-	constexpr int HMAX = 191;                    // = TC_HMAX (gmm_score_tc.cuh)
-	double HARD_SIGMA = 0.1;                     // = TC_HARD_SIGMA
+	double HARD_SIGMA = TC_HARD_SIGMA;
 	if (const char *eh = getenv("SRB200_TC_HARD_SIGMA")) HARD_SIGMA = atof(eh);   // experiments: 0 disables the add-back list
-	pm.h_tc_hard.assign((size_t)blocks * 4 * (1 + HMAX), 0);
-	std::vector<int> n_hard(blocks, 0), n_first(blocks, 0);
+	// hard-entry lists (layout: TcArgs::hard).  Rows ascend, so each block's list is sorted by column.
+	pm.h_tc_hard.assign((size_t)blocks * 4 * TC_HSTRIDE, 0);
+	std::vector<int> n_half(2 * blocks, 0);
 	bool overflow = false;
 	auto put = [&](long long row, int k, double w) {
-		const int blk = (int)(row / 64), r = (int)(row % 64);
+		const int blk = (int)(row / NB), r = (int)(row % NB);
 		const float wf = (float)w;
 		uint32_t u;
 		memcpy(&u, &wf, 4);
@@ -128,48 +130,52 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 		float hi;
 		memcpy(&hi, &u, 4);
 		const float lo = (float)(w - (double)hi);
-		const size_t off = (size_t)(k >> 2) * (64 / 8) * 32 + (size_t)(r >> 3) * 32 + (r & 7) * 4 + (k & 3);
+		const size_t off = tc_img_off(NB, r, k);
 		pm.h_tc[(size_t)blk * bf + off] = hi;
-		pm.h_tc[(size_t)blk * bf + (size_t)64 * Kp + off] = lo;
+		pm.h_tc[(size_t)blk * bf + (size_t)NB * Kp + off] = lo;
 	};
-	for (long long row = 0; row < (long long)blocks * 64; ++row) {     // rows ascend, so each block's list is sorted by column
+	for (long long row = 0; row < (long long)blocks * NB; ++row) {
 		const int s = (int)(row / cols), k = (int)(row % cols);
+		const int blk = (int)(row / NB), col = (int)(row % NB);
+		int *hdr = pm.h_tc_hard.data() + (size_t)blk * TC_HSTRIDE * 4;
 		if (s < S && k < Ks[s]) {
 			const double *mu = means[s] + (size_t)k * D, *sg = sigmas[s] + (size_t)k * D;
 			double C = weights[s][k] > 0.0 ? log2(weights[s][k]) : -1.0e30;
+			int *last_of_col = nullptr;
 			for (int d = 0; d < D; ++d) {
 				const double a = A0 / sg[d], nb = -mu[d] * a;
 				C -= log2(2.5066282746310002 * sg[d]);
 				if (sg[d] < HARD_SIGMA) {
 					// kept out of the GEMM (its three ~1e3 terms would cancel): exact add-back entry for the epilogue
-					const int blk = (int)(row / 64), col = (int)(row % 64);
-					if (n_hard[blk] >= HMAX) {
+					const int h = col >> 6;
+					if (n_half[2 * blk + h] >= TC_HHALF) {
 						overflow = true;
 						continue;
 					}
-					int *e = pm.h_tc_hard.data() + ((size_t)blk * (1 + HMAX) + 1 + n_hard[blk]) * 4;
+					const int idx = (h == 0 ? 0 : n_half[2 * blk]) + n_half[2 * blk + h];
+					int *e = hdr + (size_t)(2 + idx) * 4;
 					const float af = (float)a, nbf = (float)nb;
-					e[0] = col;
-					e[1] = ((D + d) >> 2) * (128 / 8) * 32 + ((D + d) & 3);   // K-group part of tc_img_off(128, row, D + d)
-					memcpy(&e[2], &af, 4);
-					memcpy(&e[3], &nbf, 4);
-					++n_hard[blk];
-					if (col < 32) ++n_first[blk];
+					e[0] = (int)tc_img_off(TC_M, 0, D + d) | ((col & 63) << 16);   // K-group part of the A-image offset of x_d (the x block
+					                                                      // starts at k = D) | column within the 64-column half
+					memcpy(&e[1], &af, 4);
+					memcpy(&e[2], &nbf, 4);
+					e[3] = 0;
+					last_of_col = e;
+					++n_half[2 * blk + h];
+					hdr[col >> 5] |= (int)(1u << (col & 31));
+					for (int g = (col >> 5) + 1; g <= 3; ++g) ++hdr[4 + g - 1];      // first entry of the later groups
+					++hdr[4 + 3];                                                     // total
 				} else {
 					put(row, d, -a * a);
 					put(row, D + d, -2.0 * a * nb);
 					C -= nb * nb;
 				}
 			}
+			if (last_of_col) last_of_col[3] = 1;
 			put(row, 2 * D, (C < -1.0e30 || C != C) ? -1.0e30 : C);
 		} else {
 			put(row, 2 * D, -1.0e30);      // padded row: exp2 underflows to exactly 0
 		}
-	}
-	for (int b = 0; b < blocks; ++b) {
-		int *h = pm.h_tc_hard.data() + (size_t)b * (1 + HMAX) * 4;
-		h[0] = n_first[b];
-		h[1] = n_hard[b];
 	}
 	if (overflow) {      // too many tiny-sigma entries for the sparse list: this model set stays on the FMA route
 		pm.h_tc.clear();

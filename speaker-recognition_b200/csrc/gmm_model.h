@@ -28,9 +28,9 @@ struct PackedModels {             // device-resident packed parameters of S mode
 	int S = 0, K = 0, Kpad = 0, D = 0, tiles_per_model = 0;
 	float *d_tiles = nullptr;     // S * tiles_per_model * tile_floats(D)
 	size_t bytes = 0;
-	// tensor-core path (gmm_score_tc.cuh): weight images [blocks][hi|lo][64*Kp], built on the host with the FMA tiles
+	// tensor-core path (gmm_score_tc.cuh): weight images [blocks][hi|lo][128*Kp], built on the host with the FMA tiles
 	std::vector<float> h_tc;      // host image, uploaded on first use
-	std::vector<int> h_tc_hard;   // per block: 4*(1+HMAX) ints (header + hard entries), see gmm_score_tc.cuh
+	std::vector<int> h_tc_hard;   // per block: 4*TC_HSTRIDE ints (two header words + hard entries), see gmm_score_tc.cuh
 	float *d_tc = nullptr;
 	int *d_tc_hard = nullptr;
 	int tc_Kp = 0, tc_cols_per_spk = 0, tc_blocks_total = 0;

@@ -43,8 +43,8 @@ __global__ void tc_prep_features_kernel(const float *__restrict__ X, int ld, int
 static bool g_tc_attr = false;
 
 size_t tc_smem_bytes(int Kp) {
-	// operand tiles + 14 mbarriers + TMEM slot word + pair-merge buffer [128] float2 + staged hard entries [8][32] int4
-	return (tc_a_tile_floats(Kp) + TC_BSTAGES * tc_b_block_floats(Kp)) * sizeof(float) + 128 + TC_M * 8 + 8 * 32 * 16 + 64;
+	// operand tiles + mbarriers / TMEM slot word (128 B) + staged hard entries [8][TC_HHALF + 1] int4 + pair-merge buffer [128] float2
+	return (tc_a_tile_floats(Kp) + (size_t)TC_BSTAGES * TC_NB * Kp) * sizeof(float) + 128 + 8 * (TC_HHALF + 1) * 16 + TC_M * 8 + 64;
 }
 
 bool tc_supported(const PackedModels &pm, int D) {
@@ -88,7 +88,10 @@ int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4
 	int n_chunks = 1;
 	if (n_ftiles < c.sm_count) n_chunks = std::min(pm.S, ceil_div(c.sm_count, n_ftiles));
 	int spc = ceil_div(pm.S, n_chunks);
-	if (pm.tc_cols_per_spk < TC_NB && (spc & 1)) ++spc;      // 32-column speakers: chunks start on block boundaries
+	if (pm.tc_cols_per_spk < TC_NB) {                        // small speakers: chunks start on block boundaries
+		const int per_block = TC_NB / pm.tc_cols_per_spk;
+		spc = ceil_div(spc, per_block) * per_block;
+	}
 	n_chunks = ceil_div(pm.S, spc);
 	a.n_chunks = n_chunks;
 	a.spk_per_chunk = spc;

@@ -13,38 +13,22 @@
 // epilogue, t = a x + nb, l2 -= t*t, from a per-block sparse list (about 1 % of the entries in the synthetic configs);
 // with that the route measures ~1e-6 per frame.
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
 //   warp 0  producer: cp.async.bulk of the pre-imaged operand blocks into shared memory (A: one 128-frame tile, hi|lo,
-//           resident for the whole unit; B: 64-row blocks, hi|lo, 2-stage ring), completion on mbarriers
-//   warp 1  MMA issuer: one elected lane issues 3 passes x Kp/8 tcgen05.mma (M=128, N=64, K=8) per B block into one of
-//           four 64-column TMEM accumulator slots, tcgen05.commit -> mbarriers (frees the B stage, publishes the slot)
-//   warps 2-9  epilogue: thread = frame row (TMEM lane); the two warps of a lane quarter take the column halves 0-31 / 32-63 of
-//           every block (tcgen05.ld 32 columns), each keeps an online log2-sum-exp2 over its half of the speaker's rows, the pair
+//           resident for the whole unit; B: 128-row blocks, the hi and the lo image one ring stage each), completion on mbarriers
+//   warp 1  MMA issuer: one elected lane issues 3 passes x Kp/8 tcgen05.mma (M=128, N=128, K=8) per B block into one of
+//           four 128-column TMEM accumulator slots, tcgen05.commit -> mbarriers (frees the B stage, publishes the slot)
+//   warps 2-9  epilogue: thread = frame row (TMEM lane); the two warps of a lane quarter take the column halves 0-63 / 64-127 of
+//           every block (two tcgen05.ld of 32 columns), each keeps an online log2-sum-exp2 over its half of the speaker's rows, the pair
 //           merges at the end of a speaker through shared memory; clamp / per-frame output / per-(tile, speaker) partial sums
 // Operands are K-major in the no-swizzle canonical layout (8-row x 16-byte core matrices; LBO = byte stride between
 // K-adjacent core matrices, SBO = 128 B between 8-row groups), verified by experiments/tc_gemm_test.cu; the images are
 // written to HBM in exactly the shared-memory order, so every load is ONE contiguous bulk copy.
 #pragma once
 #include "common.cuh"
+#include "gmm_score_tc_layout.h"
 
 namespace srb {
-
-constexpr int TC_M = 128;            // frames per tile (TMEM lanes)
-constexpr int TC_NB = 64;            // mixture rows per B block / accumulator slot
-constexpr int TC_SLOTS = 4;          // TMEM accumulator slots (4 x 64 = 256 columns)
-constexpr int TC_BSTAGES = 3;
-constexpr int TC_THREADS = 320;      // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter: column halves)
-constexpr float TC_LN2 = 0.69314718055994531f;
-constexpr int TC_HMAX = 191;         // capacity of a block's hard-entry list (+1 header = 192 int4 = 3 KB)
-constexpr double TC_HARD_SIGMA = 0.1;   // dims with sigma below this are kept out of the GEMM and added back exactly
-
-// floats per image block
-__host__ __device__ static inline size_t tc_a_tile_floats(int Kp) { return (size_t)2 * TC_M * Kp; }    // hi | lo
-__host__ __device__ static inline size_t tc_b_block_floats(int Kp) { return (size_t)2 * TC_NB * Kp; }
-// element (row r, k) of one part (hi or lo) of an image with `rows` rows: K-groups outermost
-__host__ __device__ static inline size_t tc_img_off(int rows, int r, int k) {
-	return (size_t)(k >> 2) * (rows / 8) * 32 + (size_t)(r >> 3) * 32 + (r & 7) * 4 + (k & 3);
-}
 
 struct TcArgs {
 	const float *A;            // [n_tiles][2][TC_M*Kp] feature images
@@ -53,7 +37,7 @@ struct TcArgs {
 	int n_ftiles;
 	int Kp;
 	int S;                     // speakers
-	int blocks_per_spk;        // 64-row blocks per speaker (rows padded to a multiple of 64) -- or, when seg < 64:
+	int blocks_per_spk;        // 128-row blocks per speaker (rows padded to a multiple of 128) -- or, when seg < 128:
 	int seg;                   // columns per speaker inside a block (32 or 64) when a speaker is smaller than a block
 	int n_blocks_total;
 	int n_chunks;              // the block range is cut into n_chunks contiguous chunks (whole speakers each)
@@ -63,8 +47,10 @@ struct TcArgs {
 	double *partial;           // [n_ftiles][S][4]
 	int clamp, frame_log2;
 	int D;
-	const int4 *hard;          // [n_blocks_total][1 + TC_HMAX]: header {n_first_half, n_total, 0, 0}, then entries sorted by
-	                           // column: {column in block, image offset of the feature x_dim (K-group part), float bits of a, of nb}
+	const int4 *hard;          // [n_blocks_total][TC_HSTRIDE]: header 0 = bit masks of the columns with entries in the four
+	                           // 32-column groups, header 1 = {first entry of group 1, of group 2, of group 3, total}; entries sorted
+	                           // by column: {image offset of x_dim (K-group part) | column within its 64-column half << 16, float bits of a, of nb,
+	                           // 1 if last of its column}
 };
 
 namespace tc {
@@ -144,19 +130,46 @@ __device__ __forceinline__ void tc_lse_update(const float *v, float &m_run, floa
 	m_run = m_new;
 }
 
+// Exact add-back, phase 1 (runs BEFORE the block's accumulator is complete, i.e. overlapped with its MMAs): walk this warp's
+// hard entries -- uniform across the warp, staged in shared memory, sorted by column, `last` flag on the final entry of a
+// column -- sum t^2 per column in a scalar register and park the sum in the warp's TMEM scratch column with a
+// one-column tcgen05.st.  TMEM addresses may be dynamic, registers may not: this is what removes the per-entry column
+// switch of the first version (ncu: 116 SM sub-partition cycles per entry).  Nothing in the loop depends on the previous
+// entry except the running sum, so the loads pipeline.
+__device__ __forceinline__ void tc_addback_park(const int4 *e, int n, const float *xrow, size_t lo_off, uint32_t scratch_taddr) {
+	float csum = 0.f;
+#pragma unroll 4
+	for (int i = 0; i < n; ++i) {
+		const int4 en = e[i];
+		const float x = xrow[en.x & 0xFFFF] + xrow[lo_off + (en.x & 0xFFFF)];          // hi + lo is the fp32 feature exactly
+		const float t = fmaf(x, __int_as_float(en.y), __int_as_float(en.z));
+		csum = fmaf(t, t, csum);
+		if (en.w) {                                                                      // uniform: last entry of column en.x >> 16
+			asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(scratch_taddr + (uint32_t)(en.x >> 16)), "r"(__float_as_uint(csum)) : "memory");
+			csum = 0.f;
+		}
+	}
+}
+// phase 2: subtract the parked sums from the accumulator columns that have entries (c[] of the other columns is stale data)
+__device__ __forceinline__ void tc_addback_apply(float (&v)[32], const float (&c)[32], uint32_t mask) {
+#pragma unroll
+	for (int j = 0; j < 32; ++j) v[j] -= (mask & (1u << j)) ? c[j] : 0.f;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArgs A) {
 	extern __shared__ __align__(1024) unsigned char tc_smem[];
 	const int Kp = A.Kp;
 	const uint32_t a_part_bytes = (uint32_t)TC_M * Kp * 4, b_part_bytes = (uint32_t)TC_NB * Kp * 4;
+	const size_t b_part_floats = (size_t)TC_NB * Kp;
 	float *sA = reinterpret_cast<float *>(tc_smem);                                  // hi | lo
-	float *sB = sA + tc_a_tile_floats(Kp);                                           // [stages][hi | lo]
-	uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TC_BSTAGES * tc_b_block_floats(Kp));
+	float *sB = sA + tc_a_tile_floats(Kp);                                           // [stages] one part each
+	uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TC_BSTAGES * b_part_floats);
 	uint64_t *full_a = bars, *empty_a = bars + 1;
 	uint64_t *full_b = bars + 2, *empty_b = full_b + TC_BSTAGES;
 	uint64_t *tm_full = empty_b + TC_BSTAGES, *tm_empty = tm_full + TC_SLOTS;
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + TC_SLOTS);
-	int4 *ent_s = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(bars) + 128);   // [8 warps][32] staged hard entries (16-B aligned)
-	float2 *ms_x = reinterpret_cast<float2 *>(ent_s + 8 * 32);                       // [128] (m, s) of the upper-half warps
+	int4 *ent_s = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(bars) + 128);   // [8 warps][TC_HHALF + 1] staged hard entries
+	float2 *ms_x = reinterpret_cast<float2 *>(ent_s + 8 * (TC_HHALF + 1));           // [128] (m, s) of the upper-half warps
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	if (tid == 0) {
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 		fence_mbar_init();
 	}
 	if (warp == 1) {
-		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_SLOTS * TC_NB)));
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
 	}
 	tc::fence_before();
@@ -188,7 +201,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 	if (warp == 0) {
 		// ======================= producer =======================
 		if (lane == 0) {
-			uint32_t it_b = 0, it_a = 0;
+			uint32_t it_p = 0, it_a = 0;
 			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it_a) {
 				const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
 				const int blk0 = chunk * blocks_per_chunk_full;
@@ -196,11 +209,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 				tc::wait(empty_a, (it_a & 1) ^ 1);
 				mbar_expect_tx(full_a, 2 * a_part_bytes);
 				bulk_g2s(sA, A.A + (size_t)tile * tc_a_tile_floats(Kp), 2 * a_part_bytes, full_a);
-				for (int b = blk0; b < blk1; ++b, ++it_b) {
-					const int st = it_b % TC_BSTAGES;
-					tc::wait(&empty_b[st], ((it_b / TC_BSTAGES) & 1) ^ 1);
-					mbar_expect_tx(&full_b[st], 2 * b_part_bytes);
-					bulk_g2s(sB + (size_t)st * tc_b_block_floats(Kp), A.B + (size_t)b * tc_b_block_floats(Kp), 2 * b_part_bytes, &full_b[st]);
+				// the block's hi image, then its lo image: one stage each, contiguous in HBM
+				const float *src = A.B + (size_t)blk0 * tc_b_block_floats(Kp);
+				for (int p = 2 * (blk1 - blk0); p > 0; --p, ++it_p, src += b_part_floats) {
+					const int st = it_p % TC_BSTAGES;
+					tc::wait(&empty_b[st], ((it_p / TC_BSTAGES) & 1) ^ 1);
+					mbar_expect_tx(&full_b[st], b_part_bytes);
+					bulk_g2s(sB + (size_t)st * b_part_floats, src, b_part_bytes, &full_b[st]);
 				}
 			}
 		}
@@ -210,47 +225,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 			// instruction descriptor: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9 / 10-12 = 2), both K-major, N>>3 at bit 17, M>>4 at bit 24
 			const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NB >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 			const uint32_t lbo_a = (TC_M / 8) * 128, lbo_b = (TC_NB / 8) * 128, sbo = 128;
+			// descriptors are two words; only the 14-bit start-address field of the low word advances between k-steps
+			const uint32_t d_hi = (uint32_t)(sbo >> 4) | (1u << 14);            // SBO | version bit 46
+			const uint32_t stepA = (2 * lbo_a) >> 4, stepB = (2 * lbo_b) >> 4;
 			const int ksteps = Kp / 8;
-			uint32_t it_b = 0, it_a = 0, it_s = 0;
+			uint32_t it_p = 0, it_a = 0, it_s = 0;
 			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it_a) {
 				const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
 				const int blk0 = chunk * blocks_per_chunk_full;
 				const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
 				tc::wait(full_a, it_a & 1);
 				const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + a_part_bytes;
-				for (int b = blk0; b < blk1; ++b, ++it_b, ++it_s) {
-					const int st = it_b % TC_BSTAGES, slot = it_s % TC_SLOTS;
+				const uint32_t dA_hi0 = ((a_hi >> 4) & 0x3FFF) | ((lbo_a >> 4) << 16), dA_lo0 = ((a_lo >> 4) & 0x3FFF) | ((lbo_a >> 4) << 16);
+				for (int b = blk0; b < blk1; ++b, ++it_s) {
+					const int slot = it_s % TC_SLOTS;
 					tc::wait(&tm_empty[slot], ((it_s / TC_SLOTS) & 1) ^ 1);
-					tc::wait(&full_b[st], (it_b / TC_BSTAGES) & 1);
-					tc::fence_after();
-					const uint32_t b_hi = smem_u32(sB + (size_t)st * tc_b_block_floats(Kp)), b_lo = b_hi + b_part_bytes;
 					const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TC_NB);
-					// 3xTF32: hi*hi, hi*lo, lo*hi.  The issuing thread is the critical resource (ncu: the first version spent ~100
-					// cycles per MMA building descriptors against 32 cycles of tensor-pipe time), so descriptors are two constant
-					// words; only the 14-bit start-address field in the low word advances, by one add per operand per k-step.
-					const uint32_t dA_hi = (uint32_t)(sbo >> 4) | (1u << 14), dB_hi = dA_hi;            // SBO | version bit 46
-					const uint32_t stepA = (2 * lbo_a) >> 4, stepB = (2 * lbo_b) >> 4;
-#pragma unroll 1
-					for (int pass = 0; pass < 3; ++pass) {
-						const uint32_t pa = pass == 2 ? a_lo : a_hi, pb = pass == 1 ? b_lo : b_hi;
-						uint32_t da = ((pa >> 4) & 0x3FFF) | ((lbo_a >> 4) << 16);
-						uint32_t db = ((pb >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
-						int k = 0;
-						if (pass == 0) {
-							tc::mma_tf32_lohi<0>(d_tmem, da, dA_hi, db, dB_hi, idesc);     // first MMA of the block overwrites the slot
-							da += stepA;
-							db += stepB;
-							k = 1;
-						}
+					// 3xTF32: (A_hi + A_lo) * B_hi from the first stage, A_hi * B_lo from the second
+					{
+						const int st = it_p % TC_BSTAGES;
+						tc::wait(&full_b[st], (it_p / TC_BSTAGES) & 1);
+						tc::fence_after();
+						const uint32_t dB0 = ((smem_u32(sB + (size_t)st * b_part_floats) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
+						uint32_t da = dA_hi0, db = dB0;
+						tc::mma_tf32_lohi<0>(d_tmem, da, d_hi, db, d_hi, idesc);        // first MMA of the block overwrites the slot
 #pragma unroll 2
-						for (; k < ksteps; ++k) {
-							tc::mma_tf32_lohi<1>(d_tmem, da, dA_hi, db, dB_hi, idesc);
+						for (int k = 1; k < ksteps; ++k) {
+							da += stepA;
+							db += stepB;
+							tc::mma_tf32_lohi<1>(d_tmem, da, d_hi, db, d_hi, idesc);
+						}
+						da = dA_lo0;
+						db = dB0;
+#pragma unroll 2
+						for (int k = 0; k < ksteps; ++k) {
+							tc::mma_tf32_lohi<1>(d_tmem, da, d_hi, db, d_hi, idesc);
 							da += stepA;
 							db += stepB;
 						}
+						tc::commit(&empty_b[st]);       // the stage may be refilled once these MMAs have read it
+						++it_p;
 					}
-					tc::commit(&empty_b[st]);       // the B stage may be refilled once these MMAs have read it
-					tc::commit(&tm_full[slot]);     // ... and the accumulator slot is complete
+					{
+						const int st = it_p % TC_BSTAGES;
+						tc::wait(&full_b[st], (it_p / TC_BSTAGES) & 1);
+						tc::fence_after();
+						uint32_t da = dA_hi0;
+						uint32_t db = ((smem_u32(sB + (size_t)st * b_part_floats) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
+#pragma unroll 2
+						for (int k = 0; k < ksteps; ++k) {
+							tc::mma_tf32_lohi<1>(d_tmem, da, d_hi, db, d_hi, idesc);
+							da += stepA;
+							db += stepB;
+						}
+						tc::commit(&empty_b[st]);
+						++it_p;
+					}
+					tc::commit(&tm_full[slot]);     // the accumulator slot is complete
 				}
 				tc::commit(empty_a);                // the A tile may be replaced
 			}
@@ -259,109 +290,109 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 		// ======================= epilogue (8 warps; thread = frame row, warp pair = column halves) =======================
 		const int ew = warp - 2;                      // 0..7
 		const int q = warp & 3;                       // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
-		const int half = ew >> 2;                     // ew 0-3 -> warps 2-5 (q = 2,3,0,1) take columns 0-31, ew 4-7 -> warps 6-9 take 32-63
+		const int half = ew >> 2;                     // warps 2-5 take columns 0-63 of every block, warps 6-9 columns 64-127
 		const int row = q * 32 + lane;                // frame within the tile
-		int4 *my_ent = ent_s + ew * 32;
-		uint32_t it_s = 0;
-		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+		int4 *my_ent = ent_s + ew * (TC_HHALF + 1);
+		const float *xrow = sA + (size_t)(row >> 3) * 32 + (row & 7) * 4;          // row part of the A image offset
+		const size_t lo_off = (size_t)TC_M * Kp;
+		const int seg = A.seg;
+		const int cols_per_spk = (seg >= TC_NB) ? A.blocks_per_spk * TC_NB : seg;
+		uint32_t it_s = 0, it_a = 0;
+		for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it_a) {
 			const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
 			const int blk0 = chunk * blocks_per_chunk_full;
 			const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
 			const int4 ft = A.ftiles[tile];
 			const bool valid = row < ft.y;
+			tc::wait(full_a, it_a & 1);               // the add-back reads x from the unit's A tile before the first accumulator wait
 			float m_run = -3.0e38f, s_run = 0.f;
 			int col_in_spk = 0;                       // columns of the current speaker consumed so far (by the pair)
-			int spk = chunk * A.spk_per_chunk;
-			const int cols_per_spk = (A.seg >= TC_NB) ? A.blocks_per_spk * TC_NB : A.seg;
+			int spk = chunk * A.spk_per_chunk;        // first speaker of the current block
+
+			// close a speaker: optional pair merge, clamp, per-frame output, per-(tile, speaker, lane quarter) partial sum
+			auto finish = [&](int my_spk, bool merge) {
+				float m = m_run, sacc = s_run;
+				bool writer = true;
+				if (merge) {
+					// the upper-half warp hands its (m, s) to the lower-half warp of the same lane quarter
+					if (half == 1) ms_x[row] = make_float2(m, sacc);
+					asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+					if (half == 0) {
+						const float2 o = ms_x[row];
+						const float M = fmaxf(m, o.x);
+						sacc = sacc * ex2_approx(m - M) + o.y * ex2_approx(o.x - M);
+						m = M;
+					}
+					asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // ms_x may be overwritten for the next speaker
+					writer = (half == 0);
+				}
+				if (writer && my_spk < A.S) {
+					const float l2 = m + lg2_approx(sacc);
+					float ll = l2 * TC_LN2;
+					if (A.clamp && !(ll >= -744.4400719213812f)) ll = -34.538776394910684f;
+					if (valid && A.frame_ll != nullptr) A.frame_ll[(size_t)my_spk * A.ldf + ft.x + row] = A.frame_log2 ? l2 : ll;
+					float local = valid ? ll : 0.f;
+#pragma unroll
+					for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+					if (lane == 0) A.partial[((size_t)tile * A.S + my_spk) * 4 + q] = (double)local;
+				}
+				m_run = -3.0e38f;
+				s_run = 0.f;
+			};
+
 			for (int b = blk0; b < blk1; ++b, ++it_s) {
 				const int slot = it_s % TC_SLOTS;
-				const int4 *hl = A.hard + (size_t)b * (1 + TC_HMAX);
-				const int4 hdr = __ldg(hl);
-				const int e0 = half == 0 ? 0 : hdr.x, e1 = half == 0 ? hdr.x : hdr.y;
-				// stage this warp's share of the block's hard entries (prefetched before the accumulator is ready)
-				int4 mine = (e0 + lane < e1) ? __ldg(hl + 1 + e0 + lane) : make_int4(0, 0, 0, 0);
+				// stage this warp's share of the block's hard entries (before the accumulator is ready)
+				const int4 *hl = A.hard + (size_t)b * TC_HSTRIDE;
+				const int4 hmask = __ldg(hl), hoff = __ldg(hl + 1);
+				const int e0 = half == 0 ? 0 : hoff.y, e1 = half == 0 ? hoff.y : hoff.w;
+				const uint32_t mask0 = (uint32_t)(half == 0 ? hmask.x : hmask.z), mask1 = (uint32_t)(half == 0 ? hmask.y : hmask.w);
+				__syncwarp();
+				for (int i = lane; i < e1 - e0; i += 32)
+					my_ent[i] = __ldg(hl + 2 + e0 + i);
+				__syncwarp();
+				const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+				const uint32_t scratch = lane_base + (uint32_t)(TC_SLOTS * TC_NB + half * 64);      // this warp's 64 scratch columns
+				tc_addback_park(my_ent, e1 - e0, xrow, lo_off, scratch);
+				asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 				tc::wait(&tm_full[slot], (it_s / TC_SLOTS) & 1);
 				tc::fence_after();
-				const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * TC_NB + half * 32);
-				float v[32];
-				tc::ld32(taddr, v);
+				const uint32_t taddr = lane_base + (uint32_t)(slot * TC_NB + half * 64);
+				float v0[32], v1[32];
+				tc::ld32(taddr, v0);
+				tc::ld32(taddr + 32, v1);
 				// the accumulator columns are in registers: release the slot right away
 				tc::fence_before();
 				__syncwarp();
 				if (lane == 0) mbar_arrive(&tm_empty[slot]);
-				// exact add-back of the (row, dim) entries kept out of the GEMM: the list is uniform across the warp, staged in
-				// shared memory 32 entries at a time and read back as broadcasts; the column switch is a uniform jump, v[] stays
-				// in registers
-#pragma unroll 1
-				for (int eb = e0; eb < e1; eb += 32) {
-					if (eb > e0) mine = (eb + lane < e1) ? __ldg(hl + 1 + eb + lane) : make_int4(0, 0, 0, 0);
-					__syncwarp();
-					my_ent[lane] = mine;
-					__syncwarp();
-					const int cnt = min(32, e1 - eb);
-					// software-pipelined: the entry and feature loads of entry j+1 are issued before the math / jump of entry j
-					const float *xrow = sA + (size_t)(row >> 3) * 32 + (row & 7) * 4;          // row part of the image offset
-					int4 en = my_ent[0];
-					float xh = xrow[en.y], xl = xrow[(size_t)TC_M * Kp + en.y];
-#pragma unroll 1
-					for (int j = 0; j < cnt; ++j) {
-						const int4 cur = en;
-						const float x = xh + xl;                                      // hi + lo is the fp32 feature exactly
-						if (j + 1 < cnt) {
-							en = my_ent[j + 1];
-							xh = xrow[en.y];
-							xl = xrow[(size_t)TC_M * Kp + en.y];
-						}
-						const float t = fmaf(x, __int_as_float(cur.z), __int_as_float(cur.w));
-						const float corr = t * t;
-						switch (cur.x & 31) {
-#define SRB_TC_CASE(c) case c: v[c] -= corr; break;
-							SRB_TC_CASE(0) SRB_TC_CASE(1) SRB_TC_CASE(2) SRB_TC_CASE(3) SRB_TC_CASE(4) SRB_TC_CASE(5) SRB_TC_CASE(6) SRB_TC_CASE(7)
-							SRB_TC_CASE(8) SRB_TC_CASE(9) SRB_TC_CASE(10) SRB_TC_CASE(11) SRB_TC_CASE(12) SRB_TC_CASE(13) SRB_TC_CASE(14) SRB_TC_CASE(15)
-							SRB_TC_CASE(16) SRB_TC_CASE(17) SRB_TC_CASE(18) SRB_TC_CASE(19) SRB_TC_CASE(20) SRB_TC_CASE(21) SRB_TC_CASE(22) SRB_TC_CASE(23)
-							SRB_TC_CASE(24) SRB_TC_CASE(25) SRB_TC_CASE(26) SRB_TC_CASE(27) SRB_TC_CASE(28) SRB_TC_CASE(29) SRB_TC_CASE(30) SRB_TC_CASE(31)
-#undef SRB_TC_CASE
-						}
-					}
+				if (mask0) {
+					float c[32];
+					tc::ld32(scratch, c);
+					tc_addback_apply(v0, c, mask0);
 				}
-				// column segmentation: cols_per_spk >= 64 -> this warp's 32 columns belong to one speaker; cols_per_spk == 32 ->
-				// the lower-half warp holds speaker 2b', the upper-half warp speaker 2b'+1 (no merge needed)
-				tc_lse_update(v, m_run, s_run);
-				col_in_spk += TC_NB;
-				const bool spk_done = (cols_per_spk >= TC_NB) ? (col_in_spk == cols_per_spk) : true;
-				if (spk_done) {
-					float m = m_run, sacc = s_run;
-					int my_spk = spk;
-					bool writer = true;
-					if (cols_per_spk >= TC_NB) {
-						// merge the pair: the upper-half warp hands its (m, s) to the lower-half warp of the same lane quarter
-						if (half == 1) ms_x[row] = make_float2(m, sacc);
-						asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-						if (half == 0) {
-							const float2 o = ms_x[row];
-							const float M = fmaxf(m, o.x);
-							sacc = sacc * ex2_approx(m - M) + o.y * ex2_approx(o.x - M);
-							m = M;
-						}
-						asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // ms_x may be overwritten for the next speaker
-						writer = (half == 0);
-					} else {
-						my_spk = spk + half;                 // two 32-column speakers per block
+				if (mask1) {
+					float c[32];
+					tc::ld32(scratch + 32, c);
+					tc_addback_apply(v1, c, mask1);
+				}
+				// column segmentation: seg >= 128 -> the block belongs to one speaker (pair merge at its end); seg == 64 -> this
+				// warp's 64 columns are one speaker; seg == 32 -> each 32-column group is one speaker
+				tc_lse_update(v0, m_run, s_run);
+				if (seg == 32) finish(spk + 2 * half, false);
+				tc_lse_update(v1, m_run, s_run);
+				if (seg == 32) {
+					finish(spk + 2 * half + 1, false);
+					spk += 4;
+				} else if (seg == 64) {
+					finish(spk + half, false);
+					spk += 2;
+				} else {
+					col_in_spk += TC_NB;
+					if (col_in_spk == cols_per_spk) {
+						finish(spk, true);
+						col_in_spk = 0;
+						++spk;
 					}
-					if (writer && my_spk < A.S) {
-						const float l2 = m + lg2_approx(sacc);
-						float ll = l2 * TC_LN2;
-						if (A.clamp && !(ll >= -744.4400719213812f)) ll = -34.538776394910684f;
-						if (valid && A.frame_ll != nullptr) A.frame_ll[(size_t)my_spk * A.ldf + ft.x + row] = A.frame_log2 ? l2 : ll;
-						float local = valid ? ll : 0.f;
-#pragma unroll
-						for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-						if (lane == 0) A.partial[((size_t)tile * A.S + my_spk) * 4 + q] = (double)local;
-					}
-					m_run = -3.0e38f;
-					s_run = 0.f;
-					col_in_spk = 0;
-					spk += (cols_per_spk >= TC_NB) ? 1 : 2;
 				}
 			}
 			__syncwarp();
@@ -370,7 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 	}
 	tc::fence_before();
 	__syncthreads();
-	if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_SLOTS * TC_NB)));
+	if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
 }  // namespace srb
