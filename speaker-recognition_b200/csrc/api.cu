@@ -155,8 +155,7 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 					const int idx = (h == 0 ? 0 : n_half[2 * blk]) + n_half[2 * blk + h];
 					int *e = hdr + (size_t)(2 + idx) * 4;
 					const float af = (float)a, nbf = (float)nb;
-					e[0] = (int)tc_img_off(TC_M, 0, D + d) | ((col & 63) << 16);   // K-group part of the A-image offset of x_d (the x block
-					                                                      // starts at k = D) | column within the 64-column half
+					e[0] = d | ((col & 63) << 16);               // feature dim | column within the 64-column half
 					memcpy(&e[1], &af, 4);
 					memcpy(&e[2], &nbf, 4);
 					e[3] = 0;

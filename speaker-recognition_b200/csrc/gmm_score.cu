@@ -342,7 +342,6 @@ struct TileTable {
 	int4 *d_ftiles = nullptr;
 	int *d_utt_tile_start = nullptr;
 	double *d_partial = nullptr;
-	float *d_Aimg = nullptr;         // tensor-core route: feature images, allocated on first use
 	uint64_t stamp = 0;
 };
 static std::vector<TileTable> g_tables;
@@ -352,7 +351,6 @@ static void free_table(TileTable &t) {
 	if (t.d_ftiles) cudaFree(t.d_ftiles);
 	if (t.d_utt_tile_start) cudaFree(t.d_utt_tile_start);
 	if (t.d_partial) cudaFree(t.d_partial);
-	if (t.d_Aimg) cudaFree(t.d_Aimg);
 	t = TileTable();
 }
 
@@ -464,9 +462,7 @@ int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *ut
 	if (path == 1 && !frame_log2 && tc_supported(pm, D)) {
 		TileTable *tt = nullptr;
 		if (get_table(utt_off, n_utt, pm.S, 128, st, &tt)) return 1;
-		if (tt->n_ftiles > 0 && tt->d_Aimg == nullptr)
-			SRB_CUDA(cudaMalloc(&tt->d_Aimg, (size_t)tt->n_ftiles * 2 * 128 * pm.tc_Kp * sizeof(float)));
-		if (launch_score_tc(pm, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_Aimg, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;
+		if (launch_score_tc(pm, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;
 		score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, 4, d_sums, d_best);
 		SRB_CUDA(cudaGetLastError());
 		return 0;

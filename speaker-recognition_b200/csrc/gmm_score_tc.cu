@@ -4,57 +4,22 @@
 
 namespace srb {
 
-// feature images: per 128-frame tile, PHI = [x^2 (D), x (D), 1, 0-pad] split into TF32 hi / fp32 remainder lo, written in
-// the shared-memory order of the MMA's A operand so the scorer loads a tile with one bulk copy.
-// One thread per (tile, row, 4-wide k-group): both parts as one float4 each.
-__global__ void tc_prep_features_kernel(const float *__restrict__ X, int ld, int D, int Kp, const int4 *__restrict__ ftiles, int n_ftiles,
-                                        float *__restrict__ Aimg) {
-	const int kgs = Kp >> 2;
-	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const long long total = (long long)n_ftiles * kgs * TC_M;
-	if (idx >= total) return;
-	const int r = (int)(idx % TC_M);
-	const int kg = (int)((idx / TC_M) % kgs);
-	const int tile = (int)(idx / ((long long)TC_M * kgs));
-	const int4 ft = ftiles[tile];
-	float hi[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
-	if (r < ft.y) {
-		const float *row = X + (size_t)(ft.x + r) * ld;
-#pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			const int k = 4 * kg + j;
-			float v = 0.f;
-			if (k < D) {
-				const float x = __ldg(row + k);
-				v = x * x;
-			} else if (k < 2 * D) v = __ldg(row + k - D);
-			else if (k == 2 * D) v = 1.f;
-			const float h = __uint_as_float(__float_as_uint(v) & ~0x1FFFu);
-			hi[j] = h;
-			lo[j] = v - h;
-		}
-	}
-	float *base = Aimg + (size_t)tile * tc_a_tile_floats(Kp);
-	const size_t off = (size_t)kg * (TC_M / 8) * 32 + (size_t)(r >> 3) * 32 + (r & 7) * 4;
-	*reinterpret_cast<float4 *>(base + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-	*reinterpret_cast<float4 *>(base + (size_t)TC_M * Kp + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-}
-
 static bool g_tc_attr = false;
 
-size_t tc_smem_bytes(int Kp) {
-	// operand tiles + mbarriers / TMEM slot word (128 B) + staged hard entries [8][TC_HHALF + 1] int4 + pair-merge buffer [128] float2
-	return (tc_a_tile_floats(Kp) + (size_t)TC_BSTAGES * TC_NB * Kp) * sizeof(float) + 128 + 8 * (TC_HHALF + 1) * 16 + TC_M * 8 + 64;
+size_t tc_smem_bytes(int Kp, int D) {
+	// B part stages + hard-entry ring + add-back scratch [16][32][32] + merge buffer [3][128] float2 + mbarriers / TMEM slot word
+	// (256 B) + raw feature tile [128][D|1]
+	return (size_t)TC_BSTAGES * TC_NB * Kp * sizeof(float) + (size_t)TC_HSTAGES * TC_HSTRIDE * 16 + 16 * 32 * 32 * sizeof(float) + 3 * TC_M * 8 + 256 +
+	       (size_t)TC_M * tc_x_stride(D) * sizeof(float);
 }
 
 bool tc_supported(const PackedModels &pm, int D) {
-	return !pm.h_tc.empty() && pm.tc_Kp == ((2 * D + 1 + 7) / 8) * 8 && tc_smem_bytes(pm.tc_Kp) <= 227 * 1024 - 1024;
+	return !pm.h_tc.empty() && pm.tc_Kp == ((2 * D + 1 + 7) / 8) * 8 && pm.tc_Kp <= TC_KP_MAX && tc_smem_bytes(pm.tc_Kp, D) <= 227 * 1024;
 }
 
-// d_ftiles: frame tiles of TC_M frames (device), d_Aimg: workspace of n_ftiles * tc_a_tile_floats(Kp) floats,
-// d_partial: [n_ftiles][S][4] doubles
-int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, float *d_Aimg, double *d_partial,
-                    float *d_frame_ll, int ldf, int clamp, int frame_log2, cudaStream_t st) {
+// d_ftiles: frame tiles of TC_M frames (device), d_partial: [n_ftiles][S][4] doubles
+int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, double *d_partial, float *d_frame_ll,
+                    int ldf, int clamp, int frame_log2, cudaStream_t st) {
 	Context &c = ctx();
 	const int Kp = pm.tc_Kp;
 	if (pm.d_tc == nullptr) {
@@ -69,13 +34,9 @@ int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4
 		g_tc_attr = true;
 	}
 	if (n_ftiles <= 0) return 0;
-	{
-		const long long total = (long long)n_ftiles * (Kp / 4) * TC_M;
-		tc_prep_features_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dX, ld, D, Kp, d_ftiles, n_ftiles, d_Aimg);
-		SRB_CUDA(cudaGetLastError());
-	}
 	TcArgs a;
-	a.A = d_Aimg;
+	a.X = dX;
+	a.ld = ld;
 	a.B = pm.d_tc;
 	a.ftiles = d_ftiles;
 	a.n_ftiles = n_ftiles;
@@ -104,7 +65,7 @@ int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4
 	a.hard = reinterpret_cast<const int4 *>(pm.d_tc_hard);
 	const long long units = (long long)n_ftiles * n_chunks;
 	const int grid = (int)std::min<long long>(units, c.sm_count);
-	gmm_score_tc_kernel<<<grid, TC_THREADS, tc_smem_bytes(Kp), st>>>(a);
+	gmm_score_tc_kernel<<<grid, TC_THREADS, tc_smem_bytes(Kp, D), st>>>(a);
 	SRB_CUDA(cudaGetLastError());
 	return 0;
 }

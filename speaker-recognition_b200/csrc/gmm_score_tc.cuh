@@ -4,26 +4,31 @@
 // the Mahalanobis term is expanded,
 //     l2_k(x) = C_k + sum_d [ (-a_kd^2) x_d^2 + (-2 a_kd nb_kd) x_d ],     C_k = c2_k - sum_d nb_kd^2,
 // i.e. a GEMM  L[frames x rows] = PHI[frames x Kp] . W[rows x Kp]^T  with PHI = [x^2, x, 1, 0-pad], Kp = 8*ceil((2D+1)/8),
-// run on the 5th-generation tensor cores as 3xTF32 (hi*hi + hi*lo + lo*hi; fp32 accumulate in TMEM).  Measured on B200
-// against float64 (experiments/tf32_numerics.py, C2-shaped models incl. sigma-floor entries): max per-frame
-// |LL - LL64| / max(1,|LL64|) = 3.7e-5 -- inside the 1e-4 bound, argmax identical -- versus 2e-7 for the FMA kernel,
-// which therefore stays the default; this path is selected explicitly (SRB200_SCORE_TC=1 / srb200_set_score_path).
-// The residual error of the expanded form comes from dimensions with a tiny sigma (the trainer's floor 0.0316): their three
-// terms are ~1e3 each and cancel.  Those (row, dim) entries are therefore left out of W and C and added back EXACTLY in the
+// run on the 5th-generation tensor cores as 3xTF32 (hi*hi + lo*hi + hi*lo; fp32 accumulate in TMEM).
+// The expanded form loses accuracy on dimensions with a tiny sigma (the trainer's floor is 0.0316): their three terms are
+// ~1e3 each and cancel.  Those (row, dim) entries are therefore left out of W and C and added back EXACTLY in the
 // epilogue, t = a x + nb, l2 -= t*t, from a per-block sparse list (about 1 % of the entries in the synthetic configs);
-// with that the route measures ~1e-6 per frame.
+// with that the route measures ~1e-6 per frame against float64 (experiments/tf32_numerics*.py, tests/test_gmm_tc_gpu.py).
 //
-// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
-//   warp 0  producer: cp.async.bulk of the pre-imaged operand blocks into shared memory (A: one 128-frame tile, hi|lo,
-//           resident for the whole unit; B: 128-row blocks, the hi and the lo image one ring stage each), completion on mbarriers
-//   warp 1  MMA issuer: one elected lane issues 3 passes x Kp/8 tcgen05.mma (M=128, N=128, K=8) per B block into one of
-//           four 128-column TMEM accumulator slots, tcgen05.commit -> mbarriers (frees the B stage, publishes the slot)
-//   warps 2-9  epilogue: thread = frame row (TMEM lane); the two warps of a lane quarter take the column halves 0-63 / 64-127 of
-//           every block (two tcgen05.ld of 32 columns), each keeps an online log2-sum-exp2 over its half of the speaker's rows, the pair
-//           merges at the end of a speaker through shared memory; clamp / per-frame output / per-(tile, speaker) partial sums
-// Operands are K-major in the no-swizzle canonical layout (8-row x 16-byte core matrices; LBO = byte stride between
-// K-adjacent core matrices, SBO = 128 B between 8-row groups), verified by experiments/tc_gemm_test.cu; the images are
-// written to HBM in exactly the shared-memory order, so every load is ONE contiguous bulk copy.
+// Structure (one persistent CTA per SM, 576 threads, warp-specialised; a work unit = one 128-frame tile x a chunk of speakers):
+//   warp 0  producer: cp.async.bulk (TMA engine) of the pre-imaged weight blocks into a 3-stage shared-memory ring -- a block is
+//           128 mixture rows, its tf32-hi and fp32-remainder-lo images are one stage each -- and of the block's hard-entry
+//           list into a 4-stage ring; completion on mbarriers
+//   warp 1  MMA issuer: one elected lane issues 3 x Kp/8 tcgen05.mma (M=128, N=128, K=8) per block into one of two
+//           128-column TMEM accumulator slots; the A operand (PHI hi / lo) is read from TENSOR MEMORY, only B from shared
+//           memory (with both operands in shared memory the operand fetch alone needs the whole 128 B/clk of the SM, ncu);
+//           tcgen05.commit -> mbarriers (frees the B stage, publishes the slot)
+//   warps 2-17 epilogue, thread = frame row = TMEM lane; the four warps of a lane quarter take the four 32-column groups
+//           (sixteen warps, not eight: the per-warp chain ld -> max -> ex2 -> sum is latency-bound, ncu):
+//           per unit they build PHI from the raw features (global -> registers -> tcgen05.st, plus a raw copy in shared
+//           memory for the add-back); per block they (1) while the block's MMAs still run, sum the hard entries' t^2 per
+//           column into a per-warp scratch column in shared memory (dynamic column index -> memory, not registers),
+//           (2) tcgen05.ld the accumulator and release the slot, (3) subtract the scratch of the flagged columns,
+//           (4) online log2-sum-exp2; at the end of a speaker the quarter's warps merge, applies the clamp, writes the per-frame
+//           value and the per-(tile, speaker) partial sum.
+// B images are K-major in the no-swizzle canonical layout (8-row x 16-byte core matrices; LBO = byte stride between
+// K-adjacent core matrices, SBO = 128 B between 8-row groups; verified by experiments/tc_gemm_test.cu) and are stored in HBM
+// in exactly the shared-memory order, so every load is ONE contiguous bulk copy.
 #pragma once
 #include "common.cuh"
 #include "gmm_score_tc_layout.h"
@@ -31,7 +36,8 @@
 namespace srb {
 
 struct TcArgs {
-	const float *A;            // [n_tiles][2][TC_M*Kp] feature images
+	const float *X;            // [n][ld] features
+	int ld;
 	const float *B;            // [n_blocks_total][2][TC_NB*Kp] weight images (speaker-major, rows padded)
 	const int4 *ftiles;        // per frame tile: {first frame, frame count, utterance, 0}
 	int n_ftiles;
@@ -49,8 +55,7 @@ struct TcArgs {
 	int D;
 	const int4 *hard;          // [n_blocks_total][TC_HSTRIDE]: header 0 = bit masks of the columns with entries in the four
 	                           // 32-column groups, header 1 = {first entry of group 1, of group 2, of group 3, total}; entries sorted
-	                           // by column: {image offset of x_dim (K-group part) | column within its 64-column half << 16, float bits of a, of nb,
-	                           // 1 if last of its column}
+	                           // by column: {dim | column within its 64-column half << 16, float bits of a, of nb, 1 if last of its column}
 };
 
 namespace tc {
@@ -114,9 +119,14 @@ __device__ __forceinline__ void wait(uint64_t *bar, uint32_t parity) {
 
 // online log2-sum-exp2 update with 32 new values (one chunk of accumulator columns) for one frame
 __device__ __forceinline__ void tc_lse_update(const float *v, float &m_run, float &s_run) {
-	float mx = v[0];
+	float t[16];                                   // tree reduction: depth 5 instead of a 31-long dependent chain
 #pragma unroll
-	for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+	for (int i = 0; i < 16; ++i) t[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+	for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+		for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
+	const float mx = t[0];
 	const float m_new = fmaxf(m_run, mx);
 	float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -130,59 +140,58 @@ __device__ __forceinline__ void tc_lse_update(const float *v, float &m_run, floa
 	m_run = m_new;
 }
 
-// Exact add-back, phase 1 (runs BEFORE the block's accumulator is complete, i.e. overlapped with its MMAs): walk this warp's
-// hard entries -- uniform across the warp, staged in shared memory, sorted by column, `last` flag on the final entry of a
-// column -- sum t^2 per column in a scalar register and park the sum in the warp's TMEM scratch column with a
-// one-column tcgen05.st.  TMEM addresses may be dynamic, registers may not: this is what removes the per-entry column
-// switch of the first version (ncu: 116 SM sub-partition cycles per entry).  Nothing in the loop depends on the previous
-// entry except the running sum, so the loads pipeline.
-__device__ __forceinline__ void tc_addback_park(const int4 *e, int n, const float *xrow, size_t lo_off, uint32_t scratch_taddr) {
-	float csum = 0.f;
-#pragma unroll 4
-	for (int i = 0; i < n; ++i) {
-		const int4 en = e[i];
-		const float x = xrow[en.x & 0xFFFF] + xrow[lo_off + (en.x & 0xFFFF)];          // hi + lo is the fp32 feature exactly
-		const float t = fmaf(x, __int_as_float(en.y), __int_as_float(en.z));
-		csum = fmaf(t, t, csum);
-		if (en.w) {                                                                      // uniform: last entry of column en.x >> 16
-			asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(scratch_taddr + (uint32_t)(en.x >> 16)), "r"(__float_as_uint(csum)) : "memory");
-			csum = 0.f;
-		}
-	}
+
+namespace tc {
+// D[tmem] (+)= A[tmem] . B[smem]^T : the A operand is read from tensor memory (lane = row, column = k)
+template <int ACC>
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+	asm volatile(
+	    "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+	    "mov.b64 db, {%2, %3};\n\t"
+	    "setp.ne.b32 p, %5, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+	    "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
+	    : "memory");
 }
-// phase 2: subtract the parked sums from the accumulator columns that have entries (c[] of the other columns is stale data)
-__device__ __forceinline__ void tc_addback_apply(float (&v)[32], const float (&c)[32], uint32_t mask) {
-#pragma unroll
-	for (int j = 0; j < 32; ++j) v[j] -= (mask & (1u << j)) ? c[j] : 0.f;
+__device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&v)[8]) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+	             "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+	             : "memory");
 }
+}  // namespace tc
 
 __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArgs A) {
 	extern __shared__ __align__(1024) unsigned char tc_smem[];
-	const int Kp = A.Kp;
-	const uint32_t a_part_bytes = (uint32_t)TC_M * Kp * 4, b_part_bytes = (uint32_t)TC_NB * Kp * 4;
+	const int Kp = A.Kp, D = A.D, XS = tc_x_stride(D);
+	const uint32_t b_part_bytes = (uint32_t)TC_NB * Kp * 4;
 	const size_t b_part_floats = (size_t)TC_NB * Kp;
-	float *sA = reinterpret_cast<float *>(tc_smem);                                  // hi | lo
-	float *sB = sA + tc_a_tile_floats(Kp);                                           // [stages] one part each
-	uint64_t *bars = reinterpret_cast<uint64_t *>(sB + TC_BSTAGES * b_part_floats);
-	uint64_t *full_a = bars, *empty_a = bars + 1;
-	uint64_t *full_b = bars + 2, *empty_b = full_b + TC_BSTAGES;
-	uint64_t *tm_full = empty_b + TC_BSTAGES, *tm_empty = tm_full + TC_SLOTS;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + TC_SLOTS);
-	int4 *ent_s = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(bars) + 128);   // [8 warps][TC_HHALF + 1] staged hard entries
-	float2 *ms_x = reinterpret_cast<float2 *>(ent_s + 8 * (TC_HHALF + 1));           // [128] (m, s) of the upper-half warps
+	float *sB = reinterpret_cast<float *>(tc_smem);                                  // [stages] one part (hi or lo) each
+	int4 *hring = reinterpret_cast<int4 *>(sB + TC_BSTAGES * b_part_floats);         // [TC_HSTAGES][TC_HSTRIDE] hard-entry lists
+	float *scr = reinterpret_cast<float *>(hring + TC_HSTAGES * TC_HSTRIDE);         // [16 warps][32 columns][32 lanes] add-back sums
+	float2 *ms_x = reinterpret_cast<float2 *>(scr + 16 * 32 * 32);                   // [3][128] (m, s) handed to the merging warp
+	uint64_t *bars = reinterpret_cast<uint64_t *>(ms_x + 3 * TC_M);
+	uint64_t *full_b = bars, *empty_b = full_b + TC_BSTAGES;
+	uint64_t *full_h = empty_b + TC_BSTAGES, *empty_h = full_h + TC_HSTAGES;
+	uint64_t *tm_full = empty_h + TC_HSTAGES, *tm_empty = tm_full + TC_SLOTS;
+	uint64_t *a_ready = tm_empty + TC_SLOTS;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
+	float *sX = reinterpret_cast<float *>(bars + 32);                                // [128][XS] raw features of the unit's tile
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	if (tid == 0) {
-		mbar_init(full_a, 1);
-		mbar_init(empty_a, 9);           // MMA commit + the eight epilogue warps (they read x from the A tile)
 		for (int s = 0; s < TC_BSTAGES; ++s) {
 			mbar_init(&full_b[s], 1);
 			mbar_init(&empty_b[s], 1);
 		}
+		for (int s = 0; s < TC_HSTAGES; ++s) {
+			mbar_init(&full_h[s], 1);
+			mbar_init(&empty_h[s], 16);      // one arrival per epilogue warp
+		}
 		for (int s = 0; s < TC_SLOTS; ++s) {
 			mbar_init(&tm_full[s], 1);
-			mbar_init(&tm_empty[s], 8);      // one arrival per epilogue warp
+			mbar_init(&tm_empty[s], 16);
 		}
+		mbar_init(a_ready, 16);
 		fence_mbar_init();
 	}
 	if (warp == 1) {
@@ -201,21 +210,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 	if (warp == 0) {
 		// ======================= producer =======================
 		if (lane == 0) {
-			uint32_t it_p = 0, it_a = 0;
-			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it_a) {
+			uint32_t it_p = 0, it_h = 0;
+			for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
 				const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
 				const int blk0 = chunk * blocks_per_chunk_full;
 				const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
-				tc::wait(empty_a, (it_a & 1) ^ 1);
-				mbar_expect_tx(full_a, 2 * a_part_bytes);
-				bulk_g2s(sA, A.A + (size_t)tile * tc_a_tile_floats(Kp), 2 * a_part_bytes, full_a);
-				// the block's hi image, then its lo image: one stage each, contiguous in HBM
-				const float *src = A.B + (size_t)blk0 * tc_b_block_floats(Kp);
-				for (int p = 2 * (blk1 - blk0); p > 0; --p, ++it_p, src += b_part_floats) {
-					const int st = it_p % TC_BSTAGES;
-					tc::wait(&empty_b[st], ((it_p / TC_BSTAGES) & 1) ^ 1);
-					mbar_expect_tx(&full_b[st], b_part_bytes);
-					bulk_g2s(sB + (size_t)st * b_part_floats, src, b_part_bytes, &full_b[st]);
+				for (int b = blk0; b < blk1; ++b, ++it_h) {
+					{   // the block's hard-entry list (needed first: the epilogue walks it while the block's MMAs run)
+						const int st = it_h % TC_HSTAGES;
+						tc::wait(&empty_h[st], ((it_h / TC_HSTAGES) & 1) ^ 1);
+						mbar_expect_tx(&full_h[st], TC_HSTRIDE * 16);
+						bulk_g2s(hring + (size_t)st * TC_HSTRIDE, A.hard + (size_t)b * TC_HSTRIDE, TC_HSTRIDE * 16, &full_h[st]);
+					}
+					// the block's hi image, then its lo image: one stage each, contiguous in HBM
+					const float *src = A.B + (size_t)b * tc_b_block_floats(Kp);
+#pragma unroll 1
+					for (int p = 0; p < 2; ++p, ++it_p, src += b_part_floats) {
+						const int st = it_p % TC_BSTAGES;
+						tc::wait(&empty_b[st], ((it_p / TC_BSTAGES) & 1) ^ 1);
+						mbar_expect_tx(&full_b[st], b_part_bytes);
+						bulk_g2s(sB + (size_t)st * b_part_floats, src, b_part_bytes, &full_b[st]);
+					}
 				}
 			}
 		}
@@ -224,22 +239,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 		if (lane == 0) {
 			// instruction descriptor: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9 / 10-12 = 2), both K-major, N>>3 at bit 17, M>>4 at bit 24
 			const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NB >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-			const uint32_t lbo_a = (TC_M / 8) * 128, lbo_b = (TC_NB / 8) * 128, sbo = 128;
-			// descriptors are two words; only the 14-bit start-address field of the low word advances between k-steps
+			const uint32_t lbo_b = (TC_NB / 8) * 128, sbo = 128;
+			// the B descriptor is two words; only the 14-bit start-address field of the low word advances between k-steps
 			const uint32_t d_hi = (uint32_t)(sbo >> 4) | (1u << 14);            // SBO | version bit 46
-			const uint32_t stepA = (2 * lbo_a) >> 4, stepB = (2 * lbo_b) >> 4;
+			const uint32_t stepB = (2 * lbo_b) >> 4;
 			const int ksteps = Kp / 8;
+			const uint32_t a_hi = tmem_base + TC_A_COL, a_lo = a_hi + (uint32_t)Kp;
 			uint32_t it_p = 0, it_a = 0, it_s = 0;
 			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it_a) {
 				const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
 				const int blk0 = chunk * blocks_per_chunk_full;
 				const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
-				tc::wait(full_a, it_a & 1);
-				const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + a_part_bytes;
-				const uint32_t dA_hi0 = ((a_hi >> 4) & 0x3FFF) | ((lbo_a >> 4) << 16), dA_lo0 = ((a_lo >> 4) & 0x3FFF) | ((lbo_a >> 4) << 16);
+				tc::wait(a_ready, it_a & 1);            // PHI of this unit's tile is in tensor memory
+				tc::fence_after();
 				for (int b = blk0; b < blk1; ++b, ++it_s) {
 					const int slot = it_s % TC_SLOTS;
 					tc::wait(&tm_empty[slot], ((it_s / TC_SLOTS) & 1) ^ 1);
+					tc::fence_after();
 					const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TC_NB);
 					// 3xTF32: (A_hi + A_lo) * B_hi from the first stage, A_hi * B_lo from the second
 					{
@@ -247,20 +263,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 						tc::wait(&full_b[st], (it_p / TC_BSTAGES) & 1);
 						tc::fence_after();
 						const uint32_t dB0 = ((smem_u32(sB + (size_t)st * b_part_floats) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
-						uint32_t da = dA_hi0, db = dB0;
-						tc::mma_tf32_lohi<0>(d_tmem, da, d_hi, db, d_hi, idesc);        // first MMA of the block overwrites the slot
+						uint32_t ta = a_hi, db = dB0;
+						tc::mma_tf32_ts<0>(d_tmem, ta, db, d_hi, idesc);        // first MMA of the block overwrites the slot
 #pragma unroll 2
 						for (int k = 1; k < ksteps; ++k) {
-							da += stepA;
+							ta += 8;
 							db += stepB;
-							tc::mma_tf32_lohi<1>(d_tmem, da, d_hi, db, d_hi, idesc);
+							tc::mma_tf32_ts<1>(d_tmem, ta, db, d_hi, idesc);
 						}
-						da = dA_lo0;
+						ta = a_lo;
 						db = dB0;
 #pragma unroll 2
 						for (int k = 0; k < ksteps; ++k) {
-							tc::mma_tf32_lohi<1>(d_tmem, da, d_hi, db, d_hi, idesc);
-							da += stepA;
+							tc::mma_tf32_ts<1>(d_tmem, ta, db, d_hi, idesc);
+							ta += 8;
 							db += stepB;
 						}
 						tc::commit(&empty_b[st]);       // the stage may be refilled once these MMAs have read it
@@ -270,12 +286,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 						const int st = it_p % TC_BSTAGES;
 						tc::wait(&full_b[st], (it_p / TC_BSTAGES) & 1);
 						tc::fence_after();
-						uint32_t da = dA_hi0;
+						uint32_t ta = a_hi;
 						uint32_t db = ((smem_u32(sB + (size_t)st * b_part_floats) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
 #pragma unroll 2
 						for (int k = 0; k < ksteps; ++k) {
-							tc::mma_tf32_lohi<1>(d_tmem, da, d_hi, db, d_hi, idesc);
-							da += stepA;
+							tc::mma_tf32_ts<1>(d_tmem, ta, db, d_hi, idesc);
+							ta += 8;
 							db += stepB;
 						}
 						tc::commit(&empty_b[st]);
@@ -283,50 +299,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 					}
 					tc::commit(&tm_full[slot]);     // the accumulator slot is complete
 				}
-				tc::commit(empty_a);                // the A tile may be replaced
 			}
 		}
 	} else {
-		// ======================= epilogue (8 warps; thread = frame row, warp pair = column halves) =======================
-		const int ew = warp - 2;                      // 0..7
+		// ======================= epilogue (16 warps; thread = frame row; the 4 warps of a lane quarter take the 4 column groups) ====
+		const int ew = warp - 2;                      // 0..15
 		const int q = warp & 3;                       // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
-		const int half = ew >> 2;                     // warps 2-5 take columns 0-63 of every block, warps 6-9 columns 64-127
+		const int cg = ew >> 2;                       // 32-column group of every block this warp owns
 		const int row = q * 32 + lane;                // frame within the tile
-		int4 *my_ent = ent_s + ew * (TC_HHALF + 1);
-		const float *xrow = sA + (size_t)(row >> 3) * 32 + (row & 7) * 4;          // row part of the A image offset
-		const size_t lo_off = (size_t)TC_M * Kp;
+		const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+		float *my_scr = scr + (size_t)ew * 32 * 32 + lane;
+		float *xrow = sX + (size_t)row * XS;
 		const int seg = A.seg;
 		const int cols_per_spk = (seg >= TC_NB) ? A.blocks_per_spk * TC_NB : seg;
-		uint32_t it_s = 0, it_a = 0;
-		for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it_a) {
+		const int nch = Kp >> 3;
+		uint32_t it_s = 0, it_h = 0;
+#define SRB_TC_QBAR() asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory")      /* the 4 warps of this lane quarter */
+		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
 			const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
 			const int blk0 = chunk * blocks_per_chunk_full;
 			const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
 			const int4 ft = A.ftiles[tile];
 			const bool valid = row < ft.y;
-			tc::wait(full_a, it_a & 1);               // the add-back reads x from the unit's A tile before the first accumulator wait
+
+			// ---- PHI = [x^2, x, 1, 0-pad] of this thread's frame -> tensor memory (tf32 hi | fp32 remainder lo); the quarter's four
+			// warps split the 8-column groups.  All MMAs of the previous unit have completed (this warp consumed its last
+			// tm_full), the quarter barrier makes sure no sibling still reads the previous tile's raw features.
+			SRB_TC_QBAR();
+			{
+				const float *xg = A.X + (size_t)(ft.x + (valid ? row : 0)) * A.ld;
+				for (int c = cg; c < nch; c += 4) {
+					uint32_t hi[8], lo[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) {
+						const int k = 8 * c + j;
+						float v = 0.f;
+						if (k < D) {
+							const float x = valid ? __ldg(xg + k) : 0.f;
+							v = x * x;
+						} else if (k < 2 * D) {
+							v = valid ? __ldg(xg + k - D) : 0.f;
+							xrow[k - D] = v;
+						} else if (k == 2 * D) {
+							v = valid ? 1.f : 0.f;
+						}
+						hi[j] = __float_as_uint(v) & ~0x1FFFu;
+						lo[j] = __float_as_uint(v - __uint_as_float(hi[j]));
+					}
+					tc::st8(lane_base + TC_A_COL + 8 * c, hi);
+					tc::st8(lane_base + TC_A_COL + Kp + 8 * c, lo);
+				}
+				asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+				tc::fence_before();
+				SRB_TC_QBAR();                                // the quarter's raw features are in shared memory
+				if (lane == 0) mbar_arrive(a_ready);
+			}
+
 			float m_run = -3.0e38f, s_run = 0.f;
-			int col_in_spk = 0;                       // columns of the current speaker consumed so far (by the pair)
+			int col_in_spk = 0;                       // columns of the current speaker consumed so far (by the quarter's warps together)
 			int spk = chunk * A.spk_per_chunk;        // first speaker of the current block
 
-			// close a speaker: optional pair merge, clamp, per-frame output, per-(tile, speaker, lane quarter) partial sum
-			auto finish = [&](int my_spk, bool merge) {
+			// close a speaker whose columns were shared by `width` (1, 2 or 4) adjacent warps of the quarter: merge, clamp,
+			// per-frame output, per-(tile, speaker, lane quarter) partial sum
+			auto finish = [&](int my_spk, int width) {
 				float m = m_run, sacc = s_run;
-				bool writer = true;
-				if (merge) {
-					// the upper-half warp hands its (m, s) to the lower-half warp of the same lane quarter
-					if (half == 1) ms_x[row] = make_float2(m, sacc);
-					asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-					if (half == 0) {
-						const float2 o = ms_x[row];
-						const float M = fmaxf(m, o.x);
-						sacc = sacc * ex2_approx(m - M) + o.y * ex2_approx(o.x - M);
-						m = M;
+				const bool leader = (cg & (width - 1)) == 0;
+				if (width > 1) {
+					if (!leader) ms_x[(cg - 1) * TC_M + row] = make_float2(m, sacc);
+					SRB_TC_QBAR();
+					if (leader) {
+						for (int o = 0; o < width - 1; ++o) {
+							const float2 other = ms_x[(cg + o) * TC_M + row];
+							const float M = fmaxf(m, other.x);
+							sacc = sacc * ex2_approx(m - M) + other.y * ex2_approx(other.x - M);
+							m = M;
+						}
 					}
-					asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // ms_x may be overwritten for the next speaker
-					writer = (half == 0);
+					SRB_TC_QBAR();                            // ms_x may be overwritten for the next speaker
 				}
-				if (writer && my_spk < A.S) {
+				if (leader && my_spk < A.S) {
 					const float l2 = m + lg2_approx(sacc);
 					float ll = l2 * TC_LN2;
 					if (A.clamp && !(ll >= -744.4400719213812f)) ll = -34.538776394910684f;
@@ -340,64 +391,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 				s_run = 0.f;
 			};
 
-			for (int b = blk0; b < blk1; ++b, ++it_s) {
-				const int slot = it_s % TC_SLOTS;
-				// stage this warp's share of the block's hard entries (before the accumulator is ready)
-				const int4 *hl = A.hard + (size_t)b * TC_HSTRIDE;
-				const int4 hmask = __ldg(hl), hoff = __ldg(hl + 1);
-				const int e0 = half == 0 ? 0 : hoff.y, e1 = half == 0 ? hoff.y : hoff.w;
-				const uint32_t mask0 = (uint32_t)(half == 0 ? hmask.x : hmask.z), mask1 = (uint32_t)(half == 0 ? hmask.y : hmask.w);
+			for (int b = blk0; b < blk1; ++b, ++it_s, ++it_h) {
+				const int slot = it_s % TC_SLOTS, hst = it_h % TC_HSTAGES;
+				// ---- exact add-back, phase 1 (the block's MMAs are still running): sum t^2 of this warp's hard entries per
+				// column -- the list is uniform across the warp, sorted by column, `last` flag on a column's final entry -- and
+				// park each column's sum in the warp's scratch row.  The column index is dynamic, hence memory, not registers
+				// (the first version switched over 32 register cases per entry: 116 SM sub-partition cycles per entry, ncu).
+				tc::wait(&full_h[hst], (it_h / TC_HSTAGES) & 1);
+				const int4 *hl = hring + (size_t)hst * TC_HSTRIDE;
+				const int4 hmask = hl[0], hoff = hl[1];
+				const int e0 = cg == 0 ? 0 : (cg == 1 ? hoff.x : (cg == 2 ? hoff.y : hoff.z));
+				const int e1 = cg == 0 ? hoff.x : (cg == 1 ? hoff.y : (cg == 2 ? hoff.z : hoff.w));
+				const uint32_t mask = (uint32_t)(cg == 0 ? hmask.x : (cg == 1 ? hmask.y : (cg == 2 ? hmask.z : hmask.w)));
+				{
+					const int4 *e = hl + 2 + e0;
+					const int n = e1 - e0;
+					float csum = 0.f;
+#pragma unroll 4
+					for (int i = 0; i < n; ++i) {
+						const int4 en = e[i];
+						const float t = fmaf(xrow[en.x & 0xFFFF], __int_as_float(en.y), __int_as_float(en.z));
+						csum = fmaf(t, t, csum);
+						if (en.w) {
+							my_scr[((en.x >> 16) & 31) * 32] = csum;
+							csum = 0.f;
+						}
+					}
+				}
 				__syncwarp();
-				for (int i = lane; i < e1 - e0; i += 32)
-					my_ent[i] = __ldg(hl + 2 + e0 + i);
-				__syncwarp();
-				const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-				const uint32_t scratch = lane_base + (uint32_t)(TC_SLOTS * TC_NB + half * 64);      // this warp's 64 scratch columns
-				tc_addback_park(my_ent, e1 - e0, xrow, lo_off, scratch);
-				asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+				if (lane == 0) mbar_arrive(&empty_h[hst]);
+				// ---- accumulator -> registers, slot released right away
 				tc::wait(&tm_full[slot], (it_s / TC_SLOTS) & 1);
 				tc::fence_after();
-				const uint32_t taddr = lane_base + (uint32_t)(slot * TC_NB + half * 64);
-				float v0[32], v1[32];
-				tc::ld32(taddr, v0);
-				tc::ld32(taddr + 32, v1);
-				// the accumulator columns are in registers: release the slot right away
+				float v[32];
+				tc::ld32(lane_base + (uint32_t)(slot * TC_NB + cg * 32), v);
 				tc::fence_before();
 				__syncwarp();
 				if (lane == 0) mbar_arrive(&tm_empty[slot]);
-				if (mask0) {
-					float c[32];
-					tc::ld32(scratch, c);
-					tc_addback_apply(v0, c, mask0);
+				// ---- add-back, phase 2: only the flagged columns have a (fresh) scratch value
+				if (mask) {
+#pragma unroll
+					for (int j = 0; j < 32; ++j)
+						if (mask & (1u << j)) v[j] -= my_scr[j * 32];
 				}
-				if (mask1) {
-					float c[32];
-					tc::ld32(scratch + 32, c);
-					tc_addback_apply(v1, c, mask1);
-				}
-				// column segmentation: seg >= 128 -> the block belongs to one speaker (pair merge at its end); seg == 64 -> this
-				// warp's 64 columns are one speaker; seg == 32 -> each 32-column group is one speaker
-				tc_lse_update(v0, m_run, s_run);
-				if (seg == 32) finish(spk + 2 * half, false);
-				tc_lse_update(v1, m_run, s_run);
+				// column segmentation: seg >= 128 -> the block belongs to one speaker (quarter-wide merge at its end); seg == 64 ->
+				// two speakers per block, two warps each; seg == 32 -> every warp's group is its own speaker
+				tc_lse_update(v, m_run, s_run);
 				if (seg == 32) {
-					finish(spk + 2 * half + 1, false);
+					finish(spk + cg, 1);
 					spk += 4;
 				} else if (seg == 64) {
-					finish(spk + half, false);
+					finish(spk + (cg >> 1), 2);
 					spk += 2;
 				} else {
 					col_in_spk += TC_NB;
 					if (col_in_spk == cols_per_spk) {
-						finish(spk, true);
+						finish(spk, 4);
 						col_in_spk = 0;
 						++spk;
 					}
 				}
 			}
-			__syncwarp();
-			if (lane == 0) mbar_arrive(empty_a);      // this warp no longer needs the unit's A tile
 		}
+#undef SRB_TC_QBAR
 	}
 	tc::fence_before();
 	__syncthreads();

@@ -13,8 +13,8 @@ void score_tables_release();
 
 // ---- gmm_score_tc.cu: tensor-core route (tcgen05, 3xTF32) ----
 bool tc_supported(const PackedModels &pm, int D);
-int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, float *d_Aimg, double *d_partial,
-                    float *d_frame_ll, int ldf, int clamp, int frame_log2, cudaStream_t st);
+int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, double *d_partial, float *d_frame_ll,
+                    int ldf, int clamp, int frame_log2, cudaStream_t st);
 
 // ---- gmm_em.cu ----
 // stats (float64): [K] N_k | [K*D] sum g x | [K*D] sum g x^2 | [1] sum log p | [1] frames used
