@@ -117,9 +117,10 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 	const double A0 = 0.84932180028801904272;
 	double HARD_SIGMA = TC_HARD_SIGMA;
 	if (const char *eh = getenv("SRB200_TC_HARD_SIGMA")) HARD_SIGMA = atof(eh);   // experiments: 0 disables the add-back list
-	// hard-entry lists (layout: TcArgs::hard).  Rows ascend, so each block's list is sorted by column.
+	// hard-entry lists (layout: TcArgs::hard).  Rows ascend, so each group's list is sorted by column.
 	pm.h_tc_hard.assign((size_t)blocks * 4 * TC_HSTRIDE, 0);
-	std::vector<int> n_half(2 * blocks, 0);
+	struct HardEntry { int x; float a, nb; int w; };
+	std::vector<std::vector<HardEntry>> groups((size_t)blocks * 4);
 	bool overflow = false;
 	auto put = [&](long long row, int k, double w) {
 		const int blk = (int)(row / NB), r = (int)(row % NB);
@@ -137,44 +138,53 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 	for (long long row = 0; row < (long long)blocks * NB; ++row) {
 		const int s = (int)(row / cols), k = (int)(row % cols);
 		const int blk = (int)(row / NB), col = (int)(row % NB);
-		int *hdr = pm.h_tc_hard.data() + (size_t)blk * TC_HSTRIDE * 4;
 		if (s < S && k < Ks[s]) {
 			const double *mu = means[s] + (size_t)k * D, *sg = sigmas[s] + (size_t)k * D;
 			double C = weights[s][k] > 0.0 ? log2(weights[s][k]) : -1.0e30;
-			int *last_of_col = nullptr;
+			std::vector<HardEntry> &g = groups[(size_t)blk * 4 + (col >> 5)];
+			bool any = false;
 			for (int d = 0; d < D; ++d) {
 				const double a = A0 / sg[d], nb = -mu[d] * a;
 				C -= log2(2.5066282746310002 * sg[d]);
 				if (sg[d] < HARD_SIGMA) {
 					// kept out of the GEMM (its three ~1e3 terms would cancel): exact add-back entry for the epilogue
-					const int h = col >> 6;
-					if (n_half[2 * blk + h] >= TC_HHALF) {
-						overflow = true;
-						continue;
-					}
-					const int idx = (h == 0 ? 0 : n_half[2 * blk]) + n_half[2 * blk + h];
-					int *e = hdr + (size_t)(2 + idx) * 4;
-					const float af = (float)a, nbf = (float)nb;
-					e[0] = d | ((col & 63) << 16);               // feature dim | column within the 64-column half
-					memcpy(&e[1], &af, 4);
-					memcpy(&e[2], &nbf, 4);
-					e[3] = 0;
-					last_of_col = e;
-					++n_half[2 * blk + h];
-					hdr[col >> 5] |= (int)(1u << (col & 31));
-					for (int g = (col >> 5) + 1; g <= 3; ++g) ++hdr[4 + g - 1];      // first entry of the later groups
-					++hdr[4 + 3];                                                     // total
+					g.push_back({4 * d, (float)a, (float)nb, 0});
+					any = true;
 				} else {
 					put(row, d, -a * a);
 					put(row, D + d, -2.0 * a * nb);
 					C -= nb * nb;
 				}
 			}
-			if (last_of_col) last_of_col[3] = 1;
+			if (any) g.back().w = 1 + 128 * (col & 31);      // last entry of this column: flush the sum to scratch column col & 31
 			put(row, 2 * D, (C < -1.0e30 || C != C) ? -1.0e30 : C);
 		} else {
 			put(row, 2 * D, -1.0e30);      // padded row: exp2 underflows to exactly 0
 		}
+	}
+	for (int blk = 0; blk < blocks && !overflow; ++blk) {
+		int *hdr = pm.h_tc_hard.data() + (size_t)blk * TC_HSTRIDE * 4;
+		int pos = 0;
+		for (int gi = 0; gi < 4; ++gi) {
+			std::vector<HardEntry> &g = groups[(size_t)blk * 4 + gi];
+			for (const HardEntry &he : g)
+				if (he.w) hdr[gi] |= (int)(1u << (((he.w - 1) / 128) & 31));
+			while (g.size() % 4) g.push_back({0, 0.f, 0.f, 0});          // null entries: t = 0, no flush
+			if (pos + (int)g.size() > TC_HSTRIDE - 2) {
+				overflow = true;
+				break;
+			}
+			for (const HardEntry &he : g) {
+				int *e = hdr + (size_t)(2 + pos) * 4;
+				e[0] = he.x;
+				memcpy(&e[1], &he.a, 4);
+				memcpy(&e[2], &he.nb, 4);
+				e[3] = he.w;
+				++pos;
+			}
+			if (gi < 3) hdr[4 + gi] = pos;      // first entry of the next group
+		}
+		hdr[7] = pos;
 	}
 	if (overflow) {      // too many tiny-sigma entries for the sparse list: this model set stays on the FMA route
 		pm.h_tc.clear();

@@ -30,7 +30,10 @@ int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4
 		SRB_CUDA(cudaStreamSynchronize(st));
 	}
 	if (!g_tc_attr) {
-		SRB_CUDA(cudaFuncSetAttribute(gmm_score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(gmm_score_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(gmm_score_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(gmm_score_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(gmm_score_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		g_tc_attr = true;
 	}
 	if (n_ftiles <= 0) return 0;
@@ -65,7 +68,13 @@ int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4
 	a.hard = reinterpret_cast<const int4 *>(pm.d_tc_hard);
 	const long long units = (long long)n_ftiles * n_chunks;
 	const int grid = (int)std::min<long long>(units, c.sm_count);
-	gmm_score_tc_kernel<<<grid, TC_THREADS, tc_smem_bytes(Kp, D), st>>>(a);
+	const size_t smem = tc_smem_bytes(Kp, D);
+	switch (Kp / 8) {      // D = 13 -> 4, D = 28 (MFCC + LPC) -> 8, D = 39 -> 10
+		case 4: gmm_score_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(a); break;
+		case 8: gmm_score_tc_kernel<8><<<grid, TC_THREADS, smem, st>>>(a); break;
+		case 10: gmm_score_tc_kernel<10><<<grid, TC_THREADS, smem, st>>>(a); break;
+		default: gmm_score_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(a); break;
+	}
 	SRB_CUDA(cudaGetLastError());
 	return 0;
 }

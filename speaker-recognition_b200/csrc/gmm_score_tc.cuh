@@ -55,7 +55,8 @@ struct TcArgs {
 	int D;
 	const int4 *hard;          // [n_blocks_total][TC_HSTRIDE]: header 0 = bit masks of the columns with entries in the four
 	                           // 32-column groups, header 1 = {first entry of group 1, of group 2, of group 3, total}; entries sorted
-	                           // by column: {dim | column within its 64-column half << 16, float bits of a, of nb, 1 if last of its column}
+	                           // by column, every group padded to a multiple of 4 with null entries: {4 * dim, float bits of a, of nb,
+	                           // last entry of its column ? 1 + 128 * (column within the group) : 0}
 };
 
 namespace tc {
@@ -143,14 +144,24 @@ __device__ __forceinline__ void tc_lse_update(const float *v, float &m_run, floa
 
 namespace tc {
 // D[tmem] (+)= A[tmem] . B[smem]^T : the A operand is read from tensor memory (lane = row, column = k)
+// Issued by the WHOLE (converged) warp; one lane is elected inside the statement (a per-thread predicate instead of
+// elect.sync brings the loop back).  (Issuing from an `if (lane == 0)` region
+// makes ptxas wrap every MMA in an elect/branch loop: ~10 dependent instructions and ~100 cycles per MMA, ncu.)
 template <int ACC>
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
 	asm volatile(
-	    "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+	    "{\n\t.reg .b64 db;\n\t.reg .pred p, pe;\n\t"
 	    "mov.b64 db, {%2, %3};\n\t"
 	    "setp.ne.b32 p, %5, 0;\n\t"
-	    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+	    "elect.sync _|pe, 0xffffffff;\n\t"
+	    "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
 	    "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
+	    : "memory");
+}
+__device__ __forceinline__ void commit_elect(uint64_t *bar) {
+	asm volatile(
+	    "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+	    "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
 	    : "memory");
 }
 __device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -160,6 +171,8 @@ __device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&v)[8]) {
 }
 }  // namespace tc
 
+// KSTEPS = Kp / 8 as a compile-time constant (fully unrolled MMA issue: 3-4 instructions per MMA), or 0 for the generic loop
+template <int KSTEPS>
 __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArgs A) {
 	extern __shared__ __align__(1024) unsigned char tc_smem[];
 	const int Kp = A.Kp, D = A.D, XS = tc_x_stride(D);
@@ -235,15 +248,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 			}
 		}
 	} else if (warp == 1) {
-		// ======================= MMA issuer =======================
-		if (lane == 0) {
+		// ======================= MMA issuer (whole warp converged; one lane elected per instruction) =======================
+		{
 			// instruction descriptor: D = F32 (bits 4-5 = 1), A/B = TF32 (bits 7-9 / 10-12 = 2), both K-major, N>>3 at bit 17, M>>4 at bit 24
 			const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NB >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-			const uint32_t lbo_b = (TC_NB / 8) * 128, sbo = 128;
+			constexpr uint32_t lbo_b = (TC_NB / 8) * 128, sbo = 128;
 			// the B descriptor is two words; only the 14-bit start-address field of the low word advances between k-steps
-			const uint32_t d_hi = (uint32_t)(sbo >> 4) | (1u << 14);            // SBO | version bit 46
-			const uint32_t stepB = (2 * lbo_b) >> 4;
-			const int ksteps = Kp / 8;
+			constexpr uint32_t d_hi = (uint32_t)(sbo >> 4) | (1u << 14);            // SBO | version bit 46
+			constexpr uint32_t stepB = (2 * lbo_b) >> 4;
+			const int ksteps = KSTEPS > 0 ? KSTEPS : Kp / 8;
 			const uint32_t a_hi = tmem_base + TC_A_COL, a_lo = a_hi + (uint32_t)Kp;
 			uint32_t it_p = 0, it_a = 0, it_s = 0;
 			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it_a) {
@@ -263,41 +276,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 						tc::wait(&full_b[st], (it_p / TC_BSTAGES) & 1);
 						tc::fence_after();
 						const uint32_t dB0 = ((smem_u32(sB + (size_t)st * b_part_floats) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
-						uint32_t ta = a_hi, db = dB0;
-						tc::mma_tf32_ts<0>(d_tmem, ta, db, d_hi, idesc);        // first MMA of the block overwrites the slot
-#pragma unroll 2
-						for (int k = 1; k < ksteps; ++k) {
-							ta += 8;
-							db += stepB;
-							tc::mma_tf32_ts<1>(d_tmem, ta, db, d_hi, idesc);
-						}
-						ta = a_lo;
-						db = dB0;
-#pragma unroll 2
-						for (int k = 0; k < ksteps; ++k) {
-							tc::mma_tf32_ts<1>(d_tmem, ta, db, d_hi, idesc);
-							ta += 8;
-							db += stepB;
-						}
-						tc::commit(&empty_b[st]);       // the stage may be refilled once these MMAs have read it
+						tc::mma_tf32_ts<0>(d_tmem, a_hi, dB0, d_hi, idesc);     // first MMA of the block overwrites the slot
+#pragma unroll
+						for (int k = 1; k < ksteps; ++k) tc::mma_tf32_ts<1>(d_tmem, a_hi + 8 * k, dB0 + stepB * k, d_hi, idesc);
+#pragma unroll
+						for (int k = 0; k < ksteps; ++k) tc::mma_tf32_ts<1>(d_tmem, a_lo + 8 * k, dB0 + stepB * k, d_hi, idesc);
+						tc::commit_elect(&empty_b[st]);     // the stage may be refilled once these MMAs have read it
 						++it_p;
 					}
 					{
 						const int st = it_p % TC_BSTAGES;
 						tc::wait(&full_b[st], (it_p / TC_BSTAGES) & 1);
 						tc::fence_after();
-						uint32_t ta = a_hi;
-						uint32_t db = ((smem_u32(sB + (size_t)st * b_part_floats) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
-#pragma unroll 2
-						for (int k = 0; k < ksteps; ++k) {
-							tc::mma_tf32_ts<1>(d_tmem, ta, db, d_hi, idesc);
-							ta += 8;
-							db += stepB;
-						}
-						tc::commit(&empty_b[st]);
+						const uint32_t dB0 = ((smem_u32(sB + (size_t)st * b_part_floats) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
+#pragma unroll
+						for (int k = 0; k < ksteps; ++k) tc::mma_tf32_ts<1>(d_tmem, a_hi + 8 * k, dB0 + stepB * k, d_hi, idesc);
+						tc::commit_elect(&empty_b[st]);
 						++it_p;
 					}
-					tc::commit(&tm_full[slot]);     // the accumulator slot is complete
+					tc::commit_elect(&tm_full[slot]);       // the accumulator slot is complete
 				}
 			}
 		}
@@ -310,6 +307,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 		const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 		float *my_scr = scr + (size_t)ew * 32 * 32 + lane;
 		float *xrow = sX + (size_t)row * XS;
+		const unsigned char *xrow_b = reinterpret_cast<const unsigned char *>(xrow);
+		unsigned char *scr_b = reinterpret_cast<unsigned char *>(my_scr) - 1;      // entry.w = 1 + byte offset of the scratch column
 		const int seg = A.seg;
 		const int cols_per_spk = (seg >= TC_NB) ? A.blocks_per_spk * TC_NB : seg;
 		const int nch = Kp >> 3;
@@ -404,16 +403,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 				const int e1 = cg == 0 ? hoff.x : (cg == 1 ? hoff.y : (cg == 2 ? hoff.z : hoff.w));
 				const uint32_t mask = (uint32_t)(cg == 0 ? hmask.x : (cg == 1 ? hmask.y : (cg == 2 ? hmask.z : hmask.w)));
 				{
+					// four entries per step (the host pads every group's list to a multiple of four with null entries): all loads
+					// of a step are issued before its first scratch store -- entries, features and scratch share the shared-memory
+					// address space, so the compiler cannot move a load above a store on its own
 					const int4 *e = hl + 2 + e0;
 					const int n = e1 - e0;
 					float csum = 0.f;
-#pragma unroll 4
-					for (int i = 0; i < n; ++i) {
-						const int4 en = e[i];
-						const float t = fmaf(xrow[en.x & 0xFFFF], __int_as_float(en.y), __int_as_float(en.z));
-						csum = fmaf(t, t, csum);
-						if (en.w) {
-							my_scr[((en.x >> 16) & 31) * 32] = csum;
+#pragma unroll 1
+					for (int i = 0; i < n; i += 4) {
+						const int4 a0 = e[i], a1 = e[i + 1], a2 = e[i + 2], a3 = e[i + 3];
+						const float x0 = *reinterpret_cast<const float *>(xrow_b + a0.x), x1 = *reinterpret_cast<const float *>(xrow_b + a1.x);
+						const float x2 = *reinterpret_cast<const float *>(xrow_b + a2.x), x3 = *reinterpret_cast<const float *>(xrow_b + a3.x);
+						const float t0 = fmaf(x0, __int_as_float(a0.y), __int_as_float(a0.z)), t1 = fmaf(x1, __int_as_float(a1.y), __int_as_float(a1.z));
+						const float t2 = fmaf(x2, __int_as_float(a2.y), __int_as_float(a2.z)), t3 = fmaf(x3, __int_as_float(a3.y), __int_as_float(a3.z));
+						csum = fmaf(t0, t0, csum);
+						if (a0.w) {
+							*reinterpret_cast<float *>(scr_b + a0.w) = csum;
+							csum = 0.f;
+						}
+						csum = fmaf(t1, t1, csum);
+						if (a1.w) {
+							*reinterpret_cast<float *>(scr_b + a1.w) = csum;
+							csum = 0.f;
+						}
+						csum = fmaf(t2, t2, csum);
+						if (a2.w) {
+							*reinterpret_cast<float *>(scr_b + a2.w) = csum;
+							csum = 0.f;
+						}
+						csum = fmaf(t3, t3, csum);
+						if (a3.w) {
+							*reinterpret_cast<float *>(scr_b + a3.w) = csum;
 							csum = 0.f;
 						}
 					}

@@ -15,8 +15,7 @@ constexpr int TC_BSTAGES = 3;        // ring of B PART stages: a stage holds the
 constexpr int TC_HSTAGES = 4;        // ring of per-block hard-entry lists
 constexpr int TC_THREADS = 576;      // producer warp, MMA warp, 16 epilogue warps (four per TMEM lane quarter: 32-column groups)
 constexpr float TC_LN2 = 0.69314718055994531f;
-constexpr int TC_HHALF = 96;         // capacity of the hard-entry list of one 64-column half of a block
-constexpr int TC_HSTRIDE = 2 + 2 * TC_HHALF;   // int4 per block: two header words + entries
+constexpr int TC_HSTRIDE = 2 + 204;  // int4 per block: two header words + up to 204 hard entries (incl. the x4 padding of the four groups)
 constexpr double TC_HARD_SIGMA = 0.1;   // dims with sigma below this are kept out of the GEMM and added back exactly
 
 __host__ __device__ static inline size_t tc_b_block_floats(int Kp) { return (size_t)2 * TC_NB * Kp; }  // hi | lo
