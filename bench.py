@@ -277,32 +277,58 @@ def main():
         flops_alg = 3.0 * DIM * T * S_SPK * K_MIX                   # survey convention: sub, mul, mul-add per dim
         fma_issued = 2.0 * DIM * T * S_SPK * K_MIX                   # what the kernel issues: 2 FFMA per (frame, mixture, dim)
         sec = score_ms * 1e-3
+        route = int(L.srb200_last_score_route())          # 1: tcgen05 3xTF32 kernel (default), 0: fp32 FMA kernel
+        kname = "gmm_score_tc_kernel" if route == 1 else "gmm_score_kernel"
         traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tpath):
-            tj = json.load(open(tpath)).get("gmm_score_kernel", {})
+            tj = json.load(open(tpath)).get(kname, {})
             if tj.get("utts") == B and tj.get("speakers") == S_SPK and tj.get("mixtures") == K_MIX:
                 traffic = tj.get("dram_bytes")
-        roofline = {"bound": "hbm", "kernel": "gmm_score_kernel", "achieved": bytes_alg / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": bytes_alg / sec / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                    "ms_per_launch": score_ms, "algorithmic_bytes": bytes_alg,
-                    "note": "scoring is bound by the fp32 FMA pipe (~2700 flop/B at C2), not HBM; see roofline_fma"}
-        fma = {"bound": "fp32_fma", "kernel": "gmm_score_kernel", "unit": "TFLOP/s",
-               "achieved": 2.0 * fma_issued / sec / 1e12, "achieved_survey_convention": flops_alg / sec / 1e12}
-        try:
-            from speaker_recognition_b200 import build as b
-            LB = C.CDLL(b.BENCH_OUT)
-            LB.srb200_bench_fma_tflops.restype = C.c_double
-            LB.srb200_bench_fma_tflops.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
-            pk = {name: LB.srb200_bench_fma_tflops(v, 4000, 3, None) for v, name in ((0, "ffma_indep"), (1, "ffma_pair"), (2, "ffma2_packed"))}
-            fma["peak"] = max(pk.values())
-            fma["peak_variants"] = pk
-            fma["peak_source"] = "measured in this run (csrc/bench/fma_peak.cu)"
-            fma["frac"] = fma["achieved"] / fma["peak"]
-        except Exception as e:  # measurement helper missing: nominal figure, flagged
-            fma["peak"] = 148 * 128 * 2 * 1.965e9 / 1e12
-            fma["peak_source"] = "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (helper failed: %s)" % e
-            fma["frac"] = fma["achieved"] / fma["peak"]
+        hbm = {"bound": "hbm", "kernel": kname, "achieved": bytes_alg / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+               "frac": bytes_alg / sec / 1e9 / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+               "ms_per_launch": score_ms, "algorithmic_bytes": bytes_alg,
+               "note": "scoring is compute-bound (~2700 flop/B at C2), not HBM-bound: see the binding roofline"}
+        fma = None
+        if route == 0:
+            fma = {"bound": "fp32_fma", "kernel": "gmm_score_kernel", "unit": "TFLOP/s",
+                   "achieved": 2.0 * fma_issued / sec / 1e12, "achieved_survey_convention": flops_alg / sec / 1e12}
+            try:
+                from speaker_recognition_b200 import build as b
+                LB = C.CDLL(b.BENCH_OUT)
+                LB.srb200_bench_fma_tflops.restype = C.c_double
+                LB.srb200_bench_fma_tflops.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+                pk = {name: LB.srb200_bench_fma_tflops(v, 4000, 3, None) for v, name in ((0, "ffma_indep"), (1, "ffma_pair"), (2, "ffma2_packed"))}
+                fma["peak"] = max(pk.values())
+                fma["peak_variants"] = pk
+                fma["peak_source"] = "measured in this run (csrc/bench/fma_peak.cu)"
+                fma["frac"] = fma["achieved"] / fma["peak"]
+            except Exception as e:  # measurement helper missing: nominal figure, flagged
+                fma["peak"] = 148 * 128 * 2 * 1.965e9 / 1e12
+                fma["peak_source"] = "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (helper failed: %s)" % e
+                fma["frac"] = fma["achieved"] / fma["peak"]
+        if route == 1:
+            # tensor route: the Mahalanobis sum as a GEMM [T x (2D+1)] . [(2D+1) x S K].  ALGORITHMIC flops = one pass over the
+            # unpadded K; the kernel executes 3 tf32 passes (3xTF32 split for fp32-grade accuracy) over
+            # K padded to a multiple of 8, reported as `executed`.  Peak: dense tf32 = half the measured cuBLAS bf16 figure
+            # (tensor-core rate halves from 16-bit to tf32 operands: 2.25 vs 1.1 PFLOP/s nominal, B200_PROFILING.md) --
+            # the sustained one, because the kernel is timed inside the step loop.
+            gemm_alg = 2.0 * (2 * DIM + 1) * T * S_SPK * K_MIX
+            kp = ((2 * DIM + 1 + 7) // 8) * 8
+            gemm_exec = 3.0 * 2.0 * kp * T * S_SPK * K_MIX
+            if peaks.get("bf16_tflops_sustained"):
+                tpeak, tsrc = peaks["bf16_tflops_sustained"] / 2.0, "measured bf16_tflops_sustained / 2 (MEASURED_PEAKS.json; tf32 = half the bf16 rate)"
+            else:
+                tpeak, tsrc = 1100.0, "fallback: nominal dense tf32 1.1 PFLOP/s (B200_PROFILING.md)"
+            roofline = {"bound": "tensor", "kernel": kname, "achieved": gemm_alg / sec / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                        "frac": gemm_alg / sec / 1e12 / tpeak, "traffic": traffic, "peak_source": tsrc, "ms_per_launch": score_ms,
+                        "algorithmic_flops": gemm_alg, "executed": gemm_exec / sec / 1e12, "executed_frac": gemm_exec / sec / 1e12 / tpeak,
+                        "note": "3xTF32: the kernel issues 3 tensor passes per algorithmic pass, so frac <= 1/3 by construction; "
+                                "executed_frac is the tensor-pipe utilisation against the same peak"}
+            binding = "tensor_tf32"
+        else:
+            roofline = hbm
+            binding = "fp32_fma"
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -323,7 +349,9 @@ def main():
                         "ms_per_step": e2e_ms / args.steps, "api": "pipeline.BatchScorer.predict_pcm"},
                 "gpu_launches": BatchScorer.KERNELS_PER_STEP * args.steps,
                 "kernel_ms": {"mfcc_features": feat_ms, "gmm_score": score_ms},
-                "roofline": roofline, "roofline_fma": fma, "binding_roofline": "fp32_fma",
+                "score_route": "tcgen05_3xtf32" if route == 1 else "fp32_fma",
+                "roofline": roofline, "roofline_hbm": hbm if route == 1 else None, "roofline_fma": fma if route == 0 else None,
+                "binding_roofline": binding,
                 "cpu_baseline": cpu_baseline, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -72,12 +72,15 @@ int srb200_get_device(void);
 int srb200_set_compat_clamp(int mode);
 int srb200_get_compat_clamp(void);
 
-/* scoring arithmetic route.  0 (default): fp32 FMA kernel, 2e-7 relative per frame.  1: tensor-core kernel (tcgen05, 3xTF32
- * with fp32 accumulation in TMEM): the expanded-square GEMM form, measured 3.7e-5 worst per-frame relative error on
- * sigma-floor models -- inside the 1e-4 parity bound, identical argmax -- and several times faster.  EM training always
- * uses route 0.  The environment variable SRB200_SCORE_TC=1 selects route 1 when this is never called. */
+/* scoring arithmetic route.  1: tensor-core kernel (tcgen05 kind::tf32 as 3xTF32, fp32 accumulation in tensor memory) on the
+ * expanded-square GEMM form, with the (mixture, dim) entries whose sigma < 0.1 added back exactly in fp32: <= 3e-5 relative
+ * per frame against float64 on sigma-floor models (tests/test_gmm_tc_gpu.py), inside the 1e-4 parity bound, identical
+ * argmax.  0: fp32 FMA kernel, 2e-7 relative per frame, about 3x slower.  -1 (default): route 1 wherever the model set
+ * supports it (D <= 63, few tiny-sigma entries) unless the environment variable SRB200_SCORE_TC=0; the per-frame log2
+ * output of the EM E-step always uses route 0.  srb200_last_score_route() tells which route the last launch took. */
 int srb200_set_score_path(int path);
 int srb200_get_score_path(void);
+int srb200_last_score_route(void);
 
 int srb200_gmm_set_params(GMM *gmm, int nr_mixture, int dim, const double *weights, const double *means, const double *sigmas); /* means,sigmas [K*D]; sigma = std-dev (gmm.hh:31) */
 int srb200_gmm_get_params(GMM *gmm, double *weights, double *means, double *sigmas);

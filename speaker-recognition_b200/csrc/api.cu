@@ -641,11 +641,12 @@ int srb200_set_compat_clamp(int mode) {
 int srb200_get_compat_clamp(void) { return ctx().compat_clamp; }
 int srb200_set_score_path(int path) {
 	API_ENTER();
-	SRB_REQUIRE(path == 0 || path == 1, "score path must be 0 (fp32 FMA) or 1 (tcgen05 3xTF32)");
+	SRB_REQUIRE(path >= -1 && path <= 1, "score path must be -1 (default), 0 (fp32 FMA) or 1 (tcgen05 3xTF32)");
 	ctx().score_path = path;
 	return 0;
 }
 int srb200_get_score_path(void) { return ctx().score_path; }
+int srb200_last_score_route(void) { return ctx().last_score_route; }
 
 GMM *new_gmm(int nr_mixture, int covariance_type) {
 	API_ENTER();

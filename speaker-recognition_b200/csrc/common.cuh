@@ -55,7 +55,8 @@ struct Context {
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;
 	int compat_clamp = 1;
-	int score_path = -1;        // 0: fp32 FMA kernel (default), 1: tcgen05 3xTF32 kernel; -1: unset -> env SRB200_SCORE_TC
+	int score_path = -1;        // 0: fp32 FMA kernel, 1: tcgen05 3xTF32 kernel; -1: default (tensor-core route unless SRB200_SCORE_TC=0)
+	int last_score_route = -1;  // route the most recent scoring launch took (0 / 1)
 	// workspaces for host entry points (guarded by mu)
 	DevBuf d_x, d_out, d_tiles, d_partial, d_sums, d_misc, d_pcm, d_ceps, d_feat, d_stats, d_frame;
 	PinBuf h_x, h_out, h_misc, h_pcm;

@@ -453,13 +453,16 @@ int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *ut
 		if (es && es[0] == '1') g_score_stagger = true;
 		g_score_attr_set = true;
 	}
-	// ---- arithmetic route: tcgen05 3xTF32 (explicit opt-in) or fp32 FMA ----
+	// ---- arithmetic route: tcgen05 3xTF32 (default where the model set supports it) or fp32 FMA (per-frame log2 output for
+	// the EM E-step, D > 63, too many tiny-sigma entries, or on request) ----
 	int path = c.score_path;
 	if (path < 0) {
 		const char *et = getenv("SRB200_SCORE_TC");
-		path = (et && et[0] == '1') ? 1 : 0;
+		path = (et && et[0] == '0') ? 0 : 1;
 	}
+	c.last_score_route = 0;
 	if (path == 1 && !frame_log2 && tc_supported(pm, D)) {
+		c.last_score_route = 1;
 		TileTable *tt = nullptr;
 		if (get_table(utt_off, n_utt, pm.S, 128, st, &tt)) return 1;
 		if (launch_score_tc(pm, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;

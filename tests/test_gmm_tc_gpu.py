@@ -19,7 +19,7 @@ def tc_route():
     L = _lib.lib()
     _lib.check(L.srb200_set_score_path(1))
     yield L
-    _lib.check(L.srb200_set_score_path(0))
+    _lib.check(L.srb200_set_score_path(-1))
 
 
 def build_set(S, K, D, seed0=1000, floor_frac=0.01):
