@@ -98,6 +98,14 @@ int srb200_score_batch_f32(GMM *gmm, const float *X, int n, int dim, float *prob
 int srb200_train_f64(GMM *gmm, const double *X, const Parameter *param, uint64_t seed, int *iters_out, double *ll_out);
 int srb200_train_from_ubm_f64(GMM *gmm, GMM *ubm, const double *X, const Parameter *param, int *iters_out, double *ll_out);
 
+/* K-MeansII initialisation (the reference's init_with_kmeans = 1: gmm.cc:331-344 -> kmeansII.cc:80-172, kmeans++.cc:157-213,
+ * kmeans.cc:150-340), also what train_model / srb200_train_f64 run when param->init_with_kmeans != 0.  X is [n][dim] HOST memory,
+ * centroids [K][dim].  All draws derive from `seed` (counter-based; the reference uses libc rand()), distances are float64 in the
+ * reference's operation order.  srb200_kmeans_lloyd_f64 runs the Lloyd iterations alone from the given centroids (in/out),
+ * optionally weighted (weight[n] or NULL), and returns the best cost and the number of iterations. */
+int srb200_kmeans_init_f64(const double *X, int n, int dim, int K, uint64_t seed, double *centroids, double *cost_out);
+int srb200_kmeans_lloyd_f64(const double *X, int n, int dim, int K, const double *weight, double *centroids, double *cost_out, int *iters_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Speaker set: S models scored in ONE launch (replaces the Python loop of GMMSet.predict_one_scores,
  * src/testbench/gmmset.py:59-64,95-99)

@@ -8,10 +8,14 @@
  *     neither; its training init draws from an RNG seeded by rand(), random.hh:21-25),
  *   - run exactly ONE GMMTrainerBaseline::iteration (gmm.cc:439-531) or one MAP iteration
  *     (GMMUBMTrainerBaseline, gmmubm.cc:40-81) from an injected start,
- *   - score contiguous double matrices without the per-row ctypes marshalling.
+ *   - score contiguous double matrices without the per-row ctypes marshalling,
+ *   - run the reference's Lloyd iterations from injected centroids (KMeansSolver::Lloyds_iteration[_weighted],
+ *     kmeans.cc:150-340) and its whole K-MeansII initialisation after srand(seed) (kmeansII.cc:80-172).
  * It includes the reference headers from where they lie; it copies no reference code.
  */
 #include "gmm.hh"
+#include "kmeansII.hh"
+#include "kmeans++.hh"
 
 #include <vector>
 #include <cstring>
@@ -105,5 +109,58 @@ void ref_score_batch_exactexp(GMM *g, const double *X, double *out, int n, int d
 
 int ref_dim(GMM *g) { return g->dim; }
 int ref_nr_mixtures(GMM *g) { return g->nr_mixtures; }
+
+
+static void to_dataset(const double *X, int n, int dim, Dataset &ds) {
+	ds.resize(n);
+	for (int i = 0; i < n; i++) {
+		ds[i].resize(dim);
+		for (int d = 0; d < dim; d++) ds[i][d] = std::make_pair(d, X[(size_t)i * dim + d]);
+	}
+}
+
+/* Lloyd iterations of the reference from the given centroids (in/out); weight may be NULL.  Returns the best cost. */
+double ref_lloyd(const double *X, int n, int dim, int K, const double *weight, double *cent, int concurrency) {
+	Dataset ds;
+	to_dataset(X, n, dim, ds);
+	std::vector<Vector> c(K, Vector(dim));
+	for (int k = 0; k < K; k++) c[k].assign(cent + (size_t)k * dim, cent + (size_t)(k + 1) * dim);
+	KMeansSolver solver(concurrency);
+	double cost;
+	if (weight) {
+		std::vector<real_t> w(weight, weight + n);
+		cost = solver.Lloyds_iteration_weighted(ds, w, c);
+	} else {
+		cost = solver.Lloyds_iteration(ds, c);
+	}
+	for (int k = 0; k < K; k++) memcpy(cent + (size_t)k * dim, c[k].data(), sizeof(double) * dim);
+	return cost;
+}
+
+/* the reference's whole K-MeansII initialisation (what init_gaussians runs, gmm.cc:331-337) after srand(seed) */
+double ref_kmeansII(const double *X, int n, int dim, int K, unsigned seed, double *cent, int concurrency) {
+	srand(seed);
+	Dataset ds;
+	to_dataset(X, n, dim, ds);
+	std::vector<Vector> c;
+	KMeansIISolver solver(concurrency);
+	const double cost = solver.cluster(ds, c, K);
+	for (int k = 0; k < K; k++) memcpy(cent + (size_t)k * dim, c[k].data(), sizeof(double) * dim);
+	return cost;
+}
+
+
+/* the reference's weighted k-means++ stage (KMeansppSolver::cluster_weighted, kmeans++.cc:157-213) on given candidates, after srand(seed) */
+double ref_kmeanspp_weighted(const double *Cand, int m, int dim, const double *weight, int K, unsigned seed, double *cent, int concurrency) {
+	srand(seed);
+	std::vector<Vector> ds(m, Vector(dim));
+	for (int i = 0; i < m; i++) ds[i].assign(Cand + (size_t)i * dim, Cand + (size_t)(i + 1) * dim);
+	std::vector<real_t> w(weight, weight + m);
+	std::vector<Vector> c;
+	KMeansppSolver solver(concurrency);
+	const double cost = solver.cluster_weighted(ds, w, c, K);
+	for (int k = 0; k < K; k++) memcpy(cent + (size_t)k * dim, c[k].data(), sizeof(double) * dim);
+	return cost;
+}
 
 }

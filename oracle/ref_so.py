@@ -57,6 +57,9 @@ def lib():
     L.ref_map_iteration.restype, L.ref_map_iteration.argtypes = None, [vp, vp, dp, ci, ci, ci]
     L.ref_score_batch.restype, L.ref_score_batch.argtypes = None, [vp, dp, dp, ci, ci, ci]
     L.ref_score_batch_exactexp.restype, L.ref_score_batch_exactexp.argtypes = None, [vp, dp, dp, ci, ci]
+    L.ref_lloyd.restype, L.ref_lloyd.argtypes = cd, [dp, ci, ci, ci, dp, dp, ci]
+    L.ref_kmeansII.restype, L.ref_kmeansII.argtypes = cd, [dp, ci, ci, ci, C.c_uint, dp, ci]
+    L.ref_kmeanspp_weighted.restype, L.ref_kmeanspp_weighted.argtypes = cd, [dp, ci, ci, dp, ci, C.c_uint, dp, ci]
     _lib = L
     return L
 
@@ -156,3 +159,50 @@ class RefGMM:
         if self.h:
             lib().ref_free(self.h)
             self.h = None
+
+
+def _quiet_call(fn, *args):
+    """the reference's k-means prints progress with printf: silence fd 1 around the call"""
+    import sys
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(devnull, 1)
+        return fn(*args)
+    finally:
+        C.CDLL(None).fflush(None)
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+
+
+def ref_lloyd(X, cent, weight=None, concurrency=4):
+    """KMeansSolver::Lloyds_iteration[_weighted] (kmeans.cc:150-340) from the given centroids: (centroids, best cost)"""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    c = np.ascontiguousarray(cent, dtype=np.float64).copy()
+    dp = C.POINTER(C.c_double)
+    w = None if weight is None else np.ascontiguousarray(weight, dtype=np.float64)
+    cost = _quiet_call(lib().ref_lloyd, X.ctypes.data_as(dp), X.shape[0], X.shape[1], c.shape[0],
+                       None if w is None else w.ctypes.data_as(dp), c.ctypes.data_as(dp), concurrency)
+    return c, float(cost)
+
+
+def ref_kmeansII(X, K, seed, concurrency=4):
+    """KMeansIISolver::cluster (kmeansII.cc:80-172) after srand(seed): (centroids, cost)"""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    c = np.zeros((K, X.shape[1]))
+    dp = C.POINTER(C.c_double)
+    cost = _quiet_call(lib().ref_kmeansII, X.ctypes.data_as(dp), X.shape[0], X.shape[1], K, int(seed), c.ctypes.data_as(dp), concurrency)
+    return c, float(cost)
+
+
+def ref_kmeanspp_weighted(Cand, weight, K, seed, concurrency=4):
+    """KMeansppSolver::cluster_weighted (kmeans++.cc:157-213) after srand(seed): (centroids, weighted cost)"""
+    Cand = np.ascontiguousarray(Cand, dtype=np.float64)
+    w = np.ascontiguousarray(weight, dtype=np.float64)
+    c = np.zeros((K, Cand.shape[1]))
+    dp = C.POINTER(C.c_double)
+    cost = _quiet_call(lib().ref_kmeanspp_weighted, Cand.ctypes.data_as(dp), Cand.shape[0], Cand.shape[1], w.ctypes.data_as(dp), K, int(seed),
+                       c.ctypes.data_as(dp), concurrency)
+    return c, float(cost)

@@ -542,8 +542,10 @@ static inline uint64_t splitmix64(uint64_t &s) {
 	return z ^ (z >> 31);
 }
 
-// init_gaussians (gmm.cc:306-361) without k-means: means = random data rows, sigma = global unbiased std, w = 1/K
-static int init_like_reference(GMM *g, const RowSrc &src, int n, int D, uint64_t seed) {
+// init_gaussians (gmm.cc:306-361): sigma = global unbiased std, w = 1/K; means = random data rows, or (init_with_kmeans) the
+// K-MeansII centroids computed on the staged device features (kmeans.cu)
+static int init_like_reference(GMM *g, const RowSrc &src, int n, int D, uint64_t seed, const float *d_staged, int ld, int with_kmeans,
+                               int verbosity) {
 	const int K = g->nr_mixtures;
 	auto row = [&](int i, int d) -> double { return src.pp ? src.pp[i][d] : src.c64[(size_t)i * D + d]; };
 	std::vector<double> mean(D, 0.0), var(D, 0.0);
@@ -559,13 +561,16 @@ static int init_like_reference(GMM *g, const RowSrc &src, int n, int D, uint64_t
 	g->weights.assign(K, 1.0 / K);
 	g->means.resize((size_t)K * D);
 	g->sigmas.resize((size_t)K * D);
+	if (with_kmeans) {
+		if (kmeans2_init_device(d_staged, n, ld, D, K, seed, g->means.data(), nullptr, verbosity)) return 1;   // gmm.cc:331-344
+	}
 	uint64_t s = seed;
 	for (int k = 0; k < K; ++k) {
 		const double u = (double)(splitmix64(s) >> 11) * (1.0 / 9007199254740992.0);
 		int idx = (int)(u * n);                          // rand_int: rand_real() * max_val, random.hh:46-48
 		if (idx >= n) idx = n - 1;
 		for (int d = 0; d < D; ++d) {
-			g->means[(size_t)k * D + d] = row(idx, d);
+			if (!with_kmeans) g->means[(size_t)k * D + d] = row(idx, d);
 			g->sigmas[(size_t)k * D + d] = sqrt(var[d] * (1.0 / (n - 1)));   // gmm.cc:323-325
 		}
 	}
@@ -587,11 +592,12 @@ static int train_host(GMM *g, GMM *ubm, const RowSrc &src, const Parameter *p, u
 	SRB_REQUIRE(n > 0, "X.size() == 0");                 // gmm.cc:582-586 (thrown as const char* in the reference)
 	SRB_REQUIRE(D >= 1 && D <= MAX_DIM, "train: nr_dim %d outside [1,%d]", D, MAX_DIM);
 	if (p->verbosity >= 1) print_param(p);
+	int ld = 0;
+	if (stage_frames(src, n, D, &ld)) return 1;
 	if (ubm == nullptr) {
 		SRB_REQUIRE(g->nr_mixtures >= 1, "train: model has no mixtures");
-		SRB_REQUIRE(p->init_with_kmeans == 0, "train: init_with_kmeans=1 (K-MeansII, kmeansII.cc) is not built yet; pygmm.py's default is 0");
 		SRB_REQUIRE(n >= 2, "train: need at least 2 instances");
-		if (init_like_reference(g, src, n, D, seed)) return 1;
+		if (init_like_reference(g, src, n, D, seed, ctx().d_x.as<float>(), ld, p->init_with_kmeans != 0, p->verbosity)) return 1;
 	} else {
 		if (gmm_pull_device_master(ubm)) return 1;
 		SRB_REQUIRE(ubm->dim == D, "train_from_ubm: UBM dim %d != data dim %d", ubm->dim, D);
@@ -603,8 +609,6 @@ static int train_host(GMM *g, GMM *ubm, const RowSrc &src, const Parameter *p, u
 		g->sigmas = ubm->sigmas;
 		g->invalidate();
 	}
-	int ld = 0;
-	if (stage_frames(src, n, D, &ld)) return 1;
 	return train_driver(g, ctx().d_x.as<float>(), n, ld, D, p, ubm ? 1 : 0, ubm, iters_out, ll_out);
 }
 
@@ -792,6 +796,30 @@ void train_model_from_ubm(GMM *gmm, GMM *ubm, double **X_in, Parameter *param) {
 	src.pp = X_in;
 	train_host(gmm, ubm, src, param, 0, nullptr, nullptr);
 }
+int srb200_kmeans_init_f64(const double *X, int n, int dim, int K, uint64_t seed, double *centroids, double *cost_out) {
+	API_ENTER();
+	SRB_REQUIRE(X != nullptr && centroids != nullptr, "kmeans_init: null argument");
+	SRB_REQUIRE(n >= 1 && K >= 1 && dim >= 1 && dim <= MAX_DIM, "kmeans_init: bad shape n=%d K=%d dim=%d", n, K, dim);
+	if (ctx().init()) return 1;
+	RowSrc src;
+	src.c64 = X;
+	int ld = 0;
+	if (stage_frames(src, n, dim, &ld)) return 1;
+	return kmeans2_init_device(ctx().d_x.as<float>(), n, ld, dim, K, seed, centroids, cost_out, 0);
+}
+
+int srb200_kmeans_lloyd_f64(const double *X, int n, int dim, int K, const double *weight, double *centroids, double *cost_out, int *iters_out) {
+	API_ENTER();
+	SRB_REQUIRE(X != nullptr && centroids != nullptr, "kmeans_lloyd: null argument");
+	SRB_REQUIRE(n >= 1 && K >= 1 && dim >= 1 && dim <= MAX_DIM, "kmeans_lloyd: bad shape n=%d K=%d dim=%d", n, K, dim);
+	if (ctx().init()) return 1;
+	RowSrc src;
+	src.c64 = X;
+	int ld = 0;
+	if (stage_frames(src, n, dim, &ld)) return 1;
+	return kmeans_lloyd_device(ctx().d_x.as<float>(), n, ld, dim, K, weight, centroids, cost_out, iters_out);
+}
+
 int srb200_train_f64(GMM *gmm, const double *X, const Parameter *param, uint64_t seed, int *iters_out, double *ll_out) {
 	API_ENTER();
 	RowSrc src;

@@ -47,6 +47,10 @@ int launch_lpc(const double *d_win, const double *d_win2, int L, int shift, cons
 int launch_lpc_for_plan(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp_off, int n_utt, int order, float *d_out,
                         int ld, int col_off, int *feat_off, cudaStream_t st);
 
+// ---- kmeans.cu: K-MeansII initialisation (gmm.cc:331-344) on staged device features ----
+int kmeans2_init_device(const float *dX, int n, int ld, int D, int K, uint64_t seed, double *centroids_out, double *cost_out, int verbosity);
+int kmeans_lloyd_device(const float *dX, int n, int ld, int D, int K, const double *h_w, double *h_cent, double *cost_out, int *iters_out);
+
 // ---- silence.cu ----
 int launch_remove_silence(const void *d_pcm, int is_u8, long long n, int frame_len, int shift_len, double perc, long long *d_ps,
                           long long *d_block, longlong3 *d_segs, long long *d_counts, void *d_out, cudaStream_t st);

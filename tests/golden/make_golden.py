@@ -181,11 +181,37 @@ def gen_lpc():
     print("lpc_ref.npz:", {k: v.shape for k, v in flat.items() if k.endswith("/out")})
 
 
+def gen_kmeans():
+    """K-MeansII initialisation (gmm.cc:331-344): the compiled reference's Lloyd iterations from injected centroids
+    (KMeansSolver::Lloyds_iteration[_weighted], kmeans.cc:150-340 -- deterministic) and the final cost of its whole
+    KMeansIISolver::cluster (kmeansII.cc:80-172) for several srand() seeds (randomised: a statistical pin)."""
+    rng = np.random.default_rng(2024)
+    flat = {}
+    for name, n_per, D, n_clusters, K in [("a", 400, 6, 10, 8), ("b", 150, 13, 24, 32)]:
+        centers = rng.normal(0, 4, (n_clusters, D))
+        X = np.concatenate([c + rng.normal(0, 1, (n_per, D)) for c in centers])
+        rng.shuffle(X)
+        X = X.astype(np.float32).astype(np.float64)                 # the product stages fp32 frames: keep the data exactly representable
+        init = X[:K].copy()
+        w = rng.integers(0, 5, len(X)).astype(np.float64)
+        c_u, cost_u = ref_so.ref_lloyd(X, init)
+        c_w, cost_w = ref_so.ref_lloyd(X, init, w)
+        costs = [ref_so.ref_kmeansII(X, K, seed)[1] for seed in range(100, 130)]
+        flat.update({name + "/X": X, name + "/K": np.int64(K), name + "/init": init, name + "/weight": w,
+                     name + "/lloyd_cent": c_u, name + "/lloyd_cost": np.float64(cost_u),
+                     name + "/wlloyd_cent": c_w, name + "/wlloyd_cost": np.float64(cost_w),
+                     name + "/kmeansII_costs": np.array(costs)})
+    np.savez_compressed(os.path.join(HERE, "kmeans_ref.npz"), **flat)
+    print("kmeans_ref.npz:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in flat.items() if "cost" in k})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mfcc", "gmm", "lpc"]
+    which = sys.argv[1:] or ["mfcc", "gmm", "lpc", "kmeans"]
     if "mfcc" in which:
         gen_mfcc()
     if "gmm" in which:
         gen_gmm()
     if "lpc" in which:
         gen_lpc()
+    if "kmeans" in which:
+        gen_kmeans()
