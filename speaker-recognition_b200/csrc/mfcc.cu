@@ -50,6 +50,10 @@ struct MfccPlan {
 	bool fast = false;
 	cpx *d_tw1 = nullptr, *d_twA = nullptr;
 	int4 *d_mel_desc = nullptr;
+	int2 *d_mel_seg = nullptr;       // 16-bin segments of the bands' runs: {first bin, band}; weights d_mel_w16[seg][16]
+	float *d_mel_w16 = nullptr;
+	int *d_mel_segptr = nullptr;     // [nb + 1] first segment of every band
+	int n_seg = 0;
 	size_t smem_fast = 0;
 	std::vector<MfccShape> shapes;
 	uint64_t stamp = 0;
@@ -71,6 +75,10 @@ struct MfccArgs {
 	double *partials;
 	const cpx *tw1, *twA;      // fast path tables
 	const int4 *mel_desc;      // fast path: per band, by descending non-zero count: {band, first nz, count, first bin}
+	const int2 *mel_seg;       // fast path: 16-bin segments {first bin, band}, weights mel_w16[seg][16] (zero outside the band's run)
+	const float *mel_w16;
+	const int *mel_segptr;
+	int n_seg;
 };
 
 __device__ __forceinline__ int find_segment(const int *__restrict__ start, int n, int x) {
@@ -265,44 +273,43 @@ __global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const M
 	srbfft::fast_power_unpack(Zs + f * 4 * srbfft::FAST_ZSTRIDE, P + f * PSTR, A.tw2, tid & 63);
 	__syncthreads();
 
-	// mel + log: one 8-lane group per (frame, band).  The filters are triangles, so a band's non-zeros are a contiguous
-	// run of bins starting at mel_col[ptr[b]] (checked on the host): the lanes read consecutive P values (no column
-	// look-up) and shuffle-reduce in a fixed order (deterministic).  Items are visited in descending non-zero count
-	// (mel_order) so that the 32 groups of a round carry similar work.
+	// mel + log.  A band's non-zeros are one contiguous run of bins (triangular filters; checked on the host).  The runs are cut
+	// into 16-bin segments (the last one end-aligned, weights zero where it overlaps its predecessor): one thread per
+	// (frame, segment) does 16 multiply-adds on consecutive P values with its weights in four 128-bit loads, all items carry
+	// the same work; then one thread per (frame, band) adds the band's segment sums in segment order (deterministic) and
+	// takes the log.  (The first version walked (frame, band) items with 8-lane groups: 25 instructions per multiply-add.)
 	float *logE = ybuf;                                                          // [NF][nb]
+	float *segsum = ybuf + 512;                                                  // [NF][n_seg]  (n_seg <= 384, host-checked)
 	{
-		const int group = tid >> 3, l8 = tid & 7;
-		const int items = MFF_NF * nb;
-		// mel_desc[rank] = {band, first non-zero j0, count n, first bin c0}: one 128-bit load per item, and two items of
-		// a group are kept in flight (independent chains) to overlap the load / shuffle latencies
-		for (int it = 0; it * 64 < items; ++it) {
-			const int itemA = it * 64 + group, itemB = itemA + 32;
-			const bool vA = itemA < items, vB = itemB < items;
-			const int4 dA = vA ? __ldg(A.mel_desc + (itemA >> 2)) : make_int4(0, 0, 0, 0);
-			const int4 dB = vB ? __ldg(A.mel_desc + (itemB >> 2)) : make_int4(0, 0, 0, 0);
-			const float *vAp = A.mel_val + dA.y, *vBp = A.mel_val + dB.y;
-			const float *PA = P + (itemA & (MFF_NF - 1)) * PSTR + dA.w, *PB = P + (itemB & (MFF_NF - 1)) * PSTR + dB.w;
-			float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-			const int nA = dA.z, nB = dB.z, nmax = nA > nB ? nA : nB;
-			for (int i = l8; i < nmax; i += 16) {
-				const float va0 = i < nA ? __ldg(vAp + i) : 0.f, va1 = i + 8 < nA ? __ldg(vAp + i + 8) : 0.f;
-				const float vb0 = i < nB ? __ldg(vBp + i) : 0.f, vb1 = i + 8 < nB ? __ldg(vBp + i + 8) : 0.f;
-				const float pa0 = i < nA ? PA[i] : 0.f, pa1 = i + 8 < nA ? PA[i + 8] : 0.f;
-				const float pb0 = i < nB ? PB[i] : 0.f, pb1 = i + 8 < nB ? PB[i + 8] : 0.f;
-				a0 = fmaf(va0, pa0, a0);
-				a1 = fmaf(va1, pa1, a1);
-				b0 = fmaf(vb0, pb0, b0);
-				b1 = fmaf(vb1, pb1, b1);
-			}
-			float ea = a0 + a1, eb = b0 + b1;
-			ea += __shfl_xor_sync(0xffffffffu, ea, 4);
-			eb += __shfl_xor_sync(0xffffffffu, eb, 4);
-			ea += __shfl_xor_sync(0xffffffffu, ea, 2);
-			eb += __shfl_xor_sync(0xffffffffu, eb, 2);
-			ea += __shfl_xor_sync(0xffffffffu, ea, 1);
-			eb += __shfl_xor_sync(0xffffffffu, eb, 1);
-			if (vA && l8 == 0) logE[(itemA & (MFF_NF - 1)) * nb + dA.x] = ea > 0.f ? logf(ea) : __ldg(A.logfloor + dA.x);
-			if (vB && l8 == 1) logE[(itemB & (MFF_NF - 1)) * nb + dB.x] = eb > 0.f ? logf(eb) : __ldg(A.logfloor + dB.x);
+		const int n_seg = A.n_seg, items = MFF_NF * n_seg;
+		for (int item = tid; item < items; item += MF_THREADS) {
+			const int ff = item / n_seg, sg = item - ff * n_seg;
+			const int2 d = __ldg(A.mel_seg + sg);
+			const float4 *w4 = reinterpret_cast<const float4 *>(A.mel_w16 + (size_t)sg * 16);
+			const float *Pp = P + ff * PSTR + d.x;
+			const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1), w2 = __ldg(w4 + 2), w3 = __ldg(w4 + 3);
+			float e0 = w0.x * Pp[0], e1 = w0.y * Pp[1], e2 = w0.z * Pp[2], e3 = w0.w * Pp[3];
+			e0 = fmaf(w1.x, Pp[4], e0);
+			e1 = fmaf(w1.y, Pp[5], e1);
+			e2 = fmaf(w1.z, Pp[6], e2);
+			e3 = fmaf(w1.w, Pp[7], e3);
+			e0 = fmaf(w2.x, Pp[8], e0);
+			e1 = fmaf(w2.y, Pp[9], e1);
+			e2 = fmaf(w2.z, Pp[10], e2);
+			e3 = fmaf(w2.w, Pp[11], e3);
+			e0 = fmaf(w3.x, Pp[12], e0);
+			e1 = fmaf(w3.y, Pp[13], e1);
+			e2 = fmaf(w3.z, Pp[14], e2);
+			e3 = fmaf(w3.w, Pp[15], e3);
+			segsum[item] = (e0 + e1) + (e2 + e3);
+		}
+		__syncthreads();
+		for (int t = tid; t < MFF_NF * nb; t += MF_THREADS) {
+			const int ff = t / nb, b = t - ff * nb;
+			const int s0 = __ldg(A.mel_segptr + b), s1 = __ldg(A.mel_segptr + b + 1);
+			float e = 0.f;
+			for (int sg = s0; sg < s1; ++sg) e += segsum[ff * n_seg + sg];
+			logE[t] = e > 0.f ? logf(e) : __ldg(A.logfloor + b);
 		}
 	}
 	__syncthreads();
@@ -510,7 +517,32 @@ static int build_tables(MfccPlan *p) {
 			const int b = order[rk], n = ptr[b + 1] - ptr[b];
 			desc[rk] = make_int4(b, ptr[b], n, n > 0 ? col[ptr[b]] : 0);
 		}
-		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_desc, desc)) return 1;
+		// 16-bin segments of the runs (see the mel stage of mfcc_frames_fast_kernel)
+		std::vector<int2> seg;
+		std::vector<float> w16;
+		std::vector<int> segptr(nb + 1, 0);
+		for (int b = 0; b < nb; ++b) {
+			const int n = ptr[b + 1] - ptr[b], c0 = n > 0 ? col[ptr[b]] : 0;
+			int covered = c0;                                    // bins of the run below this index are already in a segment
+			for (int st = c0; covered < c0 + n;) {
+				int first = st;
+				if (first + 16 > c0 + n) first = std::max(0, c0 + n - 16);   // end-align the last segment
+				seg.push_back(make_int2(first, b));
+				for (int i = 0; i < 16; ++i) {
+					const int bin = first + i;
+					const bool in = bin >= covered && bin < c0 + n;
+					w16.push_back(in ? val[ptr[b] + (bin - c0)] : 0.f);
+				}
+				covered = first + 16;
+				st = covered;
+			}
+			segptr[b + 1] = (int)seg.size();
+		}
+		p->n_seg = (int)seg.size();
+		if (p->n_seg > 384 || p->n_seg == 0) p->fast = false;   // the segment sums share a 1.5 K-float shared-memory region
+		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_desc, desc) || to_device(&p->d_mel_seg, seg) ||
+		    to_device(&p->d_mel_w16, w16) || to_device(&p->d_mel_segptr, segptr))
+			return 1;
 	}
 	if (to_device(&p->d_win, win) || to_device(&p->d_win2, win2) || to_device(&p->d_mel_ptr, ptr) ||
 	    to_device(&p->d_mel_col, col) || to_device(&p->d_mel_val, val) || to_device(&p->d_logfloor, logfloor) ||
@@ -600,6 +632,9 @@ void mfcc_plan_free(MfccPlan *p) {
 	cudaFree(p->d_tw1);
 	cudaFree(p->d_twA);
 	cudaFree(p->d_mel_desc);
+	cudaFree(p->d_mel_seg);
+	cudaFree(p->d_mel_w16);
+	cudaFree(p->d_mel_segptr);
 	delete p;
 }
 
@@ -701,6 +736,10 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.tw1 = p->d_tw1;
 	a.twA = p->d_twA;
 	a.mel_desc = p->d_mel_desc;
+	a.mel_seg = p->d_mel_seg;
+	a.mel_w16 = p->d_mel_w16;
+	a.mel_segptr = p->d_mel_segptr;
+	a.n_seg = p->n_seg;
 	static const bool force_generic = [] { const char *e = getenv("SRB200_MFCC_GENERIC"); return e && e[0] == '1'; }();
 	if (p->fast && !force_generic) mfcc_frames_fast_kernel<<<s->n_cta, MF_THREADS, p->smem_fast, st>>>(a);
 	else mfcc_frames_kernel<<<s->n_cta, MF_THREADS, p->smem, st>>>(a);

@@ -8,6 +8,7 @@ Multi-GPU: utterances are independent, so ranks simply take disjoint utterance s
 data path (SURVEY.md s8e "Predict, many utterances").
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -61,8 +62,14 @@ class BatchScorer(object):
         self._shape = key
         # sub-batches for the end-to-end path: H2D of chunk c+1 overlaps the kernels of chunk c
         self.chunks = []
-        n_chunks = 4 if B >= 8 else 1
-        bounds = [round(i * B / n_chunks) for i in range(n_chunks + 1)]
+        # a small first sub-batch starts the kernels early (its copy is the only one nothing overlaps), later ones grow so the
+        # persistent scorer's waves stay full (measured at C2 x 64: equal quarters 13.66 ms, this schedule 12.69 ms per step); SRB200_E2E_CHUNKS="f1,f2,..." (cumulative fractions) overrides
+        fr = [1 / 32, 1 / 8, 5 / 16, 5 / 8, 1.0] if B >= 32 else ([0.25, 0.5, 0.75, 1.0] if B >= 8 else [1.0])
+        env = os.environ.get("SRB200_E2E_CHUNKS")
+        if env:
+            fr = [float(x) for x in env.split(",")]
+        bounds = sorted(set([0] + [min(B, max(1, round(f * B))) for f in fr] + [B]))
+        n_chunks = len(bounds) - 1
         row0 = 0
         for c in range(n_chunks):
             u0, u1 = bounds[c], bounds[c + 1]
