@@ -34,6 +34,7 @@ struct MfccShape {                 // cached per batch shape
 	int *d_cta_start = nullptr, *d_frame_off = nullptr, *d_feat_off = nullptr;
 	float *d_ceps = nullptr;
 	double *d_partials = nullptr, *d_stats = nullptr;
+	int4 *d_cta_rec = nullptr;      // fast path, per CTA: {first sample lo, hi, first output frame row, frames (1..NF)}
 	uint64_t stamp = 0;
 };
 
@@ -74,6 +75,7 @@ struct MfccArgs {
 	float *ceps;
 	double *partials;
 	const cpx *tw1, *twA;      // fast path tables
+	const int4 *cta_rec;       // fast path: per CTA {first sample (lo, hi), first frame row in ceps, frame count}
 	const int4 *mel_desc;      // fast path: per band, by descending non-zero count: {band, first nz, count, first bin}
 	const int2 *mel_seg;       // fast path: 16-bin segments {first bin, band}, weights mel_w16[seg][16] (zero outside the band's run)
 	const float *mel_w16;
@@ -223,42 +225,36 @@ __global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const M
 	cpx *Zs = T + MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE;                        // [NF][4][260]
 	float *ybuf = reinterpret_cast<float *>(Zs + MFF_NF * 4 * srbfft::FAST_ZSTRIDE);   // [NF][512]  (later logE / cep)
 
-	const int u_ = find_segment(A.cta_start, A.n_utt, blockIdx.x);
-	const int fbase = __ldg(A.frame_off + u_);
-	const int T_u = __ldg(A.frame_off + u_ + 1) - fbase;
-	const int fr0 = (blockIdx.x - __ldg(A.cta_start + u_)) * MFF_NF;
-	const int nfr = min(MFF_NF, T_u - fr0);
-	const long long s0 = A.smp_off[u_] + (long long)fr0 * A.shift;
+	// one 16-byte record per CTA (built on the host with the shape; a binary search over the utterance table cost six
+	// dependent global loads before the first sample could be requested)
+	const int4 rec = __ldg(A.cta_rec + blockIdx.x);
+	const long long s0 = ((long long)(unsigned)rec.x) | ((long long)rec.y << 32);
+	const int row0 = rec.z, nfr = rec.w;
 
-	// window then pre-emphasis (MFCC.py:61-64) straight from global memory (each sample is touched by at most four
-	// (frame, tap) pairs of this CTA: L1 serves the repeats); zeros beyond the frame and for absent frames.
-	// Fully unrolled with the loads hoisted so the 16 global reads of a thread are in flight together.
+	// window then pre-emphasis (MFCC.py:61-64) as a 2-tap form y[i] = w[i] x[i] - w2[i] x[i-1] (w2[0] = 0).  The CTA's frames
+	// overlap, so its whole sample span (plus the sample before it) is staged once in shared memory as floats: one coalesced
+	// pass, (NF-1) shift + L + 1 conversions instead of 2 NF L scattered 2-byte loads.
 	{
-		float sc[8], sp[8];
-#pragma unroll
-		for (int it = 0; it < 8; ++it) {
-			const int ff = it >> 1, i = tid + ((it & 1) << 8);
-			sc[it] = 0.f;
-			sp[it] = 0.f;
-			if (ff < nfr && i < L) {
-				const long long g = s0 + (long long)ff * A.shift + i;
-				if (A.is_f32) {
-					const float *p = reinterpret_cast<const float *>(A.pcm);
-					sc[it] = __ldg(p + g);
-					if (i > 0) sp[it] = __ldg(p + g - 1);
-				} else {
-					const int16_t *p = reinterpret_cast<const int16_t *>(A.pcm);
-					sc[it] = (float)__ldg(p + g);
-					if (i > 0) sp[it] = (float)__ldg(p + g - 1);
-				}
-			}
+		float *span = reinterpret_cast<float *>(Zs);                             // Zs is free until the second FFT step
+		const int n_span = (nfr - 1) * A.shift + L + 1;                          // span[j] = sample s0 - 1 + j
+		for (int j = tid; j < n_span; j += MF_THREADS) {
+			const long long g = s0 - 1 + j;
+			float v = 0.f;
+			if (g >= 0) v = A.is_f32 ? __ldg(reinterpret_cast<const float *>(A.pcm) + g) : (float)__ldg(reinterpret_cast<const int16_t *>(A.pcm) + g);
+			span[j] = v;
 		}
+		__syncthreads();
 		const float w0 = tid < L ? __ldg(A.win + tid) : 0.f, w1 = tid + 256 < L ? __ldg(A.win + tid + 256) : 0.f;
 		const float v0 = tid < L ? __ldg(A.win2 + tid) : 0.f, v1 = tid + 256 < L ? __ldg(A.win2 + tid + 256) : 0.f;
 #pragma unroll
 		for (int it = 0; it < 8; ++it) {
-			const float w = (it & 1) ? w1 : w0, v = (it & 1) ? v1 : v0;
-			ybuf[(it >> 1) * MFF_YLEN + tid + ((it & 1) << 8)] = fmaf(-v, sp[it], w * sc[it]);
+			const int ff = it >> 1, i = tid + ((it & 1) << 8);
+			float y = 0.f;
+			if (ff < nfr && i < L) {
+				const float *sp = span + ff * A.shift + i;
+				y = fmaf(-((it & 1) ? v1 : v0), sp[0], ((it & 1) ? w1 : w0) * sp[1]);
+			}
+			ybuf[ff * MFF_YLEN + i] = y;
 		}
 	}
 	__syncthreads();
@@ -332,13 +328,13 @@ __global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const M
 			if (valid && q4 == 0) {
 				const float c = (float)acc;
 				cep[t] = c;
-				if (ff < nfr) A.ceps[(size_t)(fbase + fr0 + ff) * A.CL + i] = c;
+				if (ff < nfr) A.ceps[(size_t)(row0 + ff) * A.CL + i] = c;
 			}
 		}
 	}
 	for (int t = tid; t < MFF_NF * (A.CL - nc); t += MF_THREADS) {
 		const int ff = t / (A.CL - nc), i = nc + t - ff * (A.CL - nc);
-		if (ff < nfr) A.ceps[(size_t)(fbase + fr0 + ff) * A.CL + i] = 0.f;
+		if (ff < nfr) A.ceps[(size_t)(row0 + ff) * A.CL + i] = 0.f;
 	}
 	__syncthreads();
 	if (tid < nc) {
@@ -612,6 +608,7 @@ static void free_shape(MfccShape &s) {
 	cudaFree(s.d_ceps);
 	cudaFree(s.d_partials);
 	cudaFree(s.d_stats);
+	cudaFree(s.d_cta_rec);
 	s = MfccShape();
 }
 
@@ -687,6 +684,19 @@ static int get_shape(MfccPlan *p, const long long *smp_off, int n_utt, int nd, c
 	SRB_CUDA(cudaMalloc(&s.d_ceps, (size_t)s.frames_total * p->CL * sizeof(float)));
 	SRB_CUDA(cudaMalloc(&s.d_partials, (size_t)s.n_cta * 2 * p->nc * sizeof(double)));
 	SRB_CUDA(cudaMalloc(&s.d_stats, (size_t)n_utt * 2 * p->nc * sizeof(double)));
+	{
+		std::vector<int4> rec((size_t)s.n_cta);
+		for (int u = 0; u < n_utt; ++u) {
+			const int T = frame_off[u + 1] - frame_off[u];
+			for (int c = cta_start[u]; c < cta_start[u + 1]; ++c) {
+				const int fr0 = (c - cta_start[u]) * p->NF;
+				const long long s0 = smp_off[u] + (long long)fr0 * p->shift;
+				rec[c] = make_int4((int)(unsigned)(s0 & 0xFFFFFFFFll), (int)(s0 >> 32), frame_off[u] + fr0, std::min(p->NF, T - fr0));
+			}
+		}
+		SRB_CUDA(cudaMalloc(&s.d_cta_rec, rec.size() * sizeof(int4)));
+		SRB_CUDA(cudaMemcpy(s.d_cta_rec, rec.data(), rec.size() * sizeof(int4), cudaMemcpyHostToDevice));
+	}
 	SRB_CUDA(cudaMemcpyAsync(s.d_smp_off, smp_off, nu * sizeof(long long), cudaMemcpyHostToDevice, st));
 	SRB_CUDA(cudaMemcpyAsync(s.d_cta_start, cta_start.data(), nu * sizeof(int), cudaMemcpyHostToDevice, st));
 	SRB_CUDA(cudaMemcpyAsync(s.d_frame_off, frame_off.data(), nu * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -735,6 +745,7 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.partials = s->d_partials;
 	a.tw1 = p->d_tw1;
 	a.twA = p->d_twA;
+	a.cta_rec = s->d_cta_rec;
 	a.mel_desc = p->d_mel_desc;
 	a.mel_seg = p->d_mel_seg;
 	a.mel_w16 = p->d_mel_w16;
