@@ -405,7 +405,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 				{
 					// four entries per step (the host pads every group's list to a multiple of four with null entries): all loads
 					// of a step are issued before its first scratch store -- entries, features and scratch share the shared-memory
-					// address space, so the compiler cannot move a load above a store on its own
+					// address space, so the compiler cannot move a load above a store on its own.  Tried and rejected (B200, C2):
+					// a dedicated "park" warp per lane quarter doing all four groups one block ahead (8.0 ms vs 6.9: one warp cannot
+					// issue 48 dependent entry updates per block in time) and prefetching step i+1 before the stores of step i (7.4 ms).
 					const int4 *e = hl + 2 + e0;
 					const int n = e1 - e0;
 					float csum = 0.f;
