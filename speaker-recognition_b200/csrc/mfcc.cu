@@ -50,7 +50,6 @@ struct MfccPlan {
 	// fast path (M == 1024, frame length <= 512): register-resident 4 x 256-point transforms
 	bool fast = false;
 	cpx *d_tw1 = nullptr, *d_twA = nullptr;
-	int4 *d_mel_desc = nullptr;
 	int2 *d_mel_seg = nullptr;       // 16-bin segments of the bands' runs: {first bin, band}; weights d_mel_w16[seg][16]
 	float *d_mel_w16 = nullptr;
 	int *d_mel_segptr = nullptr;     // [nb + 1] first segment of every band
@@ -76,7 +75,6 @@ struct MfccArgs {
 	double *partials;
 	const cpx *tw1, *twA;      // fast path tables
 	const int4 *cta_rec;       // fast path: per CTA {first sample (lo, hi), first frame row in ceps, frame count}
-	const int4 *mel_desc;      // fast path: per band, by descending non-zero count: {band, first nz, count, first bin}
 	const int2 *mel_seg;       // fast path: 16-bin segments {first bin, band}, weights mel_w16[seg][16] (zero outside the band's run)
 	const float *mel_w16;
 	const int *mel_segptr;
@@ -505,14 +503,6 @@ static int build_tables(MfccPlan *p) {
 				tw1[(r - 1) * 256 + n] = cpx{(float)cos(-2.0 * M_PI * n * r / 1024), (float)sin(-2.0 * M_PI * n * r / 1024)};
 		for (int q2 = 0; q2 < 16; ++q2)
 			for (int u = 0; u < 16; ++u) twA[q2 * 16 + u] = cpx{(float)cos(-2.0 * M_PI * u * q2 / 256), (float)sin(-2.0 * M_PI * u * q2 / 256)};
-		std::vector<int> order(nb);
-		for (int b = 0; b < nb; ++b) order[b] = b;
-		std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return (ptr[a + 1] - ptr[a]) > (ptr[b2 + 1] - ptr[b2]); });
-		std::vector<int4> desc(nb);
-		for (int rk = 0; rk < nb; ++rk) {
-			const int b = order[rk], n = ptr[b + 1] - ptr[b];
-			desc[rk] = make_int4(b, ptr[b], n, n > 0 ? col[ptr[b]] : 0);
-		}
 		// 16-bin segments of the runs (see the mel stage of mfcc_frames_fast_kernel)
 		std::vector<int2> seg;
 		std::vector<float> w16;
@@ -536,7 +526,7 @@ static int build_tables(MfccPlan *p) {
 		}
 		p->n_seg = (int)seg.size();
 		if (p->n_seg > 384 || p->n_seg == 0) p->fast = false;   // the segment sums share a 1.5 K-float shared-memory region
-		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_desc, desc) || to_device(&p->d_mel_seg, seg) ||
+		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_seg, seg) ||
 		    to_device(&p->d_mel_w16, w16) || to_device(&p->d_mel_segptr, segptr))
 			return 1;
 	}
@@ -628,7 +618,6 @@ void mfcc_plan_free(MfccPlan *p) {
 	cudaFree(p->d_win2_d);
 	cudaFree(p->d_tw1);
 	cudaFree(p->d_twA);
-	cudaFree(p->d_mel_desc);
 	cudaFree(p->d_mel_seg);
 	cudaFree(p->d_mel_w16);
 	cudaFree(p->d_mel_segptr);
@@ -746,7 +735,6 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.tw1 = p->d_tw1;
 	a.twA = p->d_twA;
 	a.cta_rec = s->d_cta_rec;
-	a.mel_desc = p->d_mel_desc;
 	a.mel_seg = p->d_mel_seg;
 	a.mel_w16 = p->d_mel_w16;
 	a.mel_segptr = p->d_mel_segptr;

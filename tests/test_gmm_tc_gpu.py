@@ -101,3 +101,52 @@ def test_tc_route_full_size_config2(tc_route):
     for i in (0, 37, 99):
         ex = gmm_ref.score_all(W[i], M[i], Sg[i], X[:1000], gmm_ref.MODE_LOGDOMAIN)
         assert abs(gs.gmms[i].score_all(X[:1000]) - ex) < 2e-5 * abs(ex)
+
+
+def test_tc_route_limits_and_fallbacks(tc_route):
+    """the shapes the tensor route cannot take fall back to the FMA kernel (and say so); the largest one it can take works"""
+    L = tc_route
+    rng = np.random.default_rng(5)
+    for D, K, expect in [(63, 40, 1), (64, 40, 0), (100, 16, 0)]:         # Kp = 8*ceil((2D+1)/8) must fit 128 TMEM columns twice
+        W, M, Sg = synth.models(2, K, D, seed0=900 + D)
+        gs = GMMSet(gmm_order=K)
+        for i in range(2):
+            gs.gmms.append(GMM(K).set_params(W[i], M[i], Sg[i]))
+            gs.y.append(i)
+        X = synth.draw(W[1], M[1], Sg[1], 300, seed=D)
+        sums = np.array(gs.predict_one_scores(X))
+        assert L.srb200_last_score_route() == expect
+        for i in range(2):
+            ex = gmm_ref.score(W[i], M[i], Sg[i], X, gmm_ref.MODE_LOGDOMAIN).sum()
+            assert abs(sums[i] - ex) < 2e-5 * abs(ex)
+        assert int(np.argmax(sums)) == 1
+    # every sigma tiny: far more exact add-back entries than a block's list holds -> the whole set stays on the FMA route
+    K, D = 64, 20
+    w = np.full(K, 1.0 / K)
+    m = rng.normal(size=(K, D))
+    s = np.full((K, D), 0.05)
+    g = GMM(K).set_params(w, m, s)
+    X = m[rng.integers(0, K, 200)] + 0.05 * rng.normal(size=(200, D))
+    got = g.score(X)
+    assert L.srb200_last_score_route() == 0
+    assert np.max(rel_err(got, gmm_ref.score(w, m, s, X, gmm_ref.MODE_LOGDOMAIN))) < TOL
+    # a set just under the limit: 3 hard dims in every mixture of a 64-mixture model (192 entries per 128-row block) stays on route 1
+    s2 = np.full((K, D), 0.7)
+    s2[:, :3] = 0.04
+    g2 = GMM(K).set_params(w, m, s2)
+    X2 = m[rng.integers(0, K, 300)] + s2[0] * rng.normal(size=(300, D))
+    got2 = g2.score(X2)
+    assert L.srb200_last_score_route() == 1
+    assert np.max(rel_err(got2, gmm_ref.score(w, m, s2, X2, gmm_ref.MODE_LOGDOMAIN))) < TOL
+
+
+@pytest.mark.parametrize("T", [1, 2, 127, 128, 129, 255, 256, 257])
+def test_tc_route_tile_boundaries(tc_route, T):
+    S, K, D = 3, 48, 13
+    gs, W, M, Sg = build_set(S, K, D, seed0=77)
+    X = synth.draw(W[0], M[0], Sg[0], T, seed=T)
+    sums = np.array(gs.predict_one_scores(X))
+    for i in range(S):
+        ex = gmm_ref.score(W[i], M[i], Sg[i], X, gmm_ref.MODE_LOGDOMAIN)
+        assert np.max(rel_err(gs.gmms[i].score(X), ex)) < TOL
+        assert abs(sums[i] - ex.sum()) < 2e-5 * abs(ex.sum())
