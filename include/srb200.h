@@ -76,7 +76,7 @@ int srb200_get_compat_clamp(void);
  * expanded-square GEMM form, with the (mixture, dim) entries whose sigma < 0.1 added back exactly in fp32: <= 3e-5 relative
  * per frame against float64 on sigma-floor models (tests/test_gmm_tc_gpu.py), inside the 1e-4 parity bound, identical
  * argmax.  0: fp32 FMA kernel, 2e-7 relative per frame, about 3x slower.  -1 (default): route 1 wherever the model set
- * supports it (D <= 63, few tiny-sigma entries) unless the environment variable SRB200_SCORE_TC=0; the per-frame log2
+ * supports it (D <= 55, few tiny-sigma entries) unless the environment variable SRB200_SCORE_TC=0; the per-frame log2
  * output of the EM E-step always uses route 0.  srb200_last_score_route() tells which route the last launch took. */
 int srb200_set_score_path(int path);
 int srb200_get_score_path(void);

@@ -454,7 +454,7 @@ int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *ut
 		g_score_attr_set = true;
 	}
 	// ---- arithmetic route: tcgen05 3xTF32 (default where the model set supports it) or fp32 FMA (per-frame log2 output for
-	// the EM E-step, D > 63, too many tiny-sigma entries, or on request) ----
+	// the EM E-step, D > 55, too many tiny-sigma entries, or on request) ----
 	int path = c.score_path;
 	if (path < 0) {
 		const char *et = getenv("SRB200_SCORE_TC");

@@ -6,15 +6,22 @@ namespace srb {
 
 static bool g_tc_attr = false;
 
-size_t tc_smem_bytes(int Kp, int D) {
+static size_t tc_smem_bytes_n(int Kp, int D, int nst) {
 	// B part stages + hard-entry ring + add-back scratch [16][32][32] + merge buffer [3][128] float2 + mbarriers / TMEM slot word
 	// (256 B) + raw feature tile [128][D|1]
-	return (size_t)TC_BSTAGES * TC_NB * Kp * sizeof(float) + (size_t)TC_HSTAGES * TC_HSTRIDE * 16 + 16 * 32 * 32 * sizeof(float) + 3 * TC_M * 8 + 256 +
+	return (size_t)nst * TC_NB * Kp * sizeof(float) + (size_t)TC_HSTAGES * TC_HSTRIDE * 16 + 16 * 32 * 32 * sizeof(float) + 3 * TC_M * 8 + 256 +
 	       (size_t)TC_M * tc_x_stride(D) * sizeof(float);
 }
 
+// B ring depth that fits: 3 stages up to Kp = 80 (D <= 39), 2 stages up to Kp = 120 (D <= 59); 0 = the shape stays on the FMA route
+static int tc_stages(int Kp, int D) {
+	for (int nst = TC_BSTAGES; nst >= 2; --nst)
+		if (tc_smem_bytes_n(Kp, D, nst) <= 227 * 1024) return nst;
+	return 0;
+}
+
 bool tc_supported(const PackedModels &pm, int D) {
-	return !pm.h_tc.empty() && pm.tc_Kp == ((2 * D + 1 + 7) / 8) * 8 && pm.tc_Kp <= TC_KP_MAX && tc_smem_bytes(pm.tc_Kp, D) <= 227 * 1024;
+	return !pm.h_tc.empty() && pm.tc_Kp == ((2 * D + 1 + 7) / 8) * 8 && pm.tc_Kp <= TC_KP_MAX && tc_stages(pm.tc_Kp, D) > 0;
 }
 
 // d_ftiles: frame tiles of TC_M frames (device), d_partial: [n_ftiles][S][4] doubles
@@ -65,10 +72,11 @@ int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4
 	a.clamp = clamp;
 	a.frame_log2 = frame_log2;
 	a.D = D;
+	a.bstages = tc_stages(Kp, D);
 	a.hard = reinterpret_cast<const int4 *>(pm.d_tc_hard);
 	const long long units = (long long)n_ftiles * n_chunks;
 	const int grid = (int)std::min<long long>(units, c.sm_count);
-	const size_t smem = tc_smem_bytes(Kp, D);
+	const size_t smem = tc_smem_bytes_n(Kp, D, a.bstages);
 	switch (Kp / 8) {      // D = 13 -> 4, D = 28 (MFCC + LPC) -> 8, D = 39 -> 10
 		case 4: gmm_score_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(a); break;
 		case 8: gmm_score_tc_kernel<8><<<grid, TC_THREADS, smem, st>>>(a); break;

@@ -53,6 +53,7 @@ struct TcArgs {
 	double *partial;           // [n_ftiles][S][4]
 	int clamp, frame_log2;
 	int D;
+	int bstages;               // B ring depth (TC_BSTAGES, or 2 when three stages do not fit in shared memory)
 	const int4 *hard;          // [n_blocks_total][TC_HSTRIDE]: header 0 = bit masks of the columns with entries in the four
 	                           // 32-column groups, header 1 = {first entry of group 1, of group 2, of group 3, total}; entries sorted
 	                           // by column, every group padded to a multiple of 4 with null entries: {4 * dim, float bits of a, of nb,
@@ -179,7 +180,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 	const uint32_t b_part_bytes = (uint32_t)TC_NB * Kp * 4;
 	const size_t b_part_floats = (size_t)TC_NB * Kp;
 	float *sB = reinterpret_cast<float *>(tc_smem);                                  // [stages] one part (hi or lo) each
-	int4 *hring = reinterpret_cast<int4 *>(sB + TC_BSTAGES * b_part_floats);         // [TC_HSTAGES][TC_HSTRIDE] hard-entry lists
+	const int NST = A.bstages;                                                       // 3, or 2 when Kp > 80 (shared-memory budget)
+	int4 *hring = reinterpret_cast<int4 *>(sB + NST * b_part_floats);         // [TC_HSTAGES][TC_HSTRIDE] hard-entry lists
 	float *scr = reinterpret_cast<float *>(hring + TC_HSTAGES * TC_HSTRIDE);         // [16 warps][32 columns][32 lanes] add-back sums
 	float2 *ms_x = reinterpret_cast<float2 *>(scr + 16 * 32 * 32);                   // [3][128] (m, s) handed to the merging warp
 	uint64_t *bars = reinterpret_cast<uint64_t *>(ms_x + 3 * TC_M);
@@ -223,7 +225,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 	if (warp == 0) {
 		// ======================= producer =======================
 		if (lane == 0) {
-			uint32_t it_p = 0, it_h = 0;
+			uint32_t it_h = 0, ph_b = 0;
+			int st_b = 0;
 			for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
 				const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
 				const int blk0 = chunk * blocks_per_chunk_full;
@@ -238,11 +241,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 					// the block's hi image, then its lo image: one stage each, contiguous in HBM
 					const float *src = A.B + (size_t)b * tc_b_block_floats(Kp);
 #pragma unroll 1
-					for (int p = 0; p < 2; ++p, ++it_p, src += b_part_floats) {
-						const int st = it_p % TC_BSTAGES;
-						tc::wait(&empty_b[st], ((it_p / TC_BSTAGES) & 1) ^ 1);
-						mbar_expect_tx(&full_b[st], b_part_bytes);
-						bulk_g2s(sB + (size_t)st * b_part_floats, src, b_part_bytes, &full_b[st]);
+					for (int p = 0; p < 2; ++p, src += b_part_floats) {
+						tc::wait(&empty_b[st_b], ph_b ^ 1);
+						mbar_expect_tx(&full_b[st_b], b_part_bytes);
+						bulk_g2s(sB + (size_t)st_b * b_part_floats, src, b_part_bytes, &full_b[st_b]);
+						if (++st_b == NST) {
+							st_b = 0;
+							ph_b ^= 1;
+						}
 					}
 				}
 			}
@@ -258,7 +264,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 			constexpr uint32_t stepB = (2 * lbo_b) >> 4;
 			const int ksteps = KSTEPS > 0 ? KSTEPS : Kp / 8;
 			const uint32_t a_hi = tmem_base + TC_A_COL, a_lo = a_hi + (uint32_t)Kp;
-			uint32_t it_p = 0, it_a = 0, it_s = 0;
+			uint32_t ph_b = 0, it_a = 0, it_s = 0;
+			int st_b = 0;
 			for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it_a) {
 				const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
 				const int blk0 = chunk * blocks_per_chunk_full;
@@ -272,8 +279,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 					const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TC_NB);
 					// 3xTF32: (A_hi + A_lo) * B_hi from the first stage, A_hi * B_lo from the second
 					{
-						const int st = it_p % TC_BSTAGES;
-						tc::wait(&full_b[st], (it_p / TC_BSTAGES) & 1);
+						const int st = st_b;
+						tc::wait(&full_b[st], ph_b);
 						tc::fence_after();
 						const uint32_t dB0 = ((smem_u32(sB + (size_t)st * b_part_floats) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
 						tc::mma_tf32_ts<0>(d_tmem, a_hi, dB0, d_hi, idesc);     // first MMA of the block overwrites the slot
@@ -282,17 +289,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 #pragma unroll
 						for (int k = 0; k < ksteps; ++k) tc::mma_tf32_ts<1>(d_tmem, a_lo + 8 * k, dB0 + stepB * k, d_hi, idesc);
 						tc::commit_elect(&empty_b[st]);     // the stage may be refilled once these MMAs have read it
-						++it_p;
+						if (++st_b == NST) {
+							st_b = 0;
+							ph_b ^= 1;
+						}
 					}
 					{
-						const int st = it_p % TC_BSTAGES;
-						tc::wait(&full_b[st], (it_p / TC_BSTAGES) & 1);
+						const int st = st_b;
+						tc::wait(&full_b[st], ph_b);
 						tc::fence_after();
 						const uint32_t dB0 = ((smem_u32(sB + (size_t)st * b_part_floats) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
 #pragma unroll
 						for (int k = 0; k < ksteps; ++k) tc::mma_tf32_ts<1>(d_tmem, a_hi + 8 * k, dB0 + stepB * k, d_hi, idesc);
 						tc::commit_elect(&empty_b[st]);
-						++it_p;
+						if (++st_b == NST) {
+							st_b = 0;
+							ph_b ^= 1;
+						}
 					}
 					tc::commit_elect(&tm_full[slot]);       // the accumulator slot is complete
 				}

@@ -10,7 +10,8 @@ constexpr int TC_NB = 128;           // mixture rows per B block / accumulator s
                                      // an M=128 tf32 MMA costs >= 60 cycles whatever N <= 64 is, N = 128 runs at the 64-cycle peak)
 constexpr int TC_SLOTS = 2;          // TMEM accumulator slots: columns [0, 256)
 constexpr int TC_A_COL = 256;        // TMEM columns [256, 256 + Kp): PHI hi (tf32), [256 + Kp, 256 + 2 Kp): PHI lo
-constexpr int TC_KP_MAX = 128;       // so that both halves of PHI fit in the 512 TMEM columns (D <= 63)
+constexpr int TC_KP_MAX = 128;       // so that both halves of PHI fit in the 512 TMEM columns; shared memory is the tighter limit
+                                     // (gmm_score_tc.cu tc_stages: 3 B stages up to Kp = 80 / D = 39, 2 stages up to Kp = 112 / D = 55)
 constexpr int TC_BSTAGES = 3;        // ring of B PART stages: a stage holds the hi or the lo image of one block (128 x Kp floats)
 constexpr int TC_HSTAGES = 4;        // ring of per-block hard-entry lists
 constexpr int TC_THREADS = 576;      // producer warp, MMA warp, 16 epilogue warps (four per TMEM lane quarter: 32-column groups)

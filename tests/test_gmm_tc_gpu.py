@@ -107,7 +107,7 @@ def test_tc_route_limits_and_fallbacks(tc_route):
     """the shapes the tensor route cannot take fall back to the FMA kernel (and say so); the largest one it can take works"""
     L = tc_route
     rng = np.random.default_rng(5)
-    for D, K, expect in [(63, 40, 1), (64, 40, 0), (100, 16, 0)]:         # Kp = 8*ceil((2D+1)/8) must fit 128 TMEM columns twice
+    for D, K, expect in [(40, 40, 1), (55, 40, 1), (56, 40, 0), (100, 16, 0)]:   # shared-memory budget: 3 B stages to D = 39, 2 to D = 55
         W, M, Sg = synth.models(2, K, D, seed0=900 + D)
         gs = GMMSet(gmm_order=K)
         for i in range(2):
