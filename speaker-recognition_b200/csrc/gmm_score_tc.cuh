@@ -130,14 +130,29 @@ __device__ __forceinline__ void tc_lse_update(const float *v, float &m_run, floa
 		for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
 	const float mx = t[0];
 	const float m_new = fmaxf(m_run, mx);
-	float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+	// packed fp32x2 adds (SASS FADD2): the 32 subtractions and the 32 sum updates cost 16 instructions each
+	const float nm = -m_new;
+	unsigned long long nm2, acc01 = 0ull, acc23 = 0ull;
+	asm("mov.b64 %0, {%1, %1};" : "=l"(nm2) : "f"(nm));
 #pragma unroll
 	for (int i = 0; i < 32; i += 4) {
-		s0 += ex2_approx(v[i] - m_new);
-		s1 += ex2_approx(v[i + 1] - m_new);
-		s2 += ex2_approx(v[i + 2] - m_new);
-		s3 += ex2_approx(v[i + 3] - m_new);
+		unsigned long long p01, p23, d01, d23;
+		asm("mov.b64 %0, {%1, %2};" : "=l"(p01) : "f"(v[i]), "f"(v[i + 1]));
+		asm("mov.b64 %0, {%1, %2};" : "=l"(p23) : "f"(v[i + 2]), "f"(v[i + 3]));
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(p01), "l"(nm2));
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(p23), "l"(nm2));
+		float a, b, c, d;
+		asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(d01));
+		asm("mov.b64 {%0, %1}, %2;" : "=f"(c), "=f"(d) : "l"(d23));
+		unsigned long long e01, e23;
+		asm("mov.b64 %0, {%1, %2};" : "=l"(e01) : "f"(ex2_approx(a)), "f"(ex2_approx(b)));
+		asm("mov.b64 %0, {%1, %2};" : "=l"(e23) : "f"(ex2_approx(c)), "f"(ex2_approx(d)));
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc01) : "l"(acc01), "l"(e01));
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc23) : "l"(acc23), "l"(e23));
 	}
+	float s0, s1, s2, s3;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(acc01));
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(s2), "=f"(s3) : "l"(acc23));
 	s_run = fmaf(s_run, ex2_approx(m_run - m_new), (s0 + s1) + (s2 + s3));
 	m_run = m_new;
 }

@@ -45,7 +45,7 @@ struct MfccPlan {
 	float *d_win = nullptr, *d_win2 = nullptr, *d_mel_val = nullptr, *d_logfloor = nullptr;
 	cpx *d_tw = nullptr, *d_tw2 = nullptr;
 	int *d_mel_ptr = nullptr, *d_mel_col = nullptr;
-	double *d_dct = nullptr;
+	double *d_dct = nullptr, *d_dct_t = nullptr;
 	double *d_win_d = nullptr, *d_win2_d = nullptr;   // float64 window / pre-emphasised window (LPC path)
 	// fast path (M == 1024, frame length <= 512): register-resident 4 x 256-point transforms
 	bool fast = false;
@@ -71,6 +71,7 @@ struct MfccArgs {
 	const int *mel_ptr, *mel_col;
 	const float *mel_val, *logfloor;
 	const double *dct;
+	const double *dct_t;       // fast path: transposed [nb][16] (coefficients beyond nc are zero)
 	float *ceps;
 	double *partials;
 	const cpx *tw1, *twA;      // fast path tables
@@ -307,27 +308,21 @@ __global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const M
 		}
 	}
 	__syncthreads();
-	// DCT rows 1..n_ceps, float64 accumulate; each dot product is split over 4 lanes (fixed order -> deterministic)
+	// DCT rows 1..n_ceps, float64 accumulate.  One warp per frame: lane = (band parity, coefficient), the table is stored
+	// transposed [band][16 coefficients] so that a request reads two contiguous 128-byte rows (the row-major table cost
+	// eight 32-byte sectors per request: a fifth of the kernel's L1 wavefronts); the two parities are added by one shuffle
+	// (fixed order -> deterministic).
 	float *cep = logE + MFF_NF * nb;                                             // [NF][nc]
-	{
-		const int q4 = tid & 3, t4 = tid >> 2;
-		const int outs = MFF_NF * nc;
-		for (int base = 0; base < outs; base += MF_THREADS / 4) {
-			const int t = base + t4;
-			const bool valid = t < outs;
-			const int ff = valid ? t / nc : 0, i = valid ? t - ff * nc : 0;
-			const double *dr = A.dct + (size_t)i * nb;
-			const float *le = logE + ff * nb;
-			double acc = 0.0;
-			if (valid)
-				for (int b = q4; b < nb; b += 4) acc = fma(__ldg(dr + b), (double)le[b], acc);
-			acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-			acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-			if (valid && q4 == 0) {
-				const float c = (float)acc;
-				cep[t] = c;
-				if (ff < nfr) A.ceps[(size_t)(row0 + ff) * A.CL + i] = c;
-			}
+	if (tid < MFF_NF * 32) {
+		const int ff = tid >> 5, h = (tid >> 4) & 1, i = tid & 15;
+		const float *le = logE + ff * nb;
+		double acc = 0.0;
+		for (int b2 = h; b2 < nb; b2 += 2) acc = fma(__ldg(A.dct_t + b2 * 16 + i), (double)le[b2], acc);
+		acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+		if (h == 0 && i < nc) {
+			const float c = (float)acc;
+			cep[ff * nc + i] = c;
+			if (ff < nfr) A.ceps[(size_t)(row0 + ff) * A.CL + i] = c;
 		}
 	}
 	for (int t = tid; t < MFF_NF * (A.CL - nc); t += MF_THREADS) {
@@ -488,6 +483,12 @@ static int build_tables(MfccPlan *p) {
 	std::vector<double> dct((size_t)nc * nb);
 	for (int i = 0; i < nc; ++i)
 		for (int b = 0; b < nb; ++b) dct[(size_t)i * nb + b] = sqrt(2.0 / nb) * cos(M_PI * (2 * b + 1) * (i + 1) / (2.0 * nb));
+	std::vector<double> dct_t((size_t)nb * 16, 0.0);
+	if (nc <= 16)
+		for (int i = 0; i < nc; ++i)
+			for (int b = 0; b < nb; ++b) dct_t[(size_t)b * 16 + i] = dct[(size_t)i * nb + b];
+	else p->fast = false;
+	if (to_device(&p->d_dct_t, dct_t)) return 1;
 	// twiddles
 	std::vector<cpx> tw(M), tw2(M + 1);
 	for (int j = 0; j < M; ++j) tw[j] = cpx{(float)cos(-2.0 * M_PI * j / M), (float)sin(-2.0 * M_PI * j / M)};
@@ -614,6 +615,7 @@ void mfcc_plan_free(MfccPlan *p) {
 	cudaFree(p->d_mel_ptr);
 	cudaFree(p->d_mel_col);
 	cudaFree(p->d_dct);
+	cudaFree(p->d_dct_t);
 	cudaFree(p->d_win_d);
 	cudaFree(p->d_win2_d);
 	cudaFree(p->d_tw1);
@@ -730,6 +732,7 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.mel_val = p->d_mel_val;
 	a.logfloor = p->d_logfloor;
 	a.dct = p->d_dct;
+	a.dct_t = p->d_dct_t;
 	a.ceps = s->d_ceps;
 	a.partials = s->d_partials;
 	a.tw1 = p->d_tw1;
