@@ -7,9 +7,9 @@ namespace srb {
 static bool g_tc_attr = false;
 
 static size_t tc_smem_bytes_n(int Kp, int D, int nst) {
-	// B part stages + hard-entry ring + add-back scratch [16][32][32] + merge buffer [3][128] float2 + mbarriers / TMEM slot word
+	// B part stages + hard-entry ring + add-back scratch [16][32][32] + merge buffers [2][3][128] float2 + mbarriers / TMEM slot word
 	// (256 B) + raw feature tile [128][D|1]
-	return (size_t)nst * TC_NB * Kp * sizeof(float) + (size_t)TC_HSTAGES * TC_HSTRIDE * 16 + 16 * 32 * 32 * sizeof(float) + 3 * TC_M * 8 + 256 +
+	return (size_t)nst * TC_NB * Kp * sizeof(float) + (size_t)TC_HSTAGES * TC_HSTRIDE * 16 + 16 * 32 * 32 * sizeof(float) + 2 * 3 * TC_M * 8 + 256 +
 	       (size_t)TC_M * tc_x_stride(D) * sizeof(float);
 }
 

@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 	const int NST = A.bstages;                                                       // 3, or 2 when Kp > 80 (shared-memory budget)
 	int4 *hring = reinterpret_cast<int4 *>(sB + NST * b_part_floats);         // [TC_HSTAGES][TC_HSTRIDE] hard-entry lists
 	float *scr = reinterpret_cast<float *>(hring + TC_HSTAGES * TC_HSTRIDE);         // [16 warps][32 columns][32 lanes] add-back sums
-	float2 *ms_x = reinterpret_cast<float2 *>(scr + 16 * 32 * 32);                   // [3][128] (m, s) handed to the merging warp
-	uint64_t *bars = reinterpret_cast<uint64_t *>(ms_x + 3 * TC_M);
+	float2 *ms_x = reinterpret_cast<float2 *>(scr + 16 * 32 * 32);                   // [2][3][128] (m, s) handed to the merging warp
+	uint64_t *bars = reinterpret_cast<uint64_t *>(ms_x + 2 * 3 * TC_M);
 	uint64_t *full_b = bars, *empty_b = full_b + TC_BSTAGES;
 	uint64_t *full_h = empty_b + TC_BSTAGES, *empty_h = full_h + TC_HSTAGES;
 	uint64_t *tm_full = empty_h + TC_HSTAGES, *tm_empty = tm_full + TC_SLOTS;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 		const int seg = A.seg;
 		const int cols_per_spk = (seg >= TC_NB) ? A.blocks_per_spk * TC_NB : seg;
 		const int nch = Kp >> 3;
-		uint32_t it_s = 0, it_h = 0;
+		uint32_t it_s = 0, it_h = 0, n_merge = 0;
 #define SRB_TC_QBAR() asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory")      /* the 4 warps of this lane quarter */
 		for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
 			const int tile = u / A.n_chunks, chunk = u - tile * A.n_chunks;
@@ -392,17 +392,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 				float m = m_run, sacc = s_run;
 				const bool leader = (cg & (width - 1)) == 0;
 				if (width > 1) {
-					if (!leader) ms_x[(cg - 1) * TC_M + row] = make_float2(m, sacc);
+					// double-buffered hand-over (buffer = parity of the merge count): one barrier per speaker; the buffer written
+					// now is not written again before the NEXT merge's barrier, which every reader of it has passed by then
+					float2 *buf = ms_x + (size_t)(n_merge & 1) * 3 * TC_M;
+					++n_merge;
+					if (!leader) buf[(cg - 1) * TC_M + row] = make_float2(m, sacc);
 					SRB_TC_QBAR();
 					if (leader) {
 						for (int o = 0; o < width - 1; ++o) {
-							const float2 other = ms_x[(cg + o) * TC_M + row];
+							const float2 other = buf[(cg + o) * TC_M + row];
 							const float M = fmaxf(m, other.x);
 							sacc = sacc * ex2_approx(m - M) + other.y * ex2_approx(other.x - M);
 							m = M;
 						}
 					}
-					SRB_TC_QBAR();                            // ms_x may be overwritten for the next speaker
 				}
 				if (leader && my_spk < A.S) {
 					const float l2 = m + lg2_approx(sacc);
