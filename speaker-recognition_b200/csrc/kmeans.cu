@@ -80,6 +80,67 @@ __global__ void km_assign_kernel(const float *__restrict__ X, int n, int ld, int
 	belong[i] = bj;
 }
 
+// Tiled form of the two kernels above for D <= DT: the point lives in registers as float64 (the per-use float -> double
+// conversion of the simple kernels runs on the quarter-rate conversion path and dominated them), centroids are staged 32 at a
+// time in shared memory and read as broadcasts.  Same operations in the same order -> bit-identical results.
+// fresh != 0: Lloyd assignment from DBL_MAX (belong always written); fresh == 0: running minimum over centroids [c0, c1).
+template <int DT>
+__global__ void __launch_bounds__(128) km_nearest_kernel(const float *__restrict__ X, int n, int ld, int D, const double *__restrict__ cent, int c0,
+                                                        int c1, const double *__restrict__ w, double *__restrict__ dist, int *__restrict__ belong,
+                                                        int fresh) {
+	constexpr int TJ = 32;
+	__shared__ double sc[TJ * DT];
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = i < n;
+	double xr[DT];
+#pragma unroll
+	for (int d = 0; d < DT; ++d) xr[d] = (live && d < D) ? (double)X[(size_t)i * ld + d] : 0.0;
+	double best = fresh ? DBL_MAX : (live ? dist[i] : 0.0);
+	int bj = (fresh || belong == nullptr || !live) ? 0 : belong[i];
+	const double wi = (w && live) ? w[i] : 1.0;
+	for (int j0 = c0; j0 < c1; j0 += TJ) {
+		const int nj = min(TJ, c1 - j0);
+		__syncthreads();
+		for (int t = threadIdx.x; t < nj * D; t += blockDim.x) {
+			const int j = t / D, d = t - j * D;
+			sc[j * DT + d] = cent[(size_t)(j0 + j) * D + d];
+		}
+		__syncthreads();
+		for (int j = 0; j < nj; ++j) {
+			const double *c = sc + j * DT;
+			double sacc = 0.0;
+#pragma unroll
+			for (int d = 0; d < DT; ++d) {
+				if (d < D) {
+					const double t = __dsub_rn(xr[d], c[d]);
+					sacc = __dadd_rn(sacc, __dmul_rn(t, t));
+				}
+			}
+			if (w) sacc = __dmul_rn(sacc, wi);
+			if (sacc < best) {
+				best = sacc;
+				bj = j0 + j;
+			}
+		}
+	}
+	if (live) {
+		dist[i] = best;
+		if (belong) belong[i] = bj;
+	}
+}
+
+static int launch_km_nearest(const float *X, int n, int ld, int D, const double *cent, int c0, int c1, const double *w, double *dist, int *belong,
+                             int fresh, cudaStream_t st) {
+	const int grid = (n + 127) / 128;
+	if (D <= 16) km_nearest_kernel<16><<<grid, 128, 0, st>>>(X, n, ld, D, cent, c0, c1, w, dist, belong, fresh);
+	else if (D <= 28) km_nearest_kernel<28><<<grid, 128, 0, st>>>(X, n, ld, D, cent, c0, c1, w, dist, belong, fresh);
+	else if (D <= 40) km_nearest_kernel<40><<<grid, 128, 0, st>>>(X, n, ld, D, cent, c0, c1, w, dist, belong, fresh);
+	else if (fresh) km_assign_kernel<<<grid, 128, 0, st>>>(X, n, ld, D, cent, c1, w, dist, belong);
+	else km_min_dist_kernel<<<grid, 128, 0, st>>>(X, n, ld, D, cent, c0, c1, w, dist, belong);
+	SRB_CUDA(cudaGetLastError());
+	return 0;
+}
+
 // deterministic sum of n doubles: fixed chunk per CTA, fixed tree inside; second launch (1 CTA) sums the partials in order
 __global__ void km_sum_kernel(const double *__restrict__ v, long long n, double *__restrict__ out) {
 	__shared__ double sh[256];
@@ -216,8 +277,7 @@ int km_lloyd(const float *dX, int n, int ld, int D, int K, const double *d_w, Km
 	double best = DBL_MAX, last = DBL_MAX;
 	int it = 0;
 	for (; it < 200; ++it) {
-		km_assign_kernel<<<(n + 127) / 128, 128, 0, st>>>(dX, n, ld, D, d_cent, K, d_w, W.dist.as<double>(), W.belong.as<int>());
-		SRB_CUDA(cudaGetLastError());
+		if (launch_km_nearest(dX, n, ld, D, d_cent, 0, K, d_w, W.dist.as<double>(), W.belong.as<int>(), 1, st)) return 1;
 		double cost = 0.0;
 		if (km_sum(W.dist.as<double>(), n, W, st, &cost)) return 1;
 		if (cost < best) {
@@ -295,9 +355,7 @@ int kmeans2_init_device(const float *dX, int n, int ld, int D, int K, uint64_t s
 	};
 	for (int round = 0;; ++round) {
 		if (upload_cand_rows(last, (int)cand.size())) return 1;
-		km_min_dist_kernel<<<(n + 127) / 128, 128, 0, st>>>(dX, n, ld, D, W.cand_d.as<double>(), last, (int)cand.size(), nullptr, W.dist.as<double>(),
-		                                                 W.belong.as<int>());
-		SRB_CUDA(cudaGetLastError());
+		if (launch_km_nearest(dX, n, ld, D, W.cand_d.as<double>(), last, (int)cand.size(), nullptr, W.dist.as<double>(), W.belong.as<int>(), 0, st)) return 1;
 		if ((double)cand.size() > size_factor * K) break;                          // kmeansII.cc:122
 		double S = 0.0;
 		if (km_sum(W.dist.as<double>(), n, W, st, &S)) return 1;
@@ -343,9 +401,7 @@ int kmeans2_init_device(const float *dX, int n, int ld, int D, int K, uint64_t s
 	};
 	if (set_centroid(0, pick[0])) return 1;
 	for (int k = 1; k < K; ++k) {
-		km_min_dist_kernel<<<(m + 127) / 128, 128, 0, st>>>(W.cand.as<float>(), m, D, D, W.cent.as<double>(), k - 1, k, W.weight.as<double>(),
-		                                                 W.wdist.as<double>(), nullptr);
-		SRB_CUDA(cudaGetLastError());
+		if (launch_km_nearest(W.cand.as<float>(), m, D, D, W.cent.as<double>(), k - 1, k, W.weight.as<double>(), W.wdist.as<double>(), nullptr, 0, st)) return 1;
 		SRB_CUDA(cudaMemcpyAsync(h_wd.data(), W.wdist.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
 		SRB_CUDA(cudaStreamSynchronize(st));
 		double S = 0.0;
