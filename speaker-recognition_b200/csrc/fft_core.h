@@ -178,14 +178,23 @@ SRB_HD void fast_step_a(const cpx *z, const cpx *tw1, const cpx *twA, cpx *T, in
 	for (int q2 = 0; q2 < 16; ++q2) T[u * FAST_TSTRIDE + q2] = cmul(out[q2], twA[q2 * 16 + u]);
 }
 
-// step B: radix-16 over n1 of T[n1][u] -> Y_r[16 q1 + u], stored as Zr[16 q1 + u] (Zr = Zs + r * FAST_ZSTRIDE)
-SRB_HD void fast_step_b(const cpx *T, cpx *Zr, int u) {
-	cpx in[16], out[16];
+// step B: radix-16 over n1 of T[n1][u] -> Y_r[16 q1 + u], stored as Zr[16 q1 + u] (Zr = Zs + r * FAST_ZSTRIDE).
+// Split into a load and a compute/store half so that the kernel can run it IN PLACE (Zs aliasing the transpose tiles,
+// with a CTA barrier between the halves); fast_step_b is the two halves back to back for distinct buffers.
+SRB_HD void fast_step_b_load(const cpx *T, int u, cpx (&in)[16]) {
 #pragma unroll
 	for (int n1 = 0; n1 < 16; ++n1) in[n1] = T[n1 * FAST_TSTRIDE + u];
+}
+SRB_HD void fast_step_b_store(const cpx (&in)[16], cpx *Zr, int u) {
+	cpx out[16];
 	dft16(in, out);
 #pragma unroll
 	for (int q1 = 0; q1 < 16; ++q1) Zr[16 * q1 + u] = out[q1];
+}
+SRB_HD void fast_step_b(const cpx *T, cpx *Zr, int u) {
+	cpx in[16];
+	fast_step_b_load(T, u, in);
+	fast_step_b_store(in, Zr, u);
 }
 
 // one bin of the real 2048-point power spectrum from Zs[r][q] = Z[4q + r]; w = exp(-2 pi i k / 2048)

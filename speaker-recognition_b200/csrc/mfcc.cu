@@ -216,13 +216,16 @@ __global__ void __launch_bounds__(MF_THREADS) mfcc_frames_kernel(const MfccArgs 
 constexpr int MFF_NF = 4;
 constexpr int MFF_YLEN = 512;
 
-__global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const MfccArgs A) {
+__global__ void __launch_bounds__(MF_THREADS, 4) mfcc_frames_fast_kernel(const MfccArgs A) {
 	extern __shared__ __align__(16) unsigned char mf_smem[];
 	const int tid = threadIdx.x;
 	const int L = A.L, nb = A.nb, nc = A.nc;
-	cpx *T = reinterpret_cast<cpx *>(mf_smem);                                   // [NF][4][16*17]   (later P[NF][1028] floats)
-	cpx *Zs = T + MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE;                        // [NF][4][260]
-	float *ybuf = reinterpret_cast<float *>(Zs + MFF_NF * 4 * srbfft::FAST_ZSTRIDE);   // [NF][512]  (later logE / cep)
+	// Two regions, 51 KB together (4 CTAs per SM at 64 registers).  Region A: sample span -> transpose tiles T -> sub-transform
+	// outputs Zs, written IN PLACE over T after a barrier -> later the mel / log / cepstrum scratch.  Region B: windowed
+	// frames ybuf -> later the power spectrum P.
+	cpx *T = reinterpret_cast<cpx *>(mf_smem);                                   // [NF][4][16*17]
+	cpx *Zs = T;                                                                 // [NF][4][260]  (aliases T)
+	float *ybuf = reinterpret_cast<float *>(T + MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE);   // [NF][512], then P [NF][1028]
 
 	// one 16-byte record per CTA (built on the host with the shape; a binary search over the utterance table cost six
 	// dependent global loads before the first sample could be requested)
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const M
 	// overlap, so its whole sample span (plus the sample before it) is staged once in shared memory as floats: one coalesced
 	// pass, (NF-1) shift + L + 1 conversions instead of 2 NF L scattered 2-byte loads.
 	{
-		float *span = reinterpret_cast<float *>(Zs);                             // Zs is free until the second FFT step
+		float *span = reinterpret_cast<float *>(T);                              // region A is free until the first FFT step
 		const int n_span = (nfr - 1) * A.shift + L + 1;                          // span[j] = sample s0 - 1 + j
 		for (int j = tid; j < n_span; j += MF_THREADS) {
 			const long long g = s0 - 1 + j;
@@ -261,9 +264,14 @@ __global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const M
 	cpx *Tfr = T + (f * 4 + r) * 16 * srbfft::FAST_TSTRIDE;
 	srbfft::fast_step_a(reinterpret_cast<const cpx *>(ybuf + f * MFF_YLEN), A.tw1, A.twA, Tfr, r, u);
 	__syncthreads();
-	srbfft::fast_step_b(Tfr, Zs + (f * 4 + r) * srbfft::FAST_ZSTRIDE, u);
+	{
+		cpx in[16];
+		srbfft::fast_step_b_load(Tfr, u, in);
+		__syncthreads();                                                         // every tile has been read: Zs may overwrite them
+		srbfft::fast_step_b_store(in, Zs + (f * 4 + r) * srbfft::FAST_ZSTRIDE, u);
+	}
 	__syncthreads();
-	float *P = reinterpret_cast<float *>(T);                                     // [NF][1028], natural bin order
+	float *P = ybuf;                                                             // [NF][1028], natural bin order (the frames are consumed)
 	constexpr int PSTR = srbfft::FAST_PSTRIDE;
 	srbfft::fast_power_unpack(Zs + f * 4 * srbfft::FAST_ZSTRIDE, P + f * PSTR, A.tw2, tid & 63);
 	__syncthreads();
@@ -273,8 +281,8 @@ __global__ void __launch_bounds__(MF_THREADS, 3) mfcc_frames_fast_kernel(const M
 	// (frame, segment) does 16 multiply-adds on consecutive P values with its weights in four 128-bit loads, all items carry
 	// the same work; then one thread per (frame, band) adds the band's segment sums in segment order (deterministic) and
 	// takes the log.  (The first version walked (frame, band) items with 8-lane groups: 25 instructions per multiply-add.)
-	float *logE = ybuf;                                                          // [NF][nb]
-	float *segsum = ybuf + 512;                                                  // [NF][n_seg]  (n_seg <= 384, host-checked)
+	float *logE = reinterpret_cast<float *>(T);                                  // [NF][nb]   (region A: Zs is consumed)
+	float *segsum = logE + 512;                                                  // [NF][n_seg]  (n_seg <= 384, host-checked)
 	{
 		const int n_seg = A.n_seg, items = MFF_NF * n_seg;
 		for (int item = tid; item < items; item += MF_THREADS) {
@@ -571,8 +579,7 @@ MfccPlan *mfcc_plan_create(int fs, double win_ms, double shift_ms, int nfft, int
 		return nullptr;
 	}
 	p->smem = (size_t)2 * p->NF * p->M * sizeof(cpx) + ((size_t)(p->NF - 1) * p->shift + p->L) * sizeof(float);
-	p->smem_fast = (size_t)MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE * sizeof(cpx) + (size_t)MFF_NF * 4 * srbfft::FAST_ZSTRIDE * sizeof(cpx) +
-	               (size_t)MFF_NF * MFF_YLEN * sizeof(float);
+	p->smem_fast = (size_t)MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE * sizeof(cpx) + (size_t)MFF_NF * srbfft::FAST_PSTRIDE * sizeof(float);
 	if (p->smem > 200 * 1024 || (p->fast && p->smem_fast > 110 * 1024)) {
 		set_error("mfcc: frame shift %d too large for the shared-memory staging", p->shift);
 		delete p;
