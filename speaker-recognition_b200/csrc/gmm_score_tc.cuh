@@ -62,35 +62,6 @@ struct TcArgs {
 
 namespace tc {
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-	uint64_t d = 0;
-	d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-	d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-	d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-	d |= (uint64_t)1 << 46;      // sm_100 descriptor version; layout_type (bits 61-63) = 0: no swizzle
-	return d;
-}
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-	asm volatile(
-	    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-	    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-	    "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-	    : "memory");
-}
-// descriptor passed as (lo, hi) words: only the low word (start address field) changes between k-steps, by one 32-bit add
-template <int ACC>
-__device__ __forceinline__ void mma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
-	asm volatile(
-	    "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
-	    "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-	    "setp.ne.b32 p, %6, 0;\n\t"
-	    "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
-	    "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
-	    : "memory");
-}
-__device__ __forceinline__ void commit(uint64_t *bar) {
-	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ld32(uint32_t taddr, float *v) {
