@@ -340,7 +340,7 @@ def main():
                             "mfcc_s": t_m, "score_s": t_s, "top1_matches_gpu": bool(cpu_lab == int(labels_dev[0]))}
         line = {"metric": "mfcc_gmm_scored_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "vs_baseline": None, "dtype": "tf32x3+f32" if route == 1 else "f32", "data": "synthetic",
                 "config": {"workload": "C2", "speakers": S_SPK, "mixtures": K_MIX, "dim": DIM, "frames_per_utt": FRAMES_OUT,
                            "utts_per_step_per_gpu": B, "parallelism": "utterance-sharded x%d" % world,
                            "l2_policy": "inputs larger than L2 (%.0f MB PCM per step per GPU vs %d MB L2)" % (B * UTT_SAMPLES * 2 / 1e6, L2_BYTES >> 20)},
