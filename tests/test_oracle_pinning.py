@@ -197,3 +197,20 @@ def test_kmeans_uniform_stream_is_a_fixed_function():
     u = kmeans_ref.uniform(1234, 3, np.arange(5))
     assert np.all((u >= 0) & (u < 1)) and len(set(u.tolist())) == 5
     assert abs(float(kmeans_ref.uniform(0, 0, 0)) - 0.8833108082136426) < 1e-15      # known answer: locks the hash the product shares
+
+
+def test_gmm_oracle_brackets_sklearn_exact_exp(golden_gmm):
+    """secondary scoring oracle: sklearn's GaussianMixture(diag).score_samples with injected parameters is an
+    independent exact-exp float64 implementation; the log-domain oracle must agree with it to float64 round-off, and the
+    reference-style fast-exp scorer must sit within its documented ~1e-4 of both."""
+    sk = pytest.importorskip("sklearn.mixture")
+    c = golden_gmm.case("ubm64")
+    w, m, s, X = c["w"], c["mean"], c["sigma"], c["X"]
+    gm = sk.GaussianMixture(n_components=len(w), covariance_type="diag")
+    gm.weights_, gm.means_, gm.covariances_ = w, m, s ** 2       # raw weights (6-digit text: sum = 1 +- 5e-7); sigma is a std-dev (gmm.hh:31)
+    gm.precisions_cholesky_ = 1.0 / s
+    ref = gm.score_samples(X)
+    exact = gmm_ref.score(w, m, s, X, gmm_ref.MODE_LOGDOMAIN)
+    assert np.max(np.abs(exact - ref) / np.maximum(1, np.abs(ref))) < 1e-9
+    fast = gmm_ref.score(w, m, s, X, gmm_ref.MODE_FASTEXP)
+    assert np.max(np.abs(fast - ref) / np.maximum(1, np.abs(ref))) < 5e-4
