@@ -72,15 +72,18 @@ int srb200_get_device(void);
 int srb200_set_compat_clamp(int mode);
 int srb200_get_compat_clamp(void);
 
-/* scoring arithmetic route.  1: tensor-core kernel (tcgen05 kind::tf32 as 3xTF32, fp32 accumulation in tensor memory) on the
- * expanded-square GEMM form, with the (mixture, dim) entries whose sigma < 0.1 added back exactly in fp32: <= 3e-5 relative
- * per frame against float64 on sigma-floor models (tests/test_gmm_tc_gpu.py), inside the 1e-4 parity bound, identical
- * argmax.  0: fp32 FMA kernel, 2e-7 relative per frame, about 3x slower.  -1 (default): route 1 wherever the model set
- * supports it (D <= 55, few tiny-sigma entries) unless the environment variable SRB200_SCORE_TC=0; the per-frame log2
- * output of the EM E-step always uses route 0.  srb200_last_score_route() tells which route the last launch took. */
+/* scoring arithmetic route.  1: tensor-core kernel (tcgen05, fp32 accumulation in tensor memory) on the expanded-square GEMM
+ * form over centred, power-of-two-scaled features, with the few (mixture, dim) entries whose |mean - centre| / sigma would
+ * make that form cancel added back exactly in fp32: <= 5e-5 relative per frame against float64 (tests/test_gmm_tc_gpu.py),
+ * inside the 1e-4 parity bound, identical argmax.  0: fp32 FMA kernel, 2e-7 relative per frame, about 3x slower.
+ * -1 (default): route 1 wherever the model set supports it (D <= 55, add-back list within its capacity) unless the
+ * environment variable SRB200_SCORE_TC=0; the per-frame log2 output of the EM E-step always uses route 0.
+ * srb200_last_score_route() tells which route the last launch took; srb200_tc_pack_stats() (host only, no GPU needed) tells
+ * whether a model set is eligible for route 1 and how many exact add-back entries it needs (returns 1 / 0; < 0 on error). */
 int srb200_set_score_path(int path);
 int srb200_get_score_path(void);
 int srb200_last_score_route(void);
+int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int *hard_entries_out, int *max_hard_per_block_out);
 
 int srb200_gmm_set_params(GMM *gmm, int nr_mixture, int dim, const double *weights, const double *means, const double *sigmas); /* means,sigmas [K*D]; sigma = std-dev (gmm.hh:31) */
 int srb200_gmm_get_params(GMM *gmm, double *weights, double *means, double *sigmas);

@@ -86,22 +86,36 @@ int Context::init() {
 	return 0;
 }
 
-void PackedModels::release() {
-	if (d_tiles) cudaFree(d_tiles);
+void PackedModels::release_tc() {
 	if (d_tc) cudaFree(d_tc);
 	if (d_tc_hard) cudaFree(d_tc_hard);
-	d_tiles = nullptr;
+	if (d_tc_cs) cudaFree(d_tc_cs);
 	d_tc = nullptr;
 	d_tc_hard = nullptr;
+	d_tc_cs = nullptr;
 	h_tc.clear();
 	h_tc_hard.clear();
+	h_tc_cs.clear();
+	tc_built = false;
+}
+
+void PackedModels::release() {
+	if (d_tiles) cudaFree(d_tiles);
+	d_tiles = nullptr;
+	release_tc();
 	bytes = 0;
 	S = 0;
 }
 
-// Tensor-core weight images (gmm_score_tc.cuh).  Row r of speaker s holds W = [-a^2 (D), -2 a nb (D), C, 0-pad] with
-// a = sqrt(log2e/2)/sigma, nb = -mean a, C = log2 w - sum log2(sqrt(2pi) sigma) - sum nb^2; each value is split into a
-// TF32-representable hi part and the fp32 remainder lo.  Speakers are padded to 32 / 64 / multiples of 128 rows.
+// Tensor-core weight images (gmm_score_tc.cuh).  Features are transformed per dimension, x'' = (x - c_d) alpha_d, with c_d the
+// weighted mean of the set's means and alpha_d the power of two nearest to 1 / (the set's overall standard deviation in d), so
+// that the expanded square works on unit-scale, centred numbers whatever the feature's own scale is (MFCC after CMVN ~ 1, LPC
+// coefficients ~ 0.05: the shipped 34-dim UBMs).  Row r of speaker s holds W = [-a''^2 (D), -2 a'' nb'' (D), C, 0-pad] with
+// a'' = sqrt(log2e/2) / (sigma alpha), nb'' = -(mean - c) alpha a'', C = log2 w - sum log2(sqrt(2pi) sigma) - sum nb''^2; each
+// value is split into a TF32-representable hi part and the fp32 remainder lo.  The expanded form cancels where |nb''| is large
+// (error ~ eps * nb''^2 per term and the fp32 accumulator works at magnitude sum nb''^2): per row, the dimensions with the
+// largest nb''^2 are taken out of W and C until the remaining sum is below TC_HARD_BUDGET, and are added back exactly by the
+// epilogue (t = a'' x'' + nb'', l -= t^2).  Speakers are padded to 32 / 64 / multiples of 128 rows.
 void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *const *weights, const double *const *means,
                          const double *const *sigmas, const int *Ks) {
 	const int Kp = ((2 * D + 1 + 7) / 8) * 8;
@@ -110,13 +124,46 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 	const long long rows_total = (long long)S * cols;
 	const int blocks = (int)((rows_total + NB - 1) / NB);
 	const size_t bf = tc_b_block_floats(Kp);
+	pm.release_tc();
+	pm.tc_built = true;
 	pm.h_tc.assign((size_t)blocks * bf, 0.f);
 	pm.tc_Kp = Kp;
 	pm.tc_cols_per_spk = cols;
 	pm.tc_blocks_total = blocks;
 	const double A0 = 0.84932180028801904272;
-	double HARD_SIGMA = TC_HARD_SIGMA;
-	if (const char *eh = getenv("SRB200_TC_HARD_SIGMA")) HARD_SIGMA = atof(eh);   // experiments: 0 disables the add-back list
+	double BUDGET = TC_HARD_BUDGET;
+	if (const char *eh = getenv("SRB200_TC_HARD_BUDGET")) BUDGET = atof(eh);   // experiments: a huge value disables the add-back list
+	// ---- the feature transform of this set: centre and power-of-two scale per dimension ----
+	std::vector<double> cen(D, 0.0), spread(D, 0.0), alpha(D, 1.0);
+	{
+		double wsum = 0.0;
+		for (int s = 0; s < S; ++s)
+			for (int k = 0; k < Ks[s]; ++k) {
+				const double w = weights[s][k] > 0.0 ? weights[s][k] : 0.0;
+				wsum += w;
+				for (int d = 0; d < D; ++d) cen[d] += w * means[s][(size_t)k * D + d];
+			}
+		if (!(wsum > 0.0)) wsum = 1.0;
+		for (int d = 0; d < D; ++d) cen[d] /= wsum;
+		for (int s = 0; s < S; ++s)
+			for (int k = 0; k < Ks[s]; ++k) {
+				const double w = weights[s][k] > 0.0 ? weights[s][k] : 0.0;
+				for (int d = 0; d < D; ++d) {
+					const double dm = means[s][(size_t)k * D + d] - cen[d], sg = sigmas[s][(size_t)k * D + d];
+					spread[d] += w * (dm * dm + sg * sg);
+				}
+			}
+		pm.h_tc_cs.assign((size_t)2 * D, 0.f);
+		for (int d = 0; d < D; ++d) {
+			const double sd = sqrt(spread[d] / wsum);
+			int e = (sd > 0.0 && sd == sd) ? (int)lround(-log2(sd)) : 0;
+			e = std::max(-60, std::min(60, e));
+			alpha[d] = ldexp(1.0, e);
+			cen[d] = (double)(float)cen[d];            // the kernel subtracts the fp32 value: use exactly that one here
+			pm.h_tc_cs[d] = (float)cen[d];
+			pm.h_tc_cs[D + d] = (float)alpha[d];
+		}
+	}
 	// hard-entry lists (layout: TcArgs::hard).  Rows ascend, so each group's list is sorted by column.
 	pm.h_tc_hard.assign((size_t)blocks * 4 * TC_HSTRIDE, 0);
 	struct HardEntry { int x; float a, nb; int w; };
@@ -135,25 +182,42 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 		pm.h_tc[(size_t)blk * bf + off] = hi;
 		pm.h_tc[(size_t)blk * bf + (size_t)NB * Kp + off] = lo;
 	};
+	std::vector<double> av(D), nbv(D);
+	std::vector<int> order(D);
+	std::vector<char> is_hard(D);
 	for (long long row = 0; row < (long long)blocks * NB; ++row) {
 		const int s = (int)(row / cols), k = (int)(row % cols);
 		const int blk = (int)(row / NB), col = (int)(row % NB);
 		if (s < S && k < Ks[s]) {
 			const double *mu = means[s] + (size_t)k * D, *sg = sigmas[s] + (size_t)k * D;
 			double C = weights[s][k] > 0.0 ? log2(weights[s][k]) : -1.0e30;
+			double tot = 0.0;
+			for (int d = 0; d < D; ++d) {
+				av[d] = A0 / (sg[d] * alpha[d]);
+				nbv[d] = -(mu[d] - cen[d]) * alpha[d] * av[d];
+				C -= log2(2.5066282746310002 * sg[d]);
+				tot += nbv[d] * nbv[d];
+				order[d] = d;
+				is_hard[d] = 0;
+			}
+			if (tot > BUDGET) {
+				std::sort(order.begin(), order.end(), [&](int x, int y) { return nbv[x] * nbv[x] > nbv[y] * nbv[y]; });
+				for (int i = 0; i < D && tot > BUDGET; ++i) {
+					is_hard[order[i]] = 1;
+					tot -= nbv[order[i]] * nbv[order[i]];
+				}
+			}
 			std::vector<HardEntry> &g = groups[(size_t)blk * 4 + (col >> 5)];
 			bool any = false;
 			for (int d = 0; d < D; ++d) {
-				const double a = A0 / sg[d], nb = -mu[d] * a;
-				C -= log2(2.5066282746310002 * sg[d]);
-				if (sg[d] < HARD_SIGMA) {
-					// kept out of the GEMM (its three ~1e3 terms would cancel): exact add-back entry for the epilogue
-					g.push_back({4 * d, (float)a, (float)nb, 0});
+				if (is_hard[d]) {
+					// kept out of the GEMM (its three large terms would cancel): exact add-back entry for the epilogue
+					g.push_back({4 * d, (float)av[d], (float)nbv[d], 0});
 					any = true;
 				} else {
-					put(row, d, -a * a);
-					put(row, D + d, -2.0 * a * nb);
-					C -= nb * nb;
+					put(row, d, -av[d] * av[d]);
+					put(row, D + d, -2.0 * av[d] * nbv[d]);
+					C -= nbv[d] * nbv[d];
 				}
 			}
 			if (any) g.back().w = 1 + 128 * (col & 31);      // last entry of this column: flush the sum to scratch column col & 31
@@ -186,9 +250,10 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 		}
 		hdr[7] = pos;
 	}
-	if (overflow) {      // too many tiny-sigma entries for the sparse list: this model set stays on the FMA route
+	if (overflow) {      // too many cancelling entries for the sparse list: this model set stays on the FMA route
 		pm.h_tc.clear();
 		pm.h_tc_hard.clear();
+		pm.h_tc_cs.clear();
 	}
 }
 
@@ -246,6 +311,7 @@ int gmm_pull_device_master(GMM *g) {
 	if (!g->host_stale) return 0;
 	const int K = g->nr_mixtures, D = g->dim;
 	std::vector<double> buf((size_t)K + 2 * (size_t)K * D);
+	SRB_CUDA(cudaDeviceSynchronize());      // the M-step that wrote the master may have run on any (non-blocking) caller stream
 	SRB_CUDA(cudaMemcpy(buf.data(), g->d_params, buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
 	g->weights.assign(buf.begin(), buf.begin() + K);
 	g->means.assign(buf.begin() + K, buf.begin() + K + (size_t)K * D);
@@ -277,20 +343,21 @@ int gmm_ensure_device_master(GMM *g) {
 }
 
 int gmm_ensure_packed(GMM *g) {
-	if (g->packed_valid) return 0;
+	if (g->packed_valid && g->packed.tc_built) return 0;
 	if (gmm_pull_device_master(g)) return 1;
 	const int K = g->nr_mixtures, D = g->dim;
 	SRB_REQUIRE(K > 0 && D > 0 && (int)g->weights.size() == K && (int)g->means.size() == K * D, "gmm: model has no parameters (train, load or set_params first)");
 	SRB_REQUIRE(D <= MAX_DIM, "gmm: dim %d > %d unsupported", D, MAX_DIM);
-	std::vector<float> host;
-	int Kpad = 0;
 	const double *w = g->weights.data(), *m = g->means.data(), *s = g->sigmas.data();
-	pack_models_host(1, K, D, &w, &m, &s, &K, host, &Kpad);
-	if (upload_packed(g->packed, 1, K, D, host, Kpad, ctx().stream)) return 1;
-	if (g->packed.d_tc) {
-		cudaFree(g->packed.d_tc);
-		g->packed.d_tc = nullptr;
+	if (!g->packed_valid) {
+		std::vector<float> host;
+		int Kpad = 0;
+		pack_models_host(1, K, D, &w, &m, &s, &K, host, &Kpad);
+		if (upload_packed(g->packed, 1, K, D, host, Kpad, ctx().stream)) return 1;
 	}
+	// the tensor-core images are (re)built whenever the FMA tiles were repacked -- from the host here, or from the device
+	// master by the training loop (launch_pack_from_master drops them: a model scored, then trained, must not be scored with
+	// the images of its old parameters)
 	pack_models_tc_host(g->packed, 1, K, D, &w, &m, &s, &K);
 	g->packed_valid = true;
 	return 0;
@@ -919,6 +986,49 @@ srb200_gmmset *srb200_gmmset_create(GMM *const *models, int n_models) {
 	set->D = D;
 	set->K = K;
 	return set;
+}
+
+// host-only diagnostic: would this model set take the tensor-core route, and with how many exact add-back entries?
+// (runs the packer on temporary host buffers; no device work, usable without a GPU)
+int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int *hard_out, int *max_hard_per_block_out) {
+	API_ENTER();
+	if (!models || n_models < 1) {
+		set_error("tc_pack_stats: no models");
+		return -1;
+	}
+	int K = 0, D = 0;
+	std::vector<const double *> w(n_models), m(n_models), s(n_models);
+	std::vector<int> Ks(n_models);
+	for (int i = 0; i < n_models; ++i) {
+		GMM *g = models[i];
+		if (!g || g->host_stale || (int)g->weights.size() != g->nr_mixtures || g->dim < 1 || (i > 0 && g->dim != D)) {
+			set_error("tc_pack_stats: model %d has no host parameters or a different dimension", i);
+			return -1;
+		}
+		D = g->dim;
+		K = std::max(K, g->nr_mixtures);
+		Ks[i] = g->nr_mixtures;
+		w[i] = g->weights.data();
+		m[i] = g->means.data();
+		s[i] = g->sigmas.data();
+	}
+	PackedModels pm;
+	pack_models_tc_host(pm, n_models, K, D, w.data(), m.data(), s.data(), Ks.data());
+	pm.S = n_models;
+	const bool ok = tc_supported(pm, D);
+	int hard = 0, mx = 0;
+	if (ok)
+		for (int b = 0; b < pm.tc_blocks_total; ++b) {
+			int n = 0;
+			for (int e = 0; e < pm.h_tc_hard[(size_t)b * TC_HSTRIDE * 4 + 7]; ++e)
+				n += pm.h_tc_hard[((size_t)b * TC_HSTRIDE + 2 + e) * 4 + 1] != 0;        // null padding entries have a = 0
+			hard += n;
+			mx = std::max(mx, n);
+		}
+	if (blocks_out) *blocks_out = pm.tc_blocks_total;
+	if (hard_out) *hard_out = hard;
+	if (max_hard_per_block_out) *max_hard_per_block_out = mx;
+	return ok ? 1 : 0;
 }
 
 void srb200_gmmset_free(srb200_gmmset *set) {

@@ -31,10 +31,14 @@ struct PackedModels {             // device-resident packed parameters of S mode
 	// tensor-core path (gmm_score_tc.cuh): weight images [blocks][hi|lo][128*Kp], built on the host with the FMA tiles
 	std::vector<float> h_tc;      // host image, uploaded on first use
 	std::vector<int> h_tc_hard;   // per block: 4*TC_HSTRIDE ints (two header words + hard entries), see gmm_score_tc.cuh
+	std::vector<float> h_tc_cs;   // [2][D]: per-dimension centre c_d and power-of-two scale alpha_d of the feature transform x'' = (x - c) alpha
 	float *d_tc = nullptr;
 	int *d_tc_hard = nullptr;
+	float *d_tc_cs = nullptr;
 	int tc_Kp = 0, tc_cols_per_spk = 0, tc_blocks_total = 0;
+	bool tc_built = false;        // the tensor-core images describe the CURRENT parameters (possibly empty: set not supported)
 	void release();
+	void release_tc();            // drop the tensor-core images (host and device); the FMA tiles stay
 };
 
 // host-side packing of S models (each K_s <= K rows used; others padded) into `out` (size S*tiles*tile_floats)

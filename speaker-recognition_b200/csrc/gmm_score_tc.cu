@@ -34,6 +34,8 @@ int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4
 		SRB_CUDA(cudaMemcpyAsync(pm.d_tc, pm.h_tc.data(), pm.h_tc.size() * sizeof(float), cudaMemcpyHostToDevice, st));
 		SRB_CUDA(cudaMalloc(&pm.d_tc_hard, pm.h_tc_hard.size() * sizeof(int)));
 		SRB_CUDA(cudaMemcpyAsync(pm.d_tc_hard, pm.h_tc_hard.data(), pm.h_tc_hard.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+		SRB_CUDA(cudaMalloc(&pm.d_tc_cs, pm.h_tc_cs.size() * sizeof(float)));
+		SRB_CUDA(cudaMemcpyAsync(pm.d_tc_cs, pm.h_tc_cs.data(), pm.h_tc_cs.size() * sizeof(float), cudaMemcpyHostToDevice, st));
 		SRB_CUDA(cudaStreamSynchronize(st));
 	}
 	if (!g_tc_attr) {
@@ -48,6 +50,7 @@ int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4
 	a.X = dX;
 	a.ld = ld;
 	a.B = pm.d_tc;
+	a.cs = pm.d_tc_cs;
 	a.ftiles = d_ftiles;
 	a.n_ftiles = n_ftiles;
 	a.Kp = Kp;

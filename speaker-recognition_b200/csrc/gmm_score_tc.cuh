@@ -38,6 +38,7 @@ namespace srb {
 struct TcArgs {
 	const float *X;            // [n][ld] features
 	int ld;
+	const float *cs;           // [2][D] feature transform of the model set: centre c_d, power-of-two scale alpha_d; x'' = (x - c) alpha
 	const float *B;            // [n_blocks_total][2][TC_NB*Kp] weight images (speaker-major, rows padded)
 	const int4 *ftiles;        // per frame tile: {first frame, frame count, utterance, 0}
 	int n_ftiles;
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 			SRB_TC_QBAR();
 			{
 				const float *xg = A.X + (size_t)(ft.x + (valid ? row : 0)) * A.ld;
+				const float *cen = A.cs, *alp = A.cs + D;
 				for (int c = cg; c < nch; c += 4) {
 					uint32_t hi[8], lo[8];
 #pragma unroll
@@ -333,10 +335,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 						const int k = 8 * c + j;
 						float v = 0.f;
 						if (k < D) {
-							const float x = valid ? __ldg(xg + k) : 0.f;
+							const float x = valid ? (__ldg(xg + k) - __ldg(cen + k)) * __ldg(alp + k) : 0.f;
 							v = x * x;
 						} else if (k < 2 * D) {
-							v = valid ? __ldg(xg + k - D) : 0.f;
+							v = valid ? (__ldg(xg + k - D) - __ldg(cen + k - D)) * __ldg(alp + k - D) : 0.f;
 							xrow[k - D] = v;
 						} else if (k == 2 * D) {
 							v = valid ? 1.f : 0.f;

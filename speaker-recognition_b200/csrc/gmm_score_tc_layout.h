@@ -17,7 +17,8 @@ constexpr int TC_HSTAGES = 4;        // ring of per-block hard-entry lists
 constexpr int TC_THREADS = 576;      // producer warp, MMA warp, 16 epilogue warps (four per TMEM lane quarter: 32-column groups)
 constexpr float TC_LN2 = 0.69314718055994531f;
 constexpr int TC_HSTRIDE = 2 + 204;  // int4 per block: two header words + up to 204 hard entries (incl. the x4 padding of the four groups)
-constexpr double TC_HARD_SIGMA = 0.1;   // dims with sigma below this are kept out of the GEMM and added back exactly
+constexpr double TC_HARD_BUDGET = 1000.0;   // per mixture row: sum over the dims left in the GEMM of nb''^2 (the magnitude the expanded square cancels at);
+                                            // the dims above it are added back exactly by the epilogue (api.cu pack_models_tc_host)
 
 __host__ __device__ static inline size_t tc_b_block_floats(int Kp) { return (size_t)2 * TC_NB * Kp; }  // hi | lo
 // element (row r, k) of one part (hi or lo) of a B image: no-swizzle K-major canonical layout, K-groups outermost

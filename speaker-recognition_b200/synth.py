@@ -57,3 +57,22 @@ def draw(w, mean, sigma, n, seed):
     rng = np.random.default_rng(seed)
     k = rng.choice(len(w), size=n, p=w / w.sum())
     return mean[k] + sigma[k] * rng.standard_normal((n, mean.shape[1]))
+
+
+def realparam_models(S, K, pools, seed0=5000, shift=0.25):
+    """Speakers whose parameter statistics are those of REAL trained models: every mixture of every speaker is a whole
+    (mean, sigma) row resampled from `pools` -- a list of (w, mean, sigma) of trained models sharing D, e.g. the UBMs the
+    reference ships (src/gui/model/*.model, D = 34 = MFCC 19 + LPC 15: un-normalised scales, sigma floor 0.0316 present,
+    collapsed mixtures included) -- with the mean moved by shift * sigma * N(0,1) (a MAP-adaptation-sized displacement) and
+    Dirichlet weights.  Returns (W [S,K], M [S,K,D], Sg [S,K,D])."""
+    pm = np.concatenate([np.asarray(p[1], dtype=np.float64) for p in pools])
+    ps = np.concatenate([np.asarray(p[2], dtype=np.float64) for p in pools])
+    D = pm.shape[1]
+    W, M, Sg = np.empty((S, K)), np.empty((S, K, D)), np.empty((S, K, D))
+    for s in range(S):
+        rng = np.random.default_rng(seed0 + s)
+        rows = rng.integers(0, len(pm), size=K)
+        Sg[s] = ps[rows]
+        M[s] = pm[rows] + shift * ps[rows] * rng.standard_normal((K, D))
+        W[s] = rng.dirichlet(np.ones(K))
+    return W, M, Sg

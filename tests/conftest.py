@@ -39,6 +39,23 @@ def golden_gmm():
     return _Golden(os.path.join(GOLDEN, "gmm_ref.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_real():
+    return _Golden(os.path.join(GOLDEN, "realparams_ref.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_silence():
+    return _Golden(os.path.join(GOLDEN, "silence_ref.npz"))
+
+
+def shipped_ubm_pools(golden_gmm, golden_real):
+    """(w, mean, sigma) of the four UBMs the reference ships (src/gui/model/*.model), from the committed fixtures"""
+    pools = [tuple(golden_gmm.case(t)[k] for k in ("w", "mean", "sigma")) for t in ("ubm32", "ubm64", "ubm256")]
+    c = golden_real.case("ubm32p")
+    return pools + [(c["w"], c["mean"], c["sigma"])]
+
+
 def rel_err(a, ref):
     """the tolerance metric of the build: |a - ref| / max(1, |ref|)  (north_star: 1e-4 relative fp32;
     per-frame log-likelihoods can be ~0, SURVEY.md s7 hard part 2b)."""

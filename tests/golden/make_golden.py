@@ -142,6 +142,83 @@ def gen_gmm():
     print("gmm_ref.npz keys:", len(flat))
 
 
+def gen_realparams():
+    """(a) the fourth shipped UBM; (b) a 100-speaker set whose parameter statistics are resampled from the four shipped UBMs
+    (synth.realparam_models), scored by the compiled reference: utterance sums for every speaker, per-frame values for three."""
+    flat = {}
+    fname = "ubm.mixture-32.person-20.immature.model"
+    g = ref_so.RefGMM.load(os.path.join(REF, "src/gui/model", fname))
+    w, m, s = g.params()
+    X = synth.draw(w, m, s, 400, seed=31)
+    X[:40] *= 1.7
+    flat["ubm32p/w"], flat["ubm32p/mean"], flat["ubm32p/sigma"], flat["ubm32p/X"] = w, m, s, X
+    flat["ubm32p/score_fastexp"] = g.score(X, 4)
+    flat["ubm32p/score_all"] = np.float64(g.score_all_abi(X, 4))
+    g.free()
+    z = np.load(os.path.join(HERE, "gmm_ref.npz"))
+    pools = [(z[t + "/w"], z[t + "/mean"], z[t + "/sigma"]) for t in ("ubm32", "ubm64", "ubm256")] + [(w, m, s)]
+    S, K, src = 100, 32, 41
+    W, M, Sg = synth.realparam_models(S, K, pools, seed0=5000)
+    X = synth.draw(W[src], M[src], Sg[src], 600, seed=32)
+    sums, frames = np.empty(S), {}
+    for i in range(S):
+        g = ref_so.RefGMM(W[i], M[i], Sg[i])
+        sums[i] = g.score_all_abi(X, 4)
+        if i in (0, src, 99):
+            frames[i] = g.score(X, 4)
+        g.free()
+    flat["realset/S"], flat["realset/K"], flat["realset/src"], flat["realset/seed0"] = np.int64(S), np.int64(K), np.int64(src), np.int64(5000)
+    flat["realset/X"], flat["realset/sums_fastexp"] = X, sums
+    for i, f in frames.items():
+        flat["realset/frames_%d" % i] = f
+    assert int(np.argmax(sums)) == src
+    np.savez_compressed(os.path.join(HERE, "realparams_ref.npz"), **flat)
+    print("realparams_ref.npz keys:", len(flat))
+
+
+def load_reference_silence():
+    """exec the reference's filters/silence.py (py3-patched in memory: the two integer `/` -> `//`, the debug print dropped)."""
+    with open(os.path.join(REF, "src/filters/silence.py")) as f:
+        src = f.read()
+    patched = (src.replace("signal = signal - (typeinfo.max + 1) / 2", "signal = signal - (typeinfo.max + 1) // 2")
+               .replace("retsig = retsig + typeinfo.max / 2", "retsig = retsig + typeinfo.max // 2")
+               .replace("    print average_energy\n", ""))
+    assert patched.count("//") == 2 and "print average_energy" not in patched
+    mod = types.ModuleType("silence_ref_exec")
+    mod.__dict__["__name__"] = "silence_ref_exec"      # not "__main__": the file's main() must not run
+    exec(compile(patched, "ref:filters/silence.py", "exec"), mod.__dict__)
+    return mod
+
+
+def gated_audio(n, seed, fs=16000):
+    """audio with silent and quiet stretches (same generator as tests/test_silence_gpu.py)"""
+    s = synth.audio(n, seed=seed, fs=fs).astype(np.int64)
+    rng = np.random.default_rng(seed)
+    for _ in range(6):
+        w = max(8, min(4000, n // 8))
+        a = int(rng.integers(0, n - w))
+        s[a:a + int(rng.integers(w // 8, w))] //= int(rng.choice([1000, 40, 7]))
+    return s.astype(np.int16)
+
+
+def gen_silence():
+    """outputs of the reference's own remove_silence (src/filters/silence.py:11-50) on seeded gated audio, int16 and uint8"""
+    mod = load_reference_silence()
+    flat = {}
+    cases = [("a", 16000, 80000, 1, {}), ("b", 8000, 30001, 2, {}), ("c", 22050, 50000, 3, {}), ("d", 16000, 333, 4, {}),
+             ("e", 16000, 60000, 9, dict(perc=0.5)), ("f", 16000, 60000, 9, dict(frame_duration=0.03, frame_shift=0.007))]
+    for tag, fs, n, seed, kw in cases:
+        sig = gated_audio(n, seed, fs)
+        flat[tag + "/fs"], flat[tag + "/signal"], flat[tag + "/kwargs"] = np.int64(fs), sig, np.array(repr(kw))
+        flat[tag + "/out"] = mod.remove_silence(fs, sig, **kw)
+    sig = gated_audio(60000, 9)
+    u8 = ((sig.astype(np.int32) >> 8) + 128).astype(np.uint8)
+    flat["u8/fs"], flat["u8/signal"], flat["u8/kwargs"] = np.int64(16000), u8, np.array(repr({}))
+    flat["u8/out"] = mod.remove_silence(16000, u8)
+    np.savez_compressed(os.path.join(HERE, "silence_ref.npz"), **flat)
+    print("silence_ref.npz:", {k: v.shape for k, v in flat.items() if k.endswith("/out")})
+
+
 def gen_lpc():
     """LPC: the reference's feature path (src/feature/LPC.py:46-57) with its talkbox call replaced by the reference repo's
     own prototype of the same algorithm, src/lpcc/lpc_jp.py:13-66 (autocorr + LevinsonDurbin), exec'd from the tree.
@@ -206,7 +283,7 @@ def gen_kmeans():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mfcc", "gmm", "lpc", "kmeans"]
+    which = sys.argv[1:] or ["mfcc", "gmm", "lpc", "kmeans", "realparams", "silence"]
     if "mfcc" in which:
         gen_mfcc()
     if "gmm" in which:
@@ -215,3 +292,7 @@ if __name__ == "__main__":
         gen_lpc()
     if "kmeans" in which:
         gen_kmeans()
+    if "realparams" in which:
+        gen_realparams()
+    if "silence" in which:
+        gen_silence()

@@ -120,3 +120,35 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
                 assert "oracle/" not in txt and "gmm_oracle" not in txt, f
+
+
+def _tc_stats(models):
+    """(eligible, blocks, hard entries, max per block) from the host-side packer of the tensor-core route"""
+    from speaker_recognition_b200.gmm.pygmm import GMM
+    gs = [GMM(len(w)).set_params(w, m, s) for (w, m, s) in models]
+    arr = (C.c_void_p * len(gs))(*[g.gmm for g in gs])
+    b, h, mx = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = _lib.lib().srb200_tc_pack_stats(arr, len(gs), C.byref(b), C.byref(h), C.byref(mx))
+    return rc, b.value, h.value, mx.value
+
+
+def test_tensor_route_packer_takes_real_parameter_models(golden_gmm, golden_real):
+    """host-side eligibility of the tensor-core scorer (no GPU needed): every UBM the reference ships, and a 100-speaker set
+    resampled from them, fit the exact add-back list with room to spare (round 1 keyed the list on sigma < 0.1 and overflowed:
+    12-17 % of the entries of these models)"""
+    from conftest import shipped_ubm_pools
+    from speaker_recognition_b200 import synth
+    pools = shipped_ubm_pools(golden_gmm, golden_real)
+    for w, m, s in pools:
+        rc, blocks, hard, mx = _tc_stats([(w, m, s)])
+        assert rc == 1 and mx <= 64 and hard <= 0.01 * m.size, (rc, blocks, hard, mx)
+    W, M, Sg = synth.realparam_models(100, 32, pools, seed0=5000)
+    rc, blocks, hard, mx = _tc_stats([(W[i], M[i], Sg[i]) for i in range(100)])
+    assert rc == 1 and blocks == 25 and mx <= 100 and hard <= 0.01 * M.size, (rc, blocks, hard, mx)
+    W, M, Sg = synth.models(8, 128, 39, seed0=1000)            # the synthetic C2 models: 1 % of the entries at the sigma floor
+    rc, blocks, hard, mx = _tc_stats([(W[i], M[i], Sg[i]) for i in range(8)])
+    assert rc == 1 and hard <= 0.005 * M.size, (rc, blocks, hard, mx)
+    rng = np.random.default_rng(5)                              # every sigma tiny against the spread of the means: not eligible
+    m = rng.normal(size=(64, 20))
+    rc, _, _, _ = _tc_stats([(np.full(64, 1 / 64), m, np.full((64, 20), 0.05))])
+    assert rc == 0

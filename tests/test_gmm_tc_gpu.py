@@ -1,4 +1,4 @@
-"""GPU parity tests of the tensor-core scoring route (csrc/gmm_score_tc.cuh: tcgen05 kind::tf32, 3xTF32, TMEM accumulators)
+"""GPU parity tests of the tensor-core scoring route (csrc/gmm_score_tc.cuh: tcgen05, TMEM accumulators)
 against the float64 oracle and against the default fp32-FMA route.  Bound: the north_star's 1e-4 * max(1, |ref|) per frame,
 identical argmax; this route's measured worst case on sigma-floor models is ~4e-5 (the FMA route: ~2e-7)."""
 import numpy as np
@@ -45,22 +45,93 @@ def test_tc_route_matches_oracle_per_frame_and_sums(tc_route, S, K, D, T):
     assert int(np.argmax(sums)) == S // 2
 
 
-def test_tc_route_real_parameter_models_and_clamp(tc_route, golden_gmm):
-    for tag in ("ubm32", "ubm64", "ubm256"):
-        c = golden_gmm.case(tag)
+def test_tc_route_real_parameter_models_and_clamp(tc_route, golden_gmm, golden_real):
+    """the four UBMs the reference ships (D = 34 = MFCC + LPC: un-normalised scales, 12-17 % of the sigmas below 0.1) run ON the
+    tensor route -- asserted, not assumed -- and match the float64 oracle per frame and the compiled reference's sums"""
+    L = tc_route
+    for fx, tag in ((golden_gmm, "ubm32"), (golden_gmm, "ubm64"), (golden_gmm, "ubm256"), (golden_real, "ubm32p")):
+        c = fx.case(tag)
         g = GMM(len(c["w"])).set_params(c["w"], c["mean"], c["sigma"])
         got = g.score(c["X"])
+        assert L.srb200_last_score_route() == 1, tag
         exact = gmm_ref.score(c["w"], c["mean"], c["sigma"], c["X"], gmm_ref.MODE_LOGDOMAIN)
         assert np.max(rel_err(got, exact)) < TOL
+        assert np.max(rel_err(got, c["score_fastexp"])) < 5e-4         # the reference's own per-frame values (fast-exp error included)
         assert abs(g.score_all(c["X"]) - float(c["score_all"])) < 1e-5 * abs(float(c["score_all"]))
+        assert L.srb200_last_score_route() == 1, tag
     c, u = golden_gmm.case("ubm32"), golden_gmm.case("underflow")
     g = GMM(32).set_params(c["w"], c["mean"], c["sigma"])
     got = g.score(u["X"])
+    assert L.srb200_last_score_route() == 1
     exact = gmm_ref.score(c["w"], c["mean"], c["sigma"], u["X"], gmm_ref.MODE_LOGDOMAIN)
     deep = exact < gmm_ref.DENORM_LOG_MIN - 5.0
     assert deep.sum() > 3 and np.allclose(got[deep], gmm_ref.SAFE_LOG_FLOOR, atol=1e-5)      # safe_log clamp (gmm.cc:34-38)
     dom = exact > -600
     assert np.max(rel_err(got[dom], exact[dom])) < TOL
+
+
+def test_tc_route_hundred_speakers_with_real_parameter_statistics(tc_route, golden_gmm, golden_real):
+    """100 speakers x 32 mixtures, D = 34, every mixture a (mean, sigma) row resampled from the shipped UBMs
+    (synth.realparam_models): one launch on the tensor route; sums and argmax against the compiled reference
+    (tests/golden/realparams_ref.npz), per-frame values against float64"""
+    from conftest import shipped_ubm_pools
+    L = tc_route
+    c = golden_real.case("realset")
+    S, K, src = int(c["S"]), int(c["K"]), int(c["src"])
+    W, M, Sg = synth.realparam_models(S, K, shipped_ubm_pools(golden_gmm, golden_real), seed0=int(c["seed0"]))
+    gs = GMMSet(gmm_order=K)
+    for i in range(S):
+        gs.gmms.append(GMM(K).set_params(W[i], M[i], Sg[i]))
+        gs.y.append(i)
+    sums = np.array(gs.predict_one_scores(c["X"]))
+    assert L.srb200_last_score_route() == 1
+    assert np.max(np.abs(sums - c["sums_fastexp"]) / np.abs(c["sums_fastexp"])) < 1e-5
+    assert int(np.argmax(sums)) == int(np.argmax(c["sums_fastexp"])) == src
+    for i in (0, src, 99):
+        got = gs.gmms[i].score(c["X"])
+        assert L.srb200_last_score_route() == 1
+        exact = gmm_ref.score(W[i], M[i], Sg[i], c["X"], gmm_ref.MODE_LOGDOMAIN)
+        assert np.max(rel_err(got, exact)) < TOL
+        assert np.max(rel_err(got, c["frames_%d" % i])) < 5e-4
+
+
+def test_tc_route_sees_retrained_parameters(tc_route):
+    """a handle that was scored (tensor-core images built) and is then trained -- by fit(), or by the device EM building blocks --
+    must score with its NEW parameters afterwards (round-1 advisor finding: the images of the old parameters survived)"""
+    import torch
+    from speaker_recognition_b200 import dist
+    L = tc_route
+    K, D = 16, 13
+    w0, m0, s0 = synth.model(K, D, seed=71, floor_frac=0.0)
+    X = synth.draw(*synth.model(K, D, seed=72, floor_frac=0.0), 3000, seed=73)
+    # (a) set_params -> score -> fit -> score
+    g = GMM(K, nr_iteration=6, threshold=0.0, seed=3).set_params(w0, m0, s0)
+    before = g.score_all(X)
+    assert L.srb200_last_score_route() == 1
+    g.fit(X)
+    assert g.last_iterations == 6                                   # the monitor did not stop early on a frozen likelihood
+    w1, m1, s1 = g.get_params()
+    after = g.score_all(X)
+    assert L.srb200_last_score_route() == 1
+    exact = gmm_ref.score_all(w1, m1, s1, X, gmm_ref.MODE_LOGDOMAIN)
+    assert abs(after - exact) < 2e-5 * abs(exact) and after > before + 10.0
+    # (b) device EM building blocks: set_params -> E-step (packs) -> M-step -> score
+    g2 = GMM(K).set_params(w0, m0, s0)
+    g2.score_all(X[:200])
+    Xd = torch.zeros((len(X), 16), dtype=torch.float32, device="cuda")
+    Xd[:, :D] = torch.from_numpy(X.astype(np.float32)).cuda()
+    em = dist.DeviceEM(g2, Xd, len(X), 16, D)
+    for _ in range(2):
+        em.mstep(em.estep(), len(X), 1e-3, 0)
+    # the use the advisor described: score right after the device M-step (the host arrays are still the old ones)
+    mid = g2.score_all(X)
+    em.finish()
+    w2, m2, s2 = g2.get_params()
+    got = g2.score_all(X)
+    assert L.srb200_last_score_route() == 1
+    exact2 = gmm_ref.score_all(w2, m2, s2, X, gmm_ref.MODE_LOGDOMAIN)
+    assert abs(got - exact2) < 2e-5 * abs(exact2) and abs(mid - exact2) < 2e-5 * abs(exact2)
+    assert abs(exact2 - before) > 1e-3 * abs(before)
 
 
 def test_tc_route_equals_fma_route_on_batched_utterances(tc_route):

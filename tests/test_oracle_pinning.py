@@ -214,3 +214,40 @@ def test_gmm_oracle_brackets_sklearn_exact_exp(golden_gmm):
     assert np.max(np.abs(exact - ref) / np.maximum(1, np.abs(ref))) < 1e-9
     fast = gmm_ref.score(w, m, s, X, gmm_ref.MODE_FASTEXP)
     assert np.max(np.abs(fast - ref) / np.maximum(1, np.abs(ref))) < 5e-4
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "e", "f", "u8"])
+def test_silence_oracle_matches_reference_fixture(golden_silence, tag):
+    """oracle/silence_ref.py against the outputs of the reference's own src/filters/silence.py:11-50 (executed by
+    tests/golden/make_golden.py gen_silence): integer work, bit-exact"""
+    from oracle import silence_ref
+    c = golden_silence.case(tag)
+    kw = ast.literal_eval(str(c["kwargs"]))
+    got = silence_ref.remove_silence(int(c["fs"]), c["signal"], **kw)
+    assert got.dtype == c["out"].dtype and np.array_equal(got, c["out"])
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/src/filters/silence.py"), reason="reference tree absent")
+def test_live_reference_silence_agrees_with_port():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    from oracle import silence_ref
+    mod = make_golden.load_reference_silence()
+    for fs, n, seed in [(16000, 40000, 21), (11025, 25000, 22)]:
+        sig = make_golden.gated_audio(n, seed, fs)
+        assert np.array_equal(mod.remove_silence(fs, sig), silence_ref.remove_silence(fs, sig))
+
+
+@pytest.mark.skipif(not ref_so.available(), reason="compiled reference (oracle/_ref) not built")
+def test_realparam_fixture_is_reproducible_from_the_generator(golden_gmm, golden_real):
+    """the 100-speaker real-statistics set is rebuilt from the committed UBM parameters; the compiled reference gives the stored sums"""
+    from conftest import shipped_ubm_pools
+    c = golden_real.case("realset")
+    W, M, Sg = synth.realparam_models(int(c["S"]), int(c["K"]), shipped_ubm_pools(golden_gmm, golden_real), seed0=int(c["seed0"]))
+    for i in (0, int(c["src"]), 99):
+        g = ref_so.RefGMM(W[i], M[i], Sg[i])
+        assert abs(g.score_all_abi(c["X"], 2) - c["sums_fastexp"][i]) < 1e-9 * abs(c["sums_fastexp"][i])
+        g.free()
+        exact = gmm_ref.score(W[i], M[i], Sg[i], c["X"], gmm_ref.MODE_LOGDOMAIN)
+        assert np.max(rel_err(c["frames_%d" % i], exact)) < 5e-4       # the reference's own fast-exp error (SURVEY s7 2b)

@@ -41,3 +41,12 @@ def test_remove_silence_params_uint8_and_extremes():
     assert np.array_equal(remove_silence(16000, loud), silence_ref.remove_silence(16000, loud))
     with pytest.raises(TypeError):
         remove_silence(16000, sig.astype(np.float32))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "e", "f", "u8"])
+def test_remove_silence_matches_the_reference_outputs(golden_silence, tag):
+    """against the outputs of the reference's own src/filters/silence.py (tests/golden/silence_ref.npz), bit for bit"""
+    import ast
+    c = golden_silence.case(tag)
+    got = remove_silence(int(c["fs"]), c["signal"], **ast.literal_eval(str(c["kwargs"])))
+    assert got.dtype == c["out"].dtype and np.array_equal(got, c["out"])
