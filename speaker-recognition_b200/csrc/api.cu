@@ -7,6 +7,7 @@
 #include <algorithm>
 #include "../../include/srb200.h"
 #include "kernels.h"
+#include <cuda_fp16.h>
 #include "gmm_score_tc_layout.h"
 
 namespace srb {
@@ -90,6 +91,9 @@ void PackedModels::release_tc() {
 	if (d_tc) cudaFree(d_tc);
 	if (d_tc_hard) cudaFree(d_tc_hard);
 	if (d_tc_cs) cudaFree(d_tc_cs);
+	if (d_tc2) cudaFree(d_tc2);
+	d_tc2 = nullptr;
+	h_tc2.clear();
 	d_tc = nullptr;
 	d_tc_hard = nullptr;
 	d_tc_cs = nullptr;
@@ -127,6 +131,10 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 	pm.release_tc();
 	pm.tc_built = true;
 	pm.h_tc.assign((size_t)blocks * bf, 0.f);
+	const int Kp2 = t2_kp(D);
+	const size_t bh = t2_block_halfs(Kp2);
+	if (Kp2 <= T2_KP_MAX) pm.h_tc2.assign((size_t)blocks * bh, 0);
+	pm.tc2_Kp = Kp2;
 	pm.tc_Kp = Kp;
 	pm.tc_cols_per_spk = cols;
 	pm.tc_blocks_total = blocks;
@@ -181,6 +189,15 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 		const size_t off = tc_img_off(NB, r, k);
 		pm.h_tc[(size_t)blk * bf + off] = hi;
 		pm.h_tc[(size_t)blk * bf + (size_t)NB * Kp + off] = lo;
+		if (!pm.h_tc2.empty()) {
+			// fp16 head + fp16 tail, both round-to-nearest (22 significant bits, unbiased); rank = which CTA of the pair holds the row
+			const double wc = std::max(-T2_W_MAX, std::min(T2_W_MAX, w));
+			const __half h = __float2half_rn((float)wc);
+			const __half l = __float2half_rn((float)(wc - (double)__half2float(h)));
+			const size_t base = (size_t)blk * bh + (size_t)(r >> 6) * 2 * T2_NH * Kp2 + t2_img_off(r & 63, k);
+			pm.h_tc2[base] = __half_as_ushort(h);
+			pm.h_tc2[base + (size_t)T2_NH * Kp2] = __half_as_ushort(l);
+		}
 	};
 	std::vector<double> av(D), nbv(D);
 	std::vector<int> order(D);
@@ -199,10 +216,15 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 				tot += nbv[d] * nbv[d];
 				order[d] = d;
 				is_hard[d] = 0;
+				if (av[d] * av[d] > T2_W_MAX || fabs(2.0 * av[d] * nbv[d]) > T2_W_MAX) {     // outside the fp16 image's range: exact path
+					is_hard[d] = 1;
+					tot -= nbv[d] * nbv[d];
+				}
 			}
 			if (tot > BUDGET) {
 				std::sort(order.begin(), order.end(), [&](int x, int y) { return nbv[x] * nbv[x] > nbv[y] * nbv[y]; });
 				for (int i = 0; i < D && tot > BUDGET; ++i) {
+					if (is_hard[order[i]]) continue;
 					is_hard[order[i]] = 1;
 					tot -= nbv[order[i]] * nbv[order[i]];
 				}
@@ -222,6 +244,7 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 			}
 			if (any) g.back().w = 1 + 128 * (col & 31);      // last entry of this column: flush the sum to scratch column col & 31
 			put(row, 2 * D, (C < -1.0e30 || C != C) ? -1.0e30 : C);
+			pm.h_tc_hard[((size_t)blk * TC_HSTRIDE + 2) * 4 + (col >> 5)] |= (int)(1u << (col & 31));      // header word 2: valid columns
 		} else {
 			put(row, 2 * D, -1.0e30);      // padded row: exp2 underflows to exactly 0
 		}
@@ -234,12 +257,12 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 			for (const HardEntry &he : g)
 				if (he.w) hdr[gi] |= (int)(1u << (((he.w - 1) / 128) & 31));
 			while (g.size() % 4) g.push_back({0, 0.f, 0.f, 0});          // null entries: t = 0, no flush
-			if (pos + (int)g.size() > TC_HSTRIDE - 2) {
+			if (pos + (int)g.size() > TC_HSTRIDE - TC_HHEAD) {
 				overflow = true;
 				break;
 			}
 			for (const HardEntry &he : g) {
-				int *e = hdr + (size_t)(2 + pos) * 4;
+				int *e = hdr + (size_t)(TC_HHEAD + pos) * 4;
 				e[0] = he.x;
 				memcpy(&e[1], &he.a, 4);
 				memcpy(&e[2], &he.nb, 4);
@@ -252,6 +275,7 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 	}
 	if (overflow) {      // too many cancelling entries for the sparse list: this model set stays on the FMA route
 		pm.h_tc.clear();
+		pm.h_tc2.clear();
 		pm.h_tc_hard.clear();
 		pm.h_tc_cs.clear();
 	}
@@ -712,7 +736,7 @@ int srb200_set_compat_clamp(int mode) {
 int srb200_get_compat_clamp(void) { return ctx().compat_clamp; }
 int srb200_set_score_path(int path) {
 	API_ENTER();
-	SRB_REQUIRE(path >= -1 && path <= 1, "score path must be -1 (default), 0 (fp32 FMA) or 1 (tcgen05 3xTF32)");
+	SRB_REQUIRE(path >= -1 && path <= 2, "score path must be -1 (default), 0 (fp32 FMA), 1 (tcgen05 3xFP16 on CTA pairs) or 2 (round-1 tcgen05 3xTF32)");
 	ctx().score_path = path;
 	return 0;
 }
@@ -1015,13 +1039,13 @@ int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int 
 	PackedModels pm;
 	pack_models_tc_host(pm, n_models, K, D, w.data(), m.data(), s.data(), Ks.data());
 	pm.S = n_models;
-	const bool ok = tc_supported(pm, D);
+	const bool ok = tc2_supported(pm, D);
 	int hard = 0, mx = 0;
 	if (ok)
 		for (int b = 0; b < pm.tc_blocks_total; ++b) {
 			int n = 0;
 			for (int e = 0; e < pm.h_tc_hard[(size_t)b * TC_HSTRIDE * 4 + 7]; ++e)
-				n += pm.h_tc_hard[((size_t)b * TC_HSTRIDE + 2 + e) * 4 + 1] != 0;        // null padding entries have a = 0
+				n += pm.h_tc_hard[((size_t)b * TC_HSTRIDE + TC_HHEAD + e) * 4 + 1] != 0;        // null padding entries have a = 0
 			hard += n;
 			mx = std::max(mx, n);
 		}

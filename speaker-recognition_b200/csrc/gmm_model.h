@@ -31,6 +31,9 @@ struct PackedModels {             // device-resident packed parameters of S mode
 	// tensor-core path (gmm_score_tc.cuh): weight images [blocks][hi|lo][128*Kp], built on the host with the FMA tiles
 	std::vector<float> h_tc;      // host image, uploaded on first use
 	std::vector<int> h_tc_hard;   // per block: 4*TC_HSTRIDE ints (two header words + hard entries), see gmm_score_tc.cuh
+	std::vector<uint16_t> h_tc2;  // second-generation images (gmm_score_tc2.cuh): fp16 head/tail, [blocks][2 ranks][head | tail][64 * Kp16]
+	void *d_tc2 = nullptr;
+	int tc2_Kp = 0;
 	std::vector<float> h_tc_cs;   // [2][D]: per-dimension centre c_d and power-of-two scale alpha_d of the feature transform x'' = (x - c) alpha
 	float *d_tc = nullptr;
 	int *d_tc_hard = nullptr;

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_score_tc_kernel(const TcArg
 					// address space, so the compiler cannot move a load above a store on its own.  Tried and rejected (B200, C2):
 					// a dedicated "park" warp per lane quarter doing all four groups one block ahead (8.0 ms vs 6.9: one warp cannot
 					// issue 48 dependent entry updates per block in time) and prefetching step i+1 before the stores of step i (7.4 ms).
-					const int4 *e = hl + 2 + e0;
+					const int4 *e = hl + TC_HHEAD + e0;
 					const int n = e1 - e0;
 					float csum = 0.f;
 #pragma unroll 1

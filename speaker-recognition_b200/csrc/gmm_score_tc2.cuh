@@ -1,0 +1,539 @@
+// gmm_score_tc2.cuh -- tensor-core diagonal-GMM scorer for sm_100a, second generation: tcgen05 kind::f16 as "3xFP16" on CTA PAIRS.
+//
+// Same quantity as gmm_score.cu (log2 p(x) per frame and speaker, per-utterance sums).  The Mahalanobis term is expanded over
+// centred, power-of-two-scaled features x'' = (x - c_d) alpha_d (api.cu pack_models_tc_host),
+//     l2_k(x) = C_k + sum_d [ (-a''_kd^2) x''_d^2 + (-2 a''_kd nb''_kd) x''_d ],     C_k = c2_k - sum_d nb''_kd^2,
+// i.e. a GEMM  L[frames x rows] = PHI[frames x Kp] . W[rows x Kp]^T,  PHI = [x''^2, x'', 1, 0-pad],  Kp = 16 ceil((2D+1)/16).
+// Every fp32 value of PHI and W is split by ROUND-TO-NEAREST into an fp16 head and an fp16 tail (22 significant bits, unbiased;
+// round 1 truncated to tf32 heads: 2^-21 one-sided) and the product runs as three fp16 passes, hi*hi + lo*hi + hi*lo, fp32
+// accumulation in tensor memory: the same accuracy class as 3xTF32 at HALF the tensor time (a kind::f16 MMA covers K = 16 in the
+// 64 cycles a kind::tf32 MMA needs for K = 8; measured, experiments/tc2_gemm_test.cu) and half the operand bytes.
+// The few (row, dim) entries whose nb'' is so large that the expanded form would cancel are left out of W and C and added back
+// EXACTLY in fp32 by the epilogue (t = a'' x'' + nb'', l2 -= t*t), from a per-block sparse list.
+//
+// Structure: a CLUSTER OF TWO CTAs (one per SM of a TPC) works as one tcgen05 cta_group::2 unit: 256 frames (128 per CTA) against
+// the stream of 128-row weight blocks.  Each CTA bulk-copies only ITS HALF of every block (64 rows: rank r supplies rows
+// [64 r, 64 r + 64) of the block -- verified by the probe) into its own shared memory, so the L2 -> SM traffic per frame is half
+// that of a single-CTA kernel (round 1 ran at the chip's ~6.3 KB/clk L2 limit: every SM streamed every block).
+//   warp 0  producer (both CTAs): cp.async.bulk of the block's hard-entry list and of this CTA's half block (fp16 head image and
+//           tail image, one 256 Kp-byte copy) into a ring of up to 6 stages
+//   warp 1  leader CTA: MMA issuer -- waits for its own stage and for the peer's (relayed), issues 3 x Kp/16
+//           tcgen05.mma.cta_group::2.kind::f16 (M 256 = 2 x 128, N 128, K 16) with the A operand (PHI head | tail) in TENSOR MEMORY,
+//           tcgen05.commit multicast to both CTAs frees the stage and publishes the accumulator slot (three 128-column slots)
+//           peer CTA: relay -- forwards "my half of stage s has landed" to the leader with a remote mbarrier arrive
+//   warps 2-17 epilogue, thread = frame row = TMEM lane, the four warps of a lane quarter own the four 32-column groups of every
+//           block: per unit they build PHI (global -> registers -> tcgen05.st) and keep the raw x'' in shared memory; per block
+//           they sum the hard entries' t^2 per column while the MMAs run, tcgen05.ld the accumulator, release the slot (remote
+//           arrive on the leader's barrier), subtract the exact terms, and fold the 32 values into an online log2-sum-exp2;
+//           at a speaker's end the quarter's warps merge, apply the clamp and write per-frame values / per-(tile, speaker) sums.
+// B images are K-major in the no-swizzle canonical layout (8-row x 16-byte core matrices = 8 rows x 8 halfs; LBO = 1024 B between
+// K-adjacent core matrices of a 64-row half block, SBO = 128 B between 8-row groups), stored in HBM in shared-memory order.
+#pragma once
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "gmm_score_tc_layout.h"
+
+namespace srb {
+
+struct Tc2Args {
+	const float *X;            // [n][ld] features
+	int ld;
+	const float *cs;           // [2][D] feature transform of the model set: centre c_d, power-of-two scale alpha_d
+	const __half *B;           // [n_blocks_total][2 ranks][head | tail][64 * Kp] weight images
+	const int4 *ftiles;        // per frame tile of 128 frames: {first frame, frame count, utterance, 0}
+	int n_ftiles;
+	int Kp;
+	int S;                     // speakers
+	int blocks_per_spk;        // 128-row blocks per speaker (rows padded to a multiple of 128) -- or, when seg < 128:
+	int seg;                   // columns per speaker inside a block (32 or 64) when a speaker is smaller than a block
+	int n_blocks_total;
+	int n_chunks;              // the block range is cut into n_chunks contiguous chunks (whole speakers each)
+	int spk_per_chunk;
+	float *frame_ll;           // optional [S][ldf]
+	int ldf;
+	double *partial;           // [n_ftiles][S][4]
+	int clamp, frame_log2;
+	int D;
+	int bstages;               // B ring depth
+	const int4 *hard;          // [n_blocks_total][TC_HSTRIDE], layout in gmm_score_tc_layout.h
+};
+
+namespace tc2 {
+
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_rank() {
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
+	uint32_t r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+	return r;
+}
+// arrive on a barrier of the LEADER CTA (works from either CTA of the pair: `addr` is a shared::cluster address)
+__device__ __forceinline__ void arrive_cluster(uint32_t addr) {
+	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ bool try_wait_cluster(uint64_t *bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(ok)
+	    : "r"(smem_u32(bar)), "r"(parity)
+	    : "memory");
+	return ok != 0;
+}
+// bounded waits: a broken pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void wait(uint64_t *bar, uint32_t parity) {
+	long long spins = 0;
+	while (!mbar_try_wait(bar, parity)) {
+		if (++spins > 400000000LL) __trap();
+	}
+}
+__device__ __forceinline__ void wait_cluster(uint64_t *bar, uint32_t parity) {
+	long long spins = 0;
+	while (!try_wait_cluster(bar, parity)) {
+		if (++spins > 400000000LL) __trap();
+	}
+}
+__device__ __forceinline__ void ld32(uint32_t taddr, float *v) {
+	uint32_t r[32];
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+	    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+	    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+	      "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+	      "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+	      "=r"(r[31])
+	    : "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&v)[8]) {
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+	             "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+	             : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T over the CTA pair: A (this CTA's 128 rows) is read from tensor memory, B (64 rows from each
+// CTA) from shared memory.  Issued by the whole converged warp of the LEADER CTA, one lane elected inside the statement.
+template <int ACC>
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+	asm volatile(
+	    "{\n\t.reg .b64 db;\n\t.reg .pred p, pe;\n\t"
+	    "mov.b64 db, {%2, %3};\n\t"
+	    "setp.ne.b32 p, %5, 0;\n\t"
+	    "elect.sync _|pe, 0xffffffff;\n\t"
+	    "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+	    "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
+	    : "memory");
+}
+// completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void commit_pair(uint64_t *bar) {
+	asm volatile(
+	    "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+	    "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+	    "h"((uint16_t)3)
+	    : "memory");
+}
+// fp32 -> fp16 head + fp16 tail, both round-to-nearest; two values per call, packed (first value in the low half)
+__device__ __forceinline__ void split_pack(float v0, float v1, uint32_t &hi, uint32_t &lo) {
+	const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+	const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
+	hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+	lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+}
+
+}  // namespace tc2
+
+// online log2-sum-exp2 update with 32 new values (one chunk of accumulator columns) for one frame
+__device__ __forceinline__ void tc2_lse_update(const float *v, float &m_run, float &s_run) {
+	float t[16];                                   // tree reduction (ptxas fuses the pairs into three-input FMNMX3)
+#pragma unroll
+	for (int i = 0; i < 16; ++i) t[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+	for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+		for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
+	const float mx = t[0];
+	const float m_new = fmaxf(m_run, mx);
+	// packed fp32x2 adds (SASS FADD2): the 32 subtractions and the 32 sum updates cost 16 instructions each
+	const float nm = -m_new;
+	unsigned long long nm2, acc01 = 0ull, acc23 = 0ull;
+	asm("mov.b64 %0, {%1, %1};" : "=l"(nm2) : "f"(nm));
+#pragma unroll
+	for (int i = 0; i < 32; i += 4) {
+		unsigned long long p01, p23, d01, d23;
+		asm("mov.b64 %0, {%1, %2};" : "=l"(p01) : "f"(v[i]), "f"(v[i + 1]));
+		asm("mov.b64 %0, {%1, %2};" : "=l"(p23) : "f"(v[i + 2]), "f"(v[i + 3]));
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(p01), "l"(nm2));
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(p23), "l"(nm2));
+		float a, b, c, d;
+		asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(d01));
+		asm("mov.b64 {%0, %1}, %2;" : "=f"(c), "=f"(d) : "l"(d23));
+		unsigned long long e01, e23;
+		asm("mov.b64 %0, {%1, %2};" : "=l"(e01) : "f"(ex2_approx(a)), "f"(ex2_approx(b)));
+		asm("mov.b64 %0, {%1, %2};" : "=l"(e23) : "f"(ex2_approx(c)), "f"(ex2_approx(d)));
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc01) : "l"(acc01), "l"(e01));
+		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc23) : "l"(acc23), "l"(e23));
+	}
+	float s0, s1, s2, s3;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(acc01));
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(s2), "=f"(s3) : "l"(acc23));
+	s_run = fmaf(s_run, ex2_approx(m_run - m_new), (s0 + s1) + (s2 + s3));
+	m_run = m_new;
+}
+
+// KSTEPS = Kp / 16 as a compile-time constant (fully unrolled MMA issue), or 0 for the generic loop
+template <int KSTEPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_score_tc2_kernel(const Tc2Args A) {
+	extern __shared__ __align__(1024) unsigned char tc2_smem[];
+	const int Kp = A.Kp, D = A.D, XS = tc_x_stride(D);
+	const uint32_t part_bytes = (uint32_t)T2_NH * Kp * 2;              // one image part (head or tail) of a half block
+	const uint32_t stage_bytes = 2 * part_bytes;
+	const int NST = A.bstages;
+	unsigned char *sB = tc2_smem;                                                               // [NST] stages: head | tail of this CTA's half block
+	int4 *hring = reinterpret_cast<int4 *>(sB + (size_t)NST * stage_bytes);                    // [TC_HSTAGES][TC_HSTRIDE] hard-entry lists
+	float *scr = reinterpret_cast<float *>(hring + TC_HSTAGES * TC_HSTRIDE);                    // [16 warps][32 columns][32 lanes] add-back sums
+	float2 *ms_x = reinterpret_cast<float2 *>(scr + 16 * 32 * 32);                              // [2][3][128] (m, s) handed to the merging warp
+	uint64_t *bars = reinterpret_cast<uint64_t *>(ms_x + 2 * 3 * TC_M);
+	uint64_t *full_b = bars, *peer_full = full_b + T2_BSTAGES_MAX, *empty_b = peer_full + T2_BSTAGES_MAX;
+	uint64_t *full_h = empty_b + T2_BSTAGES_MAX, *empty_h = full_h + TC_HSTAGES;
+	uint64_t *tm_full = empty_h + TC_HSTAGES, *tm_empty = tm_full + T2_SLOTS;
+	uint64_t *a_ready = tm_empty + T2_SLOTS;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
+	float *sX = reinterpret_cast<float *>(bars + 64);                                           // [128][XS] x'' of the unit's tile
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t rank = tc2::cluster_rank();
+	const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+	if (tid == 0) {
+		for (int s = 0; s < T2_BSTAGES_MAX; ++s) {
+			mbar_init(&full_b[s], 1);
+			mbar_init(&peer_full[s], 1);
+			mbar_init(&empty_b[s], 1);
+		}
+		for (int s = 0; s < TC_HSTAGES; ++s) {
+			mbar_init(&full_h[s], 1);
+			mbar_init(&empty_h[s], 16);      // one arrival per epilogue warp of this CTA
+		}
+		for (int s = 0; s < T2_SLOTS; ++s) {
+			mbar_init(&tm_full[s], 1);
+			mbar_init(&tm_empty[s], 32);     // one arrival per epilogue warp of BOTH CTAs (used in the leader only)
+		}
+		mbar_init(a_ready, 32);
+		fence_mbar_init();
+	}
+	if (warp == 1) {
+		asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+	}
+	tc2::fence_before();
+	__syncthreads();
+	tc2::cluster_sync_all();           // both CTAs' barriers are initialised and both allocations are done before any cross-CTA traffic
+	tc2::fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	// work units: (pair of frame tiles, chunk of whole speakers); CTA rank r of the cluster takes tile 2 p + r
+	const int n_pairs = (A.n_ftiles + 1) >> 1;
+	const int n_units = n_pairs * A.n_chunks;
+	const int blocks_per_chunk_full = (A.seg >= TC_NB) ? A.spk_per_chunk * A.blocks_per_spk : (A.spk_per_chunk * A.seg + TC_NB - 1) / TC_NB;
+
+	if (warp == 0) {
+		// ======================= producer =======================
+		if (lane == 0) {
+			uint32_t it_h = 0, ph_b = 0;
+			int st_b = 0;
+			for (int u = cluster_id; u < n_units; u += n_clusters) {
+				const int chunk = u % A.n_chunks;
+				const int blk0 = chunk * blocks_per_chunk_full;
+				const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
+				for (int b = blk0; b < blk1; ++b, ++it_h) {
+					{   // the block's hard-entry list (needed first: the epilogue walks it while the block's MMAs run)
+						const int st = it_h % TC_HSTAGES;
+						tc2::wait(&empty_h[st], ((it_h / TC_HSTAGES) & 1) ^ 1);
+						mbar_expect_tx(&full_h[st], TC_HSTRIDE * 16);
+						bulk_g2s(hring + (size_t)st * TC_HSTRIDE, A.hard + (size_t)b * TC_HSTRIDE, TC_HSTRIDE * 16, &full_h[st]);
+					}
+					// this CTA's half of the block: head image then tail image, contiguous in HBM
+					const unsigned char *src = reinterpret_cast<const unsigned char *>(A.B) + ((size_t)b * 2 + rank) * stage_bytes;
+					tc2::wait(&empty_b[st_b], ph_b ^ 1);
+					mbar_expect_tx(&full_b[st_b], stage_bytes);
+					bulk_g2s(sB + (size_t)st_b * stage_bytes, src, stage_bytes, &full_b[st_b]);
+					if (++st_b == NST) {
+						st_b = 0;
+						ph_b ^= 1;
+					}
+				}
+			}
+		}
+	} else if (warp == 1 && rank != 0) {
+		// ======================= peer CTA: relay "my half of the stage has landed" to the leader =======================
+		if (lane == 0) {
+			uint32_t ph_b = 0;
+			int st_b = 0;
+			for (int u = cluster_id; u < n_units; u += n_clusters) {
+				const int chunk = u % A.n_chunks;
+				const int blk0 = chunk * blocks_per_chunk_full;
+				const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
+				for (int b = blk0; b < blk1; ++b) {
+					tc2::wait(&full_b[st_b], ph_b);
+					tc2::arrive_cluster(tc2::mapa(smem_u32(&peer_full[st_b]), 0));
+					if (++st_b == NST) {
+						st_b = 0;
+						ph_b ^= 1;
+					}
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ======================= leader CTA: MMA issuer (whole warp converged; one lane elected per instruction) =======================
+		// instruction descriptor: D = F32 (bits 4-5 = 1), A/B = F16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24 (M = 256: the pair)
+		const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_NB >> 3) << 17) | ((uint32_t)((2 * TC_M) >> 4) << 24);
+		constexpr uint32_t lbo_b = (T2_NH / 8) * 128, sbo = 128;
+		constexpr uint32_t d_hi = (uint32_t)(sbo >> 4) | (1u << 14);            // SBO | descriptor version bit 46
+		constexpr uint32_t stepB = (2 * lbo_b) >> 4;                            // one k-step = 16 halfs = two K-adjacent core matrices
+		const int ksteps = KSTEPS > 0 ? KSTEPS : Kp / 16;
+		const uint32_t a_hi = tmem_base + T2_A_COL, a_lo = a_hi + (uint32_t)(Kp >> 1);
+		const uint32_t tail_off = part_bytes >> 4;
+		uint32_t ph_b = 0, it_a = 0, it_s = 0;
+		int st_b = 0;
+		for (int u = cluster_id; u < n_units; u += n_clusters, ++it_a) {
+			const int chunk = u % A.n_chunks;
+			const int blk0 = chunk * blocks_per_chunk_full;
+			const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
+			tc2::wait_cluster(a_ready, it_a & 1);            // PHI of both CTAs' tiles is in tensor memory
+			tc2::fence_after();
+			for (int b = blk0; b < blk1; ++b, ++it_s) {
+				const int slot = it_s % T2_SLOTS;
+				tc2::wait_cluster(&tm_empty[slot], ((it_s / T2_SLOTS) & 1) ^ 1);
+				const int st = st_b;
+				tc2::wait(&full_b[st], ph_b);
+				tc2::wait_cluster(&peer_full[st], ph_b);
+				tc2::fence_after();
+				const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TC_NB);
+				const uint32_t dB0 = ((smem_u32(sB + (size_t)st * stage_bytes) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
+				// 3xFP16: (A_hi + A_lo) * B_hi, then A_hi * B_lo
+				tc2::mma_f16_ts<0>(d_tmem, a_hi, dB0, d_hi, idesc);     // first MMA of the block overwrites the slot
+#pragma unroll
+				for (int k = 1; k < ksteps; ++k) tc2::mma_f16_ts<1>(d_tmem, a_hi + 8 * k, dB0 + stepB * k, d_hi, idesc);
+#pragma unroll
+				for (int k = 0; k < ksteps; ++k) tc2::mma_f16_ts<1>(d_tmem, a_lo + 8 * k, dB0 + stepB * k, d_hi, idesc);
+#pragma unroll
+				for (int k = 0; k < ksteps; ++k) tc2::mma_f16_ts<1>(d_tmem, a_hi + 8 * k, dB0 + tail_off + stepB * k, d_hi, idesc);
+				tc2::commit_pair(&empty_b[st]);         // both CTAs' stage may be refilled once these MMAs have read it
+				tc2::commit_pair(&tm_full[slot]);       // the accumulator slot is complete (in both CTAs)
+				if (++st_b == NST) {
+					st_b = 0;
+					ph_b ^= 1;
+				}
+			}
+		}
+	} else {
+		// ======================= epilogue (16 warps; thread = frame row; the 4 warps of a lane quarter take the 4 column groups) ====
+		const int ew = warp - 2;                      // 0..15
+		const int q = warp & 3;                       // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+		const int cg = ew >> 2;                       // 32-column group of every block this warp owns
+		const int row = q * 32 + lane;                // frame within the tile
+		const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+		float *my_scr = scr + (size_t)ew * 32 * 32 + lane;
+		float *xrow = sX + (size_t)row * XS;
+		const unsigned char *xrow_b = reinterpret_cast<const unsigned char *>(xrow);
+		unsigned char *scr_b = reinterpret_cast<unsigned char *>(my_scr) - 1;      // entry.w = 1 + byte offset of the scratch column
+		const int seg = A.seg;
+		const int cols_per_spk = (seg >= TC_NB) ? A.blocks_per_spk * TC_NB : seg;
+		const int nch = Kp >> 4;                      // chunks of 16 k-values = 8 packed columns
+		const uint32_t a_ready_leader = tc2::mapa(smem_u32(a_ready), 0);
+		const uint32_t tm_empty_leader = tc2::mapa(smem_u32(tm_empty), 0);
+		uint32_t it_s = 0, it_h = 0, n_merge = 0;
+#define SRB_TC2_QBAR() asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory")      /* the 4 warps of this lane quarter */
+		for (int u = cluster_id; u < n_units; u += n_clusters) {
+			const int pair = u / A.n_chunks, chunk = u - pair * A.n_chunks;
+			const int tile = 2 * pair + (int)rank;
+			const bool tile_ok = tile < A.n_ftiles;
+			const int blk0 = chunk * blocks_per_chunk_full;
+			const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
+			const int4 ft = tile_ok ? A.ftiles[tile] : make_int4(0, 0, 0, 0);
+			const bool valid = row < ft.y;
+
+			// ---- PHI = [x''^2, x'', 1, 0-pad] of this thread's frame -> tensor memory (fp16 head | fp16 tail, two k per column); the
+			// quarter's four warps split the 16-value chunks.  All MMAs of the previous unit have completed (this warp consumed its
+			// last tm_full); the quarter barrier makes sure no sibling still reads the previous tile's x''.
+			SRB_TC2_QBAR();
+			{
+				const float *xg = A.X + (size_t)(ft.x + (valid ? row : 0)) * A.ld;
+				const float *cen = A.cs, *alp = A.cs + D;
+				auto xpp = [&](int d) -> float {
+					if (!valid) return 0.f;
+					const float x = (__ldg(xg + d) - __ldg(cen + d)) * __ldg(alp + d);
+					return fminf(fmaxf(x, -T2_X_CLAMP), T2_X_CLAMP);       // keeps x''^2 inside fp16 (frames out there underflow every mixture anyway)
+				};
+				auto val = [&](int k) -> float {
+					if (k < D) {
+						const float x = xpp(k);
+						return x * x;
+					}
+					if (k < 2 * D) {
+						const float x = xpp(k - D);
+						xrow[k - D] = x;
+						return x;
+					}
+					return (k == 2 * D && valid) ? 1.f : 0.f;
+				};
+				for (int c = cg; c < nch; c += 4) {
+					uint32_t hi[8], lo[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) tc2::split_pack(val(16 * c + 2 * j), val(16 * c + 2 * j + 1), hi[j], lo[j]);
+					tc2::st8(lane_base + T2_A_COL + 8 * c, hi);
+					tc2::st8(lane_base + T2_A_COL + (Kp >> 1) + 8 * c, lo);
+				}
+				asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+				tc2::fence_before();
+				SRB_TC2_QBAR();                                // the quarter's x'' are in shared memory
+				if (lane == 0) tc2::arrive_cluster(a_ready_leader);
+			}
+
+			float m_run = -3.0e38f, s_run = 0.f;
+			int col_in_spk = 0;                       // columns of the current speaker consumed so far (by the quarter's warps together)
+			int spk = chunk * A.spk_per_chunk;        // first speaker of the current block
+
+			// close a speaker whose columns were shared by `width` (1, 2 or 4) adjacent warps of the quarter: merge, clamp,
+			// per-frame output, per-(tile, speaker, lane quarter) partial sum
+			auto finish = [&](int my_spk, int width) {
+				float m = m_run, sacc = s_run;
+				const bool leader = (cg & (width - 1)) == 0;
+				if (width > 1) {
+					// double-buffered hand-over (buffer = parity of the merge count): one barrier per speaker; the buffer written
+					// now is not written again before the NEXT merge's barrier, which every reader of it has passed by then
+					float2 *buf = ms_x + (size_t)(n_merge & 1) * 3 * TC_M;
+					++n_merge;
+					if (!leader) buf[(cg - 1) * TC_M + row] = make_float2(m, sacc);
+					SRB_TC2_QBAR();
+					if (leader) {
+						for (int o = 0; o < width - 1; ++o) {
+							const float2 other = buf[(cg + o) * TC_M + row];
+							const float M = fmaxf(m, other.x);
+							sacc = sacc * ex2_approx(m - M) + other.y * ex2_approx(other.x - M);
+							m = M;
+						}
+					}
+				}
+				if (leader && my_spk < A.S && tile_ok) {
+					const float l2 = m + lg2_approx(sacc);
+					float ll = l2 * TC_LN2;
+					if (A.clamp && !(ll >= -744.4400719213812f)) ll = -34.538776394910684f;
+					if (valid && A.frame_ll != nullptr) A.frame_ll[(size_t)my_spk * A.ldf + ft.x + row] = A.frame_log2 ? l2 : ll;
+					float local = valid ? ll : 0.f;
+#pragma unroll
+					for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+					if (lane == 0) A.partial[((size_t)tile * A.S + my_spk) * 4 + q] = (double)local;
+				}
+				m_run = -3.0e38f;
+				s_run = 0.f;
+			};
+
+			for (int b = blk0; b < blk1; ++b, ++it_s, ++it_h) {
+				const int slot = it_s % T2_SLOTS, hst = it_h % TC_HSTAGES;
+				// ---- exact add-back, phase 1 (the block's MMAs are still running): sum t^2 of this warp's hard entries per column --
+				// the list is uniform across the warp, sorted by column, `last` flag on a column's final entry -- and park each
+				// column's sum in the warp's scratch row (a dynamic column index cannot address registers).
+				tc2::wait(&full_h[hst], (it_h / TC_HSTAGES) & 1);
+				const int4 *hl = hring + (size_t)hst * TC_HSTRIDE;
+				const int4 hmask = hl[0], hoff = hl[1], hval = hl[2];
+				const int e0 = cg == 0 ? 0 : (cg == 1 ? hoff.x : (cg == 2 ? hoff.y : hoff.z));
+				const int e1 = cg == 0 ? hoff.x : (cg == 1 ? hoff.y : (cg == 2 ? hoff.z : hoff.w));
+				const uint32_t mask = (uint32_t)(cg == 0 ? hmask.x : (cg == 1 ? hmask.y : (cg == 2 ? hmask.z : hmask.w)));
+				const uint32_t vmask = (uint32_t)(cg == 0 ? hval.x : (cg == 1 ? hval.y : (cg == 2 ? hval.z : hval.w)));
+				{
+					// four entries per step (the host pads every group's list to a multiple of four with null entries): all loads of a
+					// step are issued before its first scratch store
+					const int4 *e = hl + TC_HHEAD + e0;
+					const int n = e1 - e0;
+					float csum = 0.f;
+#pragma unroll 1
+					for (int i = 0; i < n; i += 4) {
+						const int4 a0 = e[i], a1 = e[i + 1], a2 = e[i + 2], a3 = e[i + 3];
+						const float x0 = *reinterpret_cast<const float *>(xrow_b + a0.x), x1 = *reinterpret_cast<const float *>(xrow_b + a1.x);
+						const float x2 = *reinterpret_cast<const float *>(xrow_b + a2.x), x3 = *reinterpret_cast<const float *>(xrow_b + a3.x);
+						const float t0 = fmaf(x0, __int_as_float(a0.y), __int_as_float(a0.z)), t1 = fmaf(x1, __int_as_float(a1.y), __int_as_float(a1.z));
+						const float t2 = fmaf(x2, __int_as_float(a2.y), __int_as_float(a2.z)), t3 = fmaf(x3, __int_as_float(a3.y), __int_as_float(a3.z));
+						csum = fmaf(t0, t0, csum);
+						if (a0.w) {
+							*reinterpret_cast<float *>(scr_b + a0.w) = csum;
+							csum = 0.f;
+						}
+						csum = fmaf(t1, t1, csum);
+						if (a1.w) {
+							*reinterpret_cast<float *>(scr_b + a1.w) = csum;
+							csum = 0.f;
+						}
+						csum = fmaf(t2, t2, csum);
+						if (a2.w) {
+							*reinterpret_cast<float *>(scr_b + a2.w) = csum;
+							csum = 0.f;
+						}
+						csum = fmaf(t3, t3, csum);
+						if (a3.w) {
+							*reinterpret_cast<float *>(scr_b + a3.w) = csum;
+							csum = 0.f;
+						}
+					}
+				}
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&empty_h[hst]);
+				// ---- accumulator -> registers, slot released right away (to the leader's barrier: its MMA warp overwrites both CTAs' slots)
+				tc2::wait(&tm_full[slot], (it_s / T2_SLOTS) & 1);
+				tc2::fence_after();
+				float v[32];
+				tc2::ld32(lane_base + (uint32_t)(slot * TC_NB + cg * 32), v);
+				tc2::fence_before();
+				__syncwarp();
+				if (lane == 0) tc2::arrive_cluster(tm_empty_leader + 8u * (uint32_t)slot);
+				// ---- add-back, phase 2: only the flagged columns have a (fresh) scratch value
+				if (mask) {
+#pragma unroll
+					for (int j = 0; j < 32; ++j)
+						if (mask & (1u << j)) v[j] -= my_scr[j * 32];
+				}
+				// ---- columns beyond a speaker's mixtures (row padding) take no part in the sum
+				if (vmask != 0xffffffffu) {
+#pragma unroll
+					for (int j = 0; j < 32; ++j)
+						if (!(vmask & (1u << j))) v[j] = -INFINITY;
+				}
+				// column segmentation: seg >= 128 -> the block belongs to one speaker (quarter-wide merge at its end); seg == 64 ->
+				// two speakers per block, two warps each; seg == 32 -> every warp's group is its own speaker
+				tc2_lse_update(v, m_run, s_run);
+				if (seg == 32) {
+					finish(spk + cg, 1);
+					spk += 4;
+				} else if (seg == 64) {
+					finish(spk + (cg >> 1), 2);
+					spk += 2;
+				} else {
+					col_in_spk += TC_NB;
+					if (col_in_spk == cols_per_spk) {
+						finish(spk, 4);
+						col_in_spk = 0;
+						++spk;
+					}
+				}
+			}
+		}
+#undef SRB_TC2_QBAR
+	}
+	tc2::fence_before();
+	__syncthreads();
+	tc2::cluster_sync_all();           // the peer's tensor memory and barriers stay alive until the leader's last MMA / commit has landed
+	if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+}  // namespace srb

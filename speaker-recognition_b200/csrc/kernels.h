@@ -16,6 +16,11 @@ bool tc_supported(const PackedModels &pm, int D);
 int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, double *d_partial, float *d_frame_ll,
                     int ldf, int clamp, int frame_log2, cudaStream_t st);
 
+// ---- gmm_score_tc2.cu: tensor-core route, second generation (tcgen05 cta_group::2, 3xFP16) ----
+bool tc2_supported(const PackedModels &pm, int D);
+int launch_score_tc2(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, double *d_partial, float *d_frame_ll,
+                     int ldf, int clamp, int frame_log2, cudaStream_t st);
+
 // ---- gmm_em.cu ----
 // stats (float64): [K] N_k | [K*D] sum g x | [K*D] sum g x^2 | [1] sum log p | [1] frames used
 static inline int em_stats_len(int K, int D) { return K + 2 * K * D + 2; }
