@@ -9,7 +9,7 @@ static bool g_tc2_attr = false;
 static size_t tc2_smem_bytes_n(int Kp, int D, int nst) {
 	// half-block stages (head | tail: 256 Kp bytes) + hard-entry ring + add-back scratch [16][32][32] + merge buffers [2][3][128] float2 +
 	// mbarriers / TMEM slot word (512 B) + x'' tile [128][D|1]
-	return (size_t)nst * 4 * T2_NH * Kp + (size_t)TC_HSTAGES * TC_HSTRIDE * 16 + 16 * 32 * 32 * sizeof(float) + 2 * 3 * TC_M * 8 + 512 +
+	return (size_t)nst * 4 * T2_NH * Kp + (size_t)T2_HSTAGES * TC_HSTRIDE * 16 + 16 * 32 * 32 * sizeof(float) + 2 * 3 * TC_M * 8 + 512 +
 	       (size_t)TC_M * tc_x_stride(D) * sizeof(float);
 }
 

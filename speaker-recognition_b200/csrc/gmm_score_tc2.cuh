@@ -75,31 +75,17 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
 	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
 	return r;
 }
-// arrive on a barrier of the LEADER CTA (works from either CTA of the pair: `addr` is a shared::cluster address)
+// arrive on a barrier of the LEADER CTA (works from either CTA of the pair: `addr` is a shared::cluster address).  Default
+// semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) uses for the same hand-overs: what is handed over
+// lives in tensor memory / was written by the TMA engine and is ordered by the tcgen05 fences and the mbarrier itself -- a
+// `.release.cluster` here compiles to MEMBAR.ALL.GPU in front of EVERY arrive (measured: the kernel ran at 4300 cycles per block).
 __device__ __forceinline__ void arrive_cluster(uint32_t addr) {
-	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
-}
-__device__ __forceinline__ bool try_wait_cluster(uint64_t *bar, uint32_t parity) {
-	uint32_t ok;
-	asm volatile(
-	    "{\n\t.reg .pred p;\n\t"
-	    "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-	    "selp.u32 %0, 1, 0, p;\n\t}"
-	    : "=r"(ok)
-	    : "r"(smem_u32(bar)), "r"(parity)
-	    : "memory");
-	return ok != 0;
+	asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 // bounded waits: a broken pipeline traps instead of hanging the GPU
 __device__ __forceinline__ void wait(uint64_t *bar, uint32_t parity) {
 	long long spins = 0;
 	while (!mbar_try_wait(bar, parity)) {
-		if (++spins > 400000000LL) __trap();
-	}
-}
-__device__ __forceinline__ void wait_cluster(uint64_t *bar, uint32_t parity) {
-	long long spins = 0;
-	while (!try_wait_cluster(bar, parity)) {
 		if (++spins > 400000000LL) __trap();
 	}
 }
@@ -201,13 +187,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 	const uint32_t stage_bytes = 2 * part_bytes;
 	const int NST = A.bstages;
 	unsigned char *sB = tc2_smem;                                                               // [NST] stages: head | tail of this CTA's half block
-	int4 *hring = reinterpret_cast<int4 *>(sB + (size_t)NST * stage_bytes);                    // [TC_HSTAGES][TC_HSTRIDE] hard-entry lists
-	float *scr = reinterpret_cast<float *>(hring + TC_HSTAGES * TC_HSTRIDE);                    // [16 warps][32 columns][32 lanes] add-back sums
+	int4 *hring = reinterpret_cast<int4 *>(sB + (size_t)NST * stage_bytes);                    // [T2_HSTAGES][TC_HSTRIDE] hard-entry lists
+	float *scr = reinterpret_cast<float *>(hring + T2_HSTAGES * TC_HSTRIDE);                    // [16 warps][32 columns][32 lanes] add-back sums
 	float2 *ms_x = reinterpret_cast<float2 *>(scr + 16 * 32 * 32);                              // [2][3][128] (m, s) handed to the merging warp
 	uint64_t *bars = reinterpret_cast<uint64_t *>(ms_x + 2 * 3 * TC_M);
 	uint64_t *full_b = bars, *peer_full = full_b + T2_BSTAGES_MAX, *empty_b = peer_full + T2_BSTAGES_MAX;
-	uint64_t *full_h = empty_b + T2_BSTAGES_MAX, *empty_h = full_h + TC_HSTAGES;
-	uint64_t *tm_full = empty_h + TC_HSTAGES, *tm_empty = tm_full + T2_SLOTS;
+	uint64_t *full_h = empty_b + T2_BSTAGES_MAX, *empty_h = full_h + T2_HSTAGES;
+	uint64_t *tm_full = empty_h + T2_HSTAGES, *tm_empty = tm_full + T2_SLOTS;
 	uint64_t *a_ready = tm_empty + T2_SLOTS;
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
 	float *sX = reinterpret_cast<float *>(bars + 64);                                           // [128][XS] x'' of the unit's tile
@@ -221,7 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 			mbar_init(&peer_full[s], 1);
 			mbar_init(&empty_b[s], 1);
 		}
-		for (int s = 0; s < TC_HSTAGES; ++s) {
+		for (int s = 0; s < T2_HSTAGES; ++s) {
 			mbar_init(&full_h[s], 1);
 			mbar_init(&empty_h[s], 16);      // one arrival per epilogue warp of this CTA
 		}
@@ -258,8 +244,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
 				for (int b = blk0; b < blk1; ++b, ++it_h) {
 					{   // the block's hard-entry list (needed first: the epilogue walks it while the block's MMAs run)
-						const int st = it_h % TC_HSTAGES;
-						tc2::wait(&empty_h[st], ((it_h / TC_HSTAGES) & 1) ^ 1);
+						const int st = it_h % T2_HSTAGES;
+						tc2::wait(&empty_h[st], ((it_h / T2_HSTAGES) & 1) ^ 1);
 						mbar_expect_tx(&full_h[st], TC_HSTRIDE * 16);
 						bulk_g2s(hring + (size_t)st * TC_HSTRIDE, A.hard + (size_t)b * TC_HSTRIDE, TC_HSTRIDE * 16, &full_h[st]);
 					}
@@ -310,14 +296,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 			const int chunk = u % A.n_chunks;
 			const int blk0 = chunk * blocks_per_chunk_full;
 			const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
-			tc2::wait_cluster(a_ready, it_a & 1);            // PHI of both CTAs' tiles is in tensor memory
+			tc2::wait(a_ready, it_a & 1);            // PHI of both CTAs' tiles is in tensor memory
 			tc2::fence_after();
 			for (int b = blk0; b < blk1; ++b, ++it_s) {
 				const int slot = it_s % T2_SLOTS;
-				tc2::wait_cluster(&tm_empty[slot], ((it_s / T2_SLOTS) & 1) ^ 1);
+				tc2::wait(&tm_empty[slot], ((it_s / T2_SLOTS) & 1) ^ 1);
 				const int st = st_b;
 				tc2::wait(&full_b[st], ph_b);
-				tc2::wait_cluster(&peer_full[st], ph_b);
+				tc2::wait(&peer_full[st], ph_b);
 				tc2::fence_after();
 				const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TC_NB);
 				const uint32_t dB0 = ((smem_u32(sB + (size_t)st * stage_bytes) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
@@ -441,11 +427,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 			};
 
 			for (int b = blk0; b < blk1; ++b, ++it_s, ++it_h) {
-				const int slot = it_s % T2_SLOTS, hst = it_h % TC_HSTAGES;
+				const int slot = it_s % T2_SLOTS, hst = it_h % T2_HSTAGES;
 				// ---- exact add-back, phase 1 (the block's MMAs are still running): sum t^2 of this warp's hard entries per column --
 				// the list is uniform across the warp, sorted by column, `last` flag on a column's final entry -- and park each
 				// column's sum in the warp's scratch row (a dynamic column index cannot address registers).
-				tc2::wait(&full_h[hst], (it_h / TC_HSTAGES) & 1);
+				tc2::wait(&full_h[hst], (it_h / T2_HSTAGES) & 1);
 				const int4 *hl = hring + (size_t)hst * TC_HSTRIDE;
 				const int4 hmask = hl[0], hoff = hl[1], hval = hl[2];
 				const int e0 = cg == 0 ? 0 : (cg == 1 ? hoff.x : (cg == 2 ? hoff.y : hoff.z));

@@ -19,7 +19,7 @@ constexpr float TC_LN2 = 0.69314718055994531f;
 constexpr int TC_HHEAD = 3;          // header words of a block's hard-entry list: [0] bit masks of the columns with entries in the four 32-column groups,
                                      // [1] {first entry of group 1, of group 2, of group 3, total}, [2] bit masks of the VALID columns (rows that are real
                                      // mixtures, not speaker padding) of the four groups
-constexpr int TC_HSTRIDE = TC_HHEAD + 204;  // int4 per block: header + up to 204 hard entries (incl. the x4 padding of the four groups); entries sorted by
+constexpr int TC_HSTRIDE = TC_HHEAD + 125;  // int4 per block (2 KB): header + up to 125 hard entries (incl. the x4 padding of the four groups); entries sorted by
                                      // column, every group padded to a multiple of 4 with null entries: {4 * dim, float bits of a'', of nb'', last entry of
                                      // its column ? 1 + 128 * (column within the group) : 0}
 constexpr double TC_HARD_BUDGET = 1000.0;   // per mixture row: sum over the dims left in the GEMM of nb''^2 (the magnitude the expanded square cancels at);
@@ -32,6 +32,8 @@ constexpr int T2_SLOTS = 3;          // TMEM accumulator slots: columns [0, 384)
 constexpr int T2_A_COL = 384;        // TMEM columns [384, 384 + Kp/2): PHI head (two fp16 per column), [384 + Kp/2, 384 + Kp): PHI tail
 constexpr int T2_KP_MAX = 128;       // 2 D + 1 <= 127
 constexpr int T2_BSTAGES_MAX = 6;    // ring of half-block stages (head | tail image of 64 rows: 256 Kp bytes)
+constexpr int T2_HSTAGES = 8;        // ring of per-block hard-entry lists: the producer runs this many blocks ahead of the SLOWEST epilogue warp, and the
+                                     // epilogue may lag the MMA warp by the three accumulator slots -- the B loads need the difference to cover the L2 latency
 constexpr int T2_THREADS = 576;      // producer warp, MMA / relay warp, 16 epilogue warps
 constexpr float T2_X_CLAMP = 240.f;  // |x''| bound before squaring (fp16 max 65504)
 constexpr double T2_W_MAX = 60000.0; // |W| bound of an fp16 image entry; larger terms are added back exactly instead
