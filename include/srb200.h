@@ -84,6 +84,10 @@ int srb200_set_score_path(int path);
 int srb200_get_score_path(void);
 int srb200_last_score_route(void);
 int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int *hard_entries_out, int *max_hard_per_block_out);
+/* the packed operands of route 1 (host only): info_out[8] = {Kp, blocks, columns per speaker, halfs per block, ints per block
+ * list, header words, 0, 0}; arrays copied when non-NULL (blocks * info[3] uint16, blocks * info[4] int32, 2 * dim float).
+ * Layouts: speaker-recognition_b200/csrc/gmm_score_tc_layout.h.  Used by the CPU emulation test of the packer. */
+int srb200_tc_pack_export(GMM *const *models, int n_models, int *info_out, uint16_t *images_out, int *hard_out, float *cs_out);
 
 int srb200_gmm_set_params(GMM *gmm, int nr_mixture, int dim, const double *weights, const double *means, const double *sigmas); /* means,sigmas [K*D]; sigma = std-dev (gmm.hh:31) */
 int srb200_gmm_get_params(GMM *gmm, double *weights, double *means, double *sigmas);

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "srb200_get_score_path": (_ci, []),
     "srb200_last_score_route": (_ci, []),
     "srb200_tc_pack_stats": (_ci, [C.POINTER(_vp), _ci, _ip, _ip, _ip]),
+    "srb200_tc_pack_export": (_ci, [C.POINTER(_vp), _ci, _ip, C.POINTER(C.c_uint16), _ip, _fp]),
     "srb200_gmm_set_params": (_ci, [_vp, _ci, _ci, _dp, _dp, _dp]),
     "srb200_gmm_get_params": (_ci, [_vp, _dp, _dp, _dp]),
     "srb200_gmm_dump_precise": (_ci, [_vp, C.c_char_p, _ci]),

@@ -88,16 +88,13 @@ int Context::init() {
 }
 
 void PackedModels::release_tc() {
-	if (d_tc) cudaFree(d_tc);
 	if (d_tc_hard) cudaFree(d_tc_hard);
 	if (d_tc_cs) cudaFree(d_tc_cs);
 	if (d_tc2) cudaFree(d_tc2);
 	d_tc2 = nullptr;
 	h_tc2.clear();
-	d_tc = nullptr;
 	d_tc_hard = nullptr;
 	d_tc_cs = nullptr;
-	h_tc.clear();
 	h_tc_hard.clear();
 	h_tc_cs.clear();
 	tc_built = false;
@@ -111,33 +108,32 @@ void PackedModels::release() {
 	S = 0;
 }
 
-// Tensor-core weight images (gmm_score_tc.cuh).  Features are transformed per dimension, x'' = (x - c_d) alpha_d, with c_d the
+// Tensor-core weight images (gmm_score_tc2.cuh).  Features are transformed per dimension, x'' = (x - c_d) alpha_d, with c_d the
 // weighted mean of the set's means and alpha_d the power of two nearest to 1 / (the set's overall standard deviation in d), so
 // that the expanded square works on unit-scale, centred numbers whatever the feature's own scale is (MFCC after CMVN ~ 1, LPC
 // coefficients ~ 0.05: the shipped 34-dim UBMs).  Row r of speaker s holds W = [-a''^2 (D), -2 a'' nb'' (D), C, 0-pad] with
 // a'' = sqrt(log2e/2) / (sigma alpha), nb'' = -(mean - c) alpha a'', C = log2 w - sum log2(sqrt(2pi) sigma) - sum nb''^2; each
-// value is split into a TF32-representable hi part and the fp32 remainder lo.  The expanded form cancels where |nb''| is large
-// (error ~ eps * nb''^2 per term and the fp32 accumulator works at magnitude sum nb''^2): per row, the dimensions with the
-// largest nb''^2 are taken out of W and C until the remaining sum is below TC_HARD_BUDGET, and are added back exactly by the
-// epilogue (t = a'' x'' + nb'', l -= t^2).  Speakers are padded to 32 / 64 / multiples of 128 rows.
+// value is split by round-to-nearest into an fp16 head and an fp16 tail.  The expanded form cancels where |nb''| is large (error
+// ~ eps * nb''^2 per term, and the fp32 accumulator works at magnitude sum nb''^2): per row, the dimensions with the largest
+// nb''^2 are taken out of W and C until the remaining sum is below TC_HARD_BUDGET, and are added back exactly by the epilogue
+// (t = a'' x'' + nb'', l -= t^2).  Speakers are padded to 32 / 64 / multiples of 128 rows; inside every 32-column group the rows
+// that carry such entries are placed FIRST (a log-sum-exp does not care about the order of its terms), so the epilogue's
+// correction is a prefix of the group's columns.
 void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *const *weights, const double *const *means,
                          const double *const *sigmas, const int *Ks) {
-	const int Kp = ((2 * D + 1 + 7) / 8) * 8;
 	const int NB = TC_NB;
 	const int cols = K <= 32 ? 32 : (K <= 64 ? 64 : ((K + NB - 1) / NB) * NB);
 	const long long rows_total = (long long)S * cols;
 	const int blocks = (int)((rows_total + NB - 1) / NB);
-	const size_t bf = tc_b_block_floats(Kp);
 	pm.release_tc();
 	pm.tc_built = true;
-	pm.h_tc.assign((size_t)blocks * bf, 0.f);
 	const int Kp2 = t2_kp(D);
-	const size_t bh = t2_block_halfs(Kp2);
-	if (Kp2 <= T2_KP_MAX) pm.h_tc2.assign((size_t)blocks * bh, 0);
 	pm.tc2_Kp = Kp2;
-	pm.tc_Kp = Kp;
 	pm.tc_cols_per_spk = cols;
 	pm.tc_blocks_total = blocks;
+	if (Kp2 > T2_KP_MAX) return;                   // 2 D + 1 > 127: PHI does not fit beside the accumulator slots -> FMA route
+	const size_t bh = t2_block_halfs(Kp2);
+	pm.h_tc2.assign((size_t)blocks * bh, 0);
 	const double A0 = 0.84932180028801904272;
 	double BUDGET = TC_HARD_BUDGET;
 	if (const char *eh = getenv("SRB200_TC_HARD_BUDGET")) BUDGET = atof(eh);   // experiments: a huge value disables the add-back list
@@ -172,95 +168,97 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 			pm.h_tc_cs[D + d] = (float)alpha[d];
 		}
 	}
-	// hard-entry lists (layout: TcArgs::hard).  Rows ascend, so each group's list is sorted by column.
+	// image writer: block blk, column col (0..127), k -> fp16 head + fp16 tail, both round-to-nearest (22 significant bits, unbiased);
+	// the CTA of the pair that holds the row is col >> 6
+	auto put = [&](int blk, int col, int k, double w) {
+		const double wc = std::max(-T2_W_MAX, std::min(T2_W_MAX, w));
+		const __half h = __float2half_rn((float)wc);
+		const __half l = __float2half_rn((float)(wc - (double)__half2float(h)));
+		const size_t base = (size_t)blk * bh + (size_t)(col >> 6) * 2 * T2_NH * Kp2 + t2_img_off(col & 63, k);
+		pm.h_tc2[base] = __half_as_ushort(h);
+		pm.h_tc2[base + (size_t)T2_NH * Kp2] = __half_as_ushort(l);
+	};
+	// hard-entry lists (layout: gmm_score_tc_layout.h)
 	pm.h_tc_hard.assign((size_t)blocks * 4 * TC_HSTRIDE, 0);
 	struct HardEntry { int x; float a, nb; int w; };
-	std::vector<std::vector<HardEntry>> groups((size_t)blocks * 4);
+	struct RowPlan { bool real; double C; std::vector<double> av, nbv; std::vector<char> hard; int n_hard; };
 	bool overflow = false;
-	auto put = [&](long long row, int k, double w) {
-		const int blk = (int)(row / NB), r = (int)(row % NB);
-		const float wf = (float)w;
-		uint32_t u;
-		memcpy(&u, &wf, 4);
-		u &= ~0x1FFFu;
-		float hi;
-		memcpy(&hi, &u, 4);
-		const float lo = (float)(w - (double)hi);
-		const size_t off = tc_img_off(NB, r, k);
-		pm.h_tc[(size_t)blk * bf + off] = hi;
-		pm.h_tc[(size_t)blk * bf + (size_t)NB * Kp + off] = lo;
-		if (!pm.h_tc2.empty()) {
-			// fp16 head + fp16 tail, both round-to-nearest (22 significant bits, unbiased); rank = which CTA of the pair holds the row
-			const double wc = std::max(-T2_W_MAX, std::min(T2_W_MAX, w));
-			const __half h = __float2half_rn((float)wc);
-			const __half l = __float2half_rn((float)(wc - (double)__half2float(h)));
-			const size_t base = (size_t)blk * bh + (size_t)(r >> 6) * 2 * T2_NH * Kp2 + t2_img_off(r & 63, k);
-			pm.h_tc2[base] = __half_as_ushort(h);
-			pm.h_tc2[base + (size_t)T2_NH * Kp2] = __half_as_ushort(l);
-		}
-	};
-	std::vector<double> av(D), nbv(D);
 	std::vector<int> order(D);
-	std::vector<char> is_hard(D);
-	for (long long row = 0; row < (long long)blocks * NB; ++row) {
-		const int s = (int)(row / cols), k = (int)(row % cols);
-		const int blk = (int)(row / NB), col = (int)(row % NB);
-		if (s < S && k < Ks[s]) {
-			const double *mu = means[s] + (size_t)k * D, *sg = sigmas[s] + (size_t)k * D;
-			double C = weights[s][k] > 0.0 ? log2(weights[s][k]) : -1.0e30;
-			double tot = 0.0;
-			for (int d = 0; d < D; ++d) {
-				av[d] = A0 / (sg[d] * alpha[d]);
-				nbv[d] = -(mu[d] - cen[d]) * alpha[d] * av[d];
-				C -= log2(2.5066282746310002 * sg[d]);
-				tot += nbv[d] * nbv[d];
-				order[d] = d;
-				is_hard[d] = 0;
-				if (av[d] * av[d] > T2_W_MAX || fabs(2.0 * av[d] * nbv[d]) > T2_W_MAX) {     // outside the fp16 image's range: exact path
-					is_hard[d] = 1;
-					tot -= nbv[d] * nbv[d];
-				}
-			}
-			if (tot > BUDGET) {
-				std::sort(order.begin(), order.end(), [&](int x, int y) { return nbv[x] * nbv[x] > nbv[y] * nbv[y]; });
-				for (int i = 0; i < D && tot > BUDGET; ++i) {
-					if (is_hard[order[i]]) continue;
-					is_hard[order[i]] = 1;
-					tot -= nbv[order[i]] * nbv[order[i]];
-				}
-			}
-			std::vector<HardEntry> &g = groups[(size_t)blk * 4 + (col >> 5)];
-			bool any = false;
-			for (int d = 0; d < D; ++d) {
-				if (is_hard[d]) {
-					// kept out of the GEMM (its three large terms would cancel): exact add-back entry for the epilogue
-					g.push_back({4 * d, (float)av[d], (float)nbv[d], 0});
-					any = true;
-				} else {
-					put(row, d, -av[d] * av[d]);
-					put(row, D + d, -2.0 * av[d] * nbv[d]);
-					C -= nbv[d] * nbv[d];
-				}
-			}
-			if (any) g.back().w = 1 + 128 * (col & 31);      // last entry of this column: flush the sum to scratch column col & 31
-			put(row, 2 * D, (C < -1.0e30 || C != C) ? -1.0e30 : C);
-			pm.h_tc_hard[((size_t)blk * TC_HSTRIDE + 2) * 4 + (col >> 5)] |= (int)(1u << (col & 31));      // header word 2: valid columns
-		} else {
-			put(row, 2 * D, -1.0e30);      // padded row: exp2 underflows to exactly 0
-		}
-	}
 	for (int blk = 0; blk < blocks && !overflow; ++blk) {
 		int *hdr = pm.h_tc_hard.data() + (size_t)blk * TC_HSTRIDE * 4;
-		int pos = 0;
-		for (int gi = 0; gi < 4; ++gi) {
-			std::vector<HardEntry> &g = groups[(size_t)blk * 4 + gi];
-			for (const HardEntry &he : g)
-				if (he.w) hdr[gi] |= (int)(1u << (((he.w - 1) / 128) & 31));
+		int pos = 0;                                    // entries of this block so far
+		for (int gi = 0; gi < 4 && !overflow; ++gi) {
+			RowPlan rp[32];
+			for (int j = 0; j < 32; ++j) {
+				const long long row = (long long)blk * NB + gi * 32 + j;
+				const int s = (int)(row / cols), k = (int)(row % cols);
+				RowPlan &r = rp[j];
+				r.real = s < S && k < Ks[s];
+				r.n_hard = 0;
+				if (!r.real) continue;
+				const double *mu = means[s] + (size_t)k * D, *sg = sigmas[s] + (size_t)k * D;
+				r.av.resize(D), r.nbv.resize(D), r.hard.assign(D, 0);
+				double C = weights[s][k] > 0.0 ? log2(weights[s][k]) : -1.0e30, tot = 0.0;
+				for (int d = 0; d < D; ++d) {
+					r.av[d] = A0 / (sg[d] * alpha[d]);
+					r.nbv[d] = -(mu[d] - cen[d]) * alpha[d] * r.av[d];
+					C -= log2(2.5066282746310002 * sg[d]);
+					order[d] = d;
+					if (r.av[d] * r.av[d] > T2_W_MAX || fabs(2.0 * r.av[d] * r.nbv[d]) > T2_W_MAX) r.hard[d] = 1;   // outside the fp16 image's range
+					else tot += r.nbv[d] * r.nbv[d];
+				}
+				if (tot > BUDGET) {
+					std::sort(order.begin(), order.end(), [&](int x, int y) { return r.nbv[x] * r.nbv[x] > r.nbv[y] * r.nbv[y]; });
+					for (int i = 0; i < D && tot > BUDGET; ++i) {
+						if (r.hard[order[i]]) continue;
+						r.hard[order[i]] = 1;
+						tot -= r.nbv[order[i]] * r.nbv[order[i]];
+					}
+				}
+				for (int d = 0; d < D; ++d) {
+					if (r.hard[d]) ++r.n_hard;
+					else C -= r.nbv[d] * r.nbv[d];
+				}
+				r.C = (C < -1.0e30 || C != C) ? -1.0e30 : C;
+			}
+			// rows with exact entries first (stable), then the others, padding rows last
+			int perm[32], np = 0, nflag = 0;
+			for (int j = 0; j < 32; ++j)
+				if (rp[j].real && rp[j].n_hard > 0) perm[np++] = j;
+			nflag = np;
+			for (int j = 0; j < 32; ++j)
+				if (rp[j].real && rp[j].n_hard == 0) perm[np++] = j;
+			for (int j = 0; j < 32; ++j)
+				if (!rp[j].real) perm[np++] = j;
+			std::vector<HardEntry> g;
+			for (int p = 0; p < 32; ++p) {
+				const RowPlan &r = rp[perm[p]];
+				const int col = gi * 32 + p;
+				if (!r.real) {
+					put(blk, col, 2 * D, -T2_W_MAX);        // padded row; its column is masked out by header word 2 anyway
+					continue;
+				}
+				hdr[8 + gi] |= (int)(1u << p);              // header word 2: valid columns
+				for (int d = 0; d < D; ++d) {
+					if (r.hard[d]) {
+						g.push_back({4 * d, (float)r.av[d], (float)r.nbv[d], 0});
+					} else {
+						put(blk, col, d, -r.av[d] * r.av[d]);
+						put(blk, col, D + d, -2.0 * r.av[d] * r.nbv[d]);
+					}
+				}
+				if (r.n_hard > 0) g.back().w = 1 + 4 * p;   // last entry of this column: flush the sum to scratch slot p
+				put(blk, col, 2 * D, r.C);
+			}
+			// the epilogue corrects whole groups of four columns: null entries flush a zero into the unused slots of the last group
+			const int nflag4 = (nflag + 3) & ~3;
+			for (int p = nflag; p < nflag4; ++p) g.push_back({0, 0.f, 0.f, 1 + 4 * p});
 			while (g.size() % 4) g.push_back({0, 0.f, 0.f, 0});          // null entries: t = 0, no flush
-			if (pos + (int)g.size() > TC_HSTRIDE - TC_HHEAD) {
+			if (nflag4 > T2_MAX_FLAGGED || pos + (int)g.size() > TC_HSTRIDE - TC_HHEAD) {
 				overflow = true;
 				break;
 			}
+			hdr[gi] = nflag4;                               // header word 0: flagged columns of the group (its first nflag4)
 			for (const HardEntry &he : g) {
 				int *e = hdr + (size_t)(TC_HHEAD + pos) * 4;
 				e[0] = he.x;
@@ -269,12 +267,11 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 				e[3] = he.w;
 				++pos;
 			}
-			if (gi < 3) hdr[4 + gi] = pos;      // first entry of the next group
+			if (gi < 3) hdr[4 + gi] = pos;                  // header word 1: first entry of the next group
 		}
 		hdr[7] = pos;
 	}
 	if (overflow) {      // too many cancelling entries for the sparse list: this model set stays on the FMA route
-		pm.h_tc.clear();
 		pm.h_tc2.clear();
 		pm.h_tc_hard.clear();
 		pm.h_tc_cs.clear();
@@ -736,7 +733,7 @@ int srb200_set_compat_clamp(int mode) {
 int srb200_get_compat_clamp(void) { return ctx().compat_clamp; }
 int srb200_set_score_path(int path) {
 	API_ENTER();
-	SRB_REQUIRE(path >= -1 && path <= 2, "score path must be -1 (default), 0 (fp32 FMA), 1 (tcgen05 3xFP16 on CTA pairs) or 2 (round-1 tcgen05 3xTF32)");
+	SRB_REQUIRE(path >= -1 && path <= 1, "score path must be -1 (default), 0 (fp32 FMA) or 1 (tcgen05 3xFP16 on CTA pairs)");
 	ctx().score_path = path;
 	return 0;
 }
@@ -1012,12 +1009,12 @@ srb200_gmmset *srb200_gmmset_create(GMM *const *models, int n_models) {
 	return set;
 }
 
-// host-only diagnostic: would this model set take the tensor-core route, and with how many exact add-back entries?
-// (runs the packer on temporary host buffers; no device work, usable without a GPU)
-int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int *hard_out, int *max_hard_per_block_out) {
-	API_ENTER();
+// host-only diagnostics of the tensor-core route (no device work, usable without a GPU): run the packer on temporary host
+// buffers.  srb200_tc_pack_stats: is the set eligible, and with how many exact add-back entries?  srb200_tc_pack_export: the
+// packed operands themselves (what the kernel will read), for the CPU emulation in tests/test_tc_pack_cpu.py.
+static int tc_pack_tmp(GMM *const *models, int n_models, PackedModels &pm, int *D_out) {
 	if (!models || n_models < 1) {
-		set_error("tc_pack_stats: no models");
+		set_error("tc_pack: no models");
 		return -1;
 	}
 	int K = 0, D = 0;
@@ -1026,7 +1023,7 @@ int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int 
 	for (int i = 0; i < n_models; ++i) {
 		GMM *g = models[i];
 		if (!g || g->host_stale || (int)g->weights.size() != g->nr_mixtures || g->dim < 1 || (i > 0 && g->dim != D)) {
-			set_error("tc_pack_stats: model %d has no host parameters or a different dimension", i);
+			set_error("tc_pack: model %d has no host parameters or a different dimension", i);
 			return -1;
 		}
 		D = g->dim;
@@ -1036,10 +1033,18 @@ int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int 
 		m[i] = g->means.data();
 		s[i] = g->sigmas.data();
 	}
-	PackedModels pm;
 	pack_models_tc_host(pm, n_models, K, D, w.data(), m.data(), s.data(), Ks.data());
 	pm.S = n_models;
-	const bool ok = tc2_supported(pm, D);
+	*D_out = D;
+	return tc2_supported(pm, D) ? 1 : 0;
+}
+
+int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int *hard_out, int *max_hard_per_block_out) {
+	API_ENTER();
+	PackedModels pm;
+	int D = 0;
+	const int ok = tc_pack_tmp(models, n_models, pm, &D);
+	if (ok < 0) return ok;
 	int hard = 0, mx = 0;
 	if (ok)
 		for (int b = 0; b < pm.tc_blocks_total; ++b) {
@@ -1052,7 +1057,25 @@ int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int 
 	if (blocks_out) *blocks_out = pm.tc_blocks_total;
 	if (hard_out) *hard_out = hard;
 	if (max_hard_per_block_out) *max_hard_per_block_out = mx;
-	return ok ? 1 : 0;
+	return ok;
+}
+
+// info_out[8] = {Kp, blocks, columns per speaker, halfs per block, ints per block list, header words, 0, 0}; the arrays are
+// copied when non-NULL (sizes: blocks * info[3] uint16, blocks * info[4] int32, 2 * D float)
+int srb200_tc_pack_export(GMM *const *models, int n_models, int *info_out, uint16_t *images_out, int *hard_out, float *cs_out) {
+	API_ENTER();
+	PackedModels pm;
+	int D = 0;
+	const int ok = tc_pack_tmp(models, n_models, pm, &D);
+	if (ok <= 0) return ok;
+	if (info_out) {
+		const int info[8] = {pm.tc2_Kp, pm.tc_blocks_total, pm.tc_cols_per_spk, (int)t2_block_halfs(pm.tc2_Kp), TC_HSTRIDE * 4, TC_HHEAD, 0, 0};
+		memcpy(info_out, info, sizeof info);
+	}
+	if (images_out) memcpy(images_out, pm.h_tc2.data(), pm.h_tc2.size() * sizeof(uint16_t));
+	if (hard_out) memcpy(hard_out, pm.h_tc_hard.data(), pm.h_tc_hard.size() * sizeof(int));
+	if (cs_out) memcpy(cs_out, pm.h_tc_cs.data(), pm.h_tc_cs.size() * sizeof(float));
+	return 1;
 }
 
 void srb200_gmmset_free(srb200_gmmset *set) {

@@ -520,8 +520,8 @@ int launch_pack_from_master(const double *d_params, int K, int D, PackedModels &
 	}
 	// the tensor-core images (built on the host from the PREVIOUS parameters) no longer describe this model: drop them, so that
 	// scoring falls back to the FMA tiles written below until gmm_ensure_packed rebuilds the images from the pulled master
-	if (pm.tc_built || pm.d_tc) {
-		if (pm.d_tc) SRB_CUDA(cudaStreamSynchronize(st));      // a scoring launch may still be reading the device images
+	if (pm.tc_built || pm.d_tc2) {
+		if (pm.d_tc2) SRB_CUDA(cudaStreamSynchronize(st));      // a scoring launch may still be reading the device images
 		pm.release_tc();
 	}
 	pm.S = 1;

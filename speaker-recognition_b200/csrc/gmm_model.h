@@ -28,17 +28,15 @@ struct PackedModels {             // device-resident packed parameters of S mode
 	int S = 0, K = 0, Kpad = 0, D = 0, tiles_per_model = 0;
 	float *d_tiles = nullptr;     // S * tiles_per_model * tile_floats(D)
 	size_t bytes = 0;
-	// tensor-core path (gmm_score_tc.cuh): weight images [blocks][hi|lo][128*Kp], built on the host with the FMA tiles
-	std::vector<float> h_tc;      // host image, uploaded on first use
-	std::vector<int> h_tc_hard;   // per block: 4*TC_HSTRIDE ints (two header words + hard entries), see gmm_score_tc.cuh
-	std::vector<uint16_t> h_tc2;  // second-generation images (gmm_score_tc2.cuh): fp16 head/tail, [blocks][2 ranks][head | tail][64 * Kp16]
+	// tensor-core path (gmm_score_tc2.cuh), built on the host with the FMA tiles, uploaded on first use
+	std::vector<uint16_t> h_tc2;  // weight images: fp16 head/tail, [blocks][2 ranks][head | tail][64 * Kp]
+	std::vector<int> h_tc_hard;   // per block: 4*TC_HSTRIDE ints (header + hard entries), see gmm_score_tc_layout.h
 	void *d_tc2 = nullptr;
 	int tc2_Kp = 0;
 	std::vector<float> h_tc_cs;   // [2][D]: per-dimension centre c_d and power-of-two scale alpha_d of the feature transform x'' = (x - c) alpha
-	float *d_tc = nullptr;
 	int *d_tc_hard = nullptr;
 	float *d_tc_cs = nullptr;
-	int tc_Kp = 0, tc_cols_per_spk = 0, tc_blocks_total = 0;
+	int tc_cols_per_spk = 0, tc_blocks_total = 0;
 	bool tc_built = false;        // the tensor-core images describe the CURRENT parameters (possibly empty: set not supported)
 	void release();
 	void release_tc();            // drop the tensor-core images (host and device); the FMA tiles stay

@@ -470,15 +470,6 @@ int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *ut
 		SRB_CUDA(cudaGetLastError());
 		return 0;
 	}
-	if (path == 2 && !frame_log2 && tc_supported(pm, D)) {      // round-1 kernel (single CTA, 3xTF32): kept for A/B measurements
-		c.last_score_route = 2;
-		TileTable *tt = nullptr;
-		if (get_table(utt_off, n_utt, pm.S, 128, st, &tt)) return 1;
-		if (launch_score_tc(pm, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;
-		score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, 4, d_sums, d_best);
-		SRB_CUDA(cudaGetLastError());
-		return 0;
-	}
 	int warps = g_score_scalar ? 4 : g_score_warps;
 	if (score_smem_bytes(D, warps * 64) > 113 * 1024) warps = 4;   // 8-warp CTAs need two per SM
 	const int FT = warps * 64;

@@ -7,10 +7,10 @@ namespace srb {
 static bool g_tc2_attr = false;
 
 static size_t tc2_smem_bytes_n(int Kp, int D, int nst) {
-	// half-block stages (head | tail: 256 Kp bytes) + hard-entry ring + add-back scratch [16][32][32] + merge buffers [2][3][128] float2 +
-	// mbarriers / TMEM slot word (512 B) + x'' tile [128][D|1]
-	return (size_t)nst * 4 * T2_NH * Kp + (size_t)T2_HSTAGES * TC_HSTRIDE * 16 + 16 * 32 * 32 * sizeof(float) + 2 * 3 * TC_M * 8 + 512 +
-	       (size_t)TC_M * tc_x_stride(D) * sizeof(float);
+	// half-block stages (head | tail: 256 Kp bytes) + hard-entry ring + add-back scratch [16][32][T2_SCR_STRIDE] + finisher ring
+	// [T2_FSLOTS][4][128] float2 + mbarriers / TMEM slot word (512 B) + x'' tile [128][D|1]
+	return (size_t)nst * 4 * T2_NH * Kp + (size_t)T2_HSTAGES * TC_HSTRIDE * 16 + 16 * 32 * T2_SCR_STRIDE * sizeof(float) +
+	       (size_t)T2_FSLOTS * 4 * TC_M * 8 + 512 + (size_t)TC_M * tc_x_stride(D) * sizeof(float);
 }
 
 // deepest B ring that fits (a stage is 960 tensor cycles of work at Kp = 80; the ring has to cover the L2 latency); 0 = unsupported

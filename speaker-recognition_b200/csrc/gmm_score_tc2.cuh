@@ -1,4 +1,4 @@
-// gmm_score_tc2.cuh -- tensor-core diagonal-GMM scorer for sm_100a, second generation: tcgen05 kind::f16 as "3xFP16" on CTA PAIRS.
+// gmm_score_tc2.cuh -- tensor-core diagonal-GMM scorer for sm_100a: tcgen05 kind::f16 as "3xFP16" on CTA PAIRS.
 //
 // Same quantity as gmm_score.cu (log2 p(x) per frame and speaker, per-utterance sums).  The Mahalanobis term is expanded over
 // centred, power-of-two-scaled features x'' = (x - c_d) alpha_d (api.cu pack_models_tc_host),
@@ -25,7 +25,10 @@
 //           block: per unit they build PHI (global -> registers -> tcgen05.st) and keep the raw x'' in shared memory; per block
 //           they sum the hard entries' t^2 per column while the MMAs run, tcgen05.ld the accumulator, release the slot (remote
 //           arrive on the leader's barrier), subtract the exact terms, and fold the 32 values into an online log2-sum-exp2;
-//           at a speaker's end the quarter's warps merge, apply the clamp and write per-frame values / per-(tile, speaker) sums.
+//           at a speaker's end every warp hands its (max, sum) to the finishers through a shared-memory ring -- no barrier
+//           between the epilogue warps (round 1: a named barrier per block and the merge on one of the four warps)
+//   warps 18-19 finishers (64 rows each): merge the four column groups of a speaker, log2, clamp, per-frame output and the
+//           per-(tile, speaker, lane quarter) partial sums
 // B images are K-major in the no-swizzle canonical layout (8-row x 16-byte core matrices = 8 rows x 8 halfs; LBO = 1024 B between
 // K-adjacent core matrices of a 64-row half block, SBO = 128 B between 8-row groups), stored in HBM in shared-memory order.
 #pragma once
@@ -188,14 +191,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 	const int NST = A.bstages;
 	unsigned char *sB = tc2_smem;                                                               // [NST] stages: head | tail of this CTA's half block
 	int4 *hring = reinterpret_cast<int4 *>(sB + (size_t)NST * stage_bytes);                    // [T2_HSTAGES][TC_HSTRIDE] hard-entry lists
-	float *scr = reinterpret_cast<float *>(hring + T2_HSTAGES * TC_HSTRIDE);                    // [16 warps][32 columns][32 lanes] add-back sums
-	float2 *ms_x = reinterpret_cast<float2 *>(scr + 16 * 32 * 32);                              // [2][3][128] (m, s) handed to the merging warp
-	uint64_t *bars = reinterpret_cast<uint64_t *>(ms_x + 2 * 3 * TC_M);
+	float *scr = reinterpret_cast<float *>(hring + T2_HSTAGES * TC_HSTRIDE);                    // [16 warps][32 lanes][T2_SCR_STRIDE] add-back sums
+	float2 *fin = reinterpret_cast<float2 *>(scr + 16 * 32 * T2_SCR_STRIDE);                    // [T2_FSLOTS][4 groups][128 rows] (m, s) for the finishers
+	uint64_t *bars = reinterpret_cast<uint64_t *>(fin + T2_FSLOTS * 4 * TC_M);
 	uint64_t *full_b = bars, *peer_full = full_b + T2_BSTAGES_MAX, *empty_b = peer_full + T2_BSTAGES_MAX;
 	uint64_t *full_h = empty_b + T2_BSTAGES_MAX, *empty_h = full_h + T2_HSTAGES;
 	uint64_t *tm_full = empty_h + T2_HSTAGES, *tm_empty = tm_full + T2_SLOTS;
 	uint64_t *a_ready = tm_empty + T2_SLOTS;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 1);
+	uint64_t *fin_full = a_ready + 1, *fin_empty = fin_full + T2_FSLOTS;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fin_empty + T2_FSLOTS);
 	float *sX = reinterpret_cast<float *>(bars + 64);                                           // [128][XS] x'' of the unit's tile
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -216,6 +220,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 			mbar_init(&tm_empty[s], 32);     // one arrival per epilogue warp of BOTH CTAs (used in the leader only)
 		}
 		mbar_init(a_ready, 32);
+		for (int s = 0; s < T2_FSLOTS; ++s) {
+			mbar_init(&fin_full[s], 16);     // every epilogue warp has stored its (m, s)
+			mbar_init(&fin_empty[s], 2);     // both finisher warps have read them
+		}
 		fence_mbar_init();
 	}
 	if (warp == 1) {
@@ -323,6 +331,65 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				}
 			}
 		}
+	} else if (warp >= 18) {
+		// ======================= finishers: warp 18 rows 0-63, warp 19 rows 64-127 =======================
+		const int f = warp - 18;
+		const int seg = A.seg;
+		uint32_t it_f = 0;
+		for (int u = cluster_id; u < n_units; u += n_clusters) {
+			const int pair = u / A.n_chunks, chunk = u - pair * A.n_chunks;
+			const int tile = 2 * pair + (int)rank;
+			const bool tile_ok = tile < A.n_ftiles;
+			const int blk0 = chunk * blocks_per_chunk_full;
+			const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
+			const int4 ft = tile_ok ? A.ftiles[tile] : make_int4(0, 0, 0, 0);
+			int spk = chunk * A.spk_per_chunk;
+			const int n_entries = seg >= TC_NB ? (blk1 - blk0) / A.blocks_per_spk : (blk1 - blk0);
+			for (int e = 0; e < n_entries; ++e, ++it_f) {
+				const int slot = it_f % T2_FSLOTS;
+				tc2::wait(&fin_full[slot], (it_f / T2_FSLOTS) & 1);
+				const float2 *fs = fin + (size_t)slot * 4 * TC_M;
+#pragma unroll
+				for (int batch = 0; batch < 2; ++batch) {
+					const int q = 2 * f + batch, row = q * 32 + lane;
+					const bool valid = row < ft.y;
+					float2 g[4];
+#pragma unroll
+					for (int c = 0; c < 4; ++c) g[c] = fs[c * TC_M + row];
+					// close one speaker from its (m, s): clamp, per-frame output, per-(tile, speaker, lane quarter) partial sum
+					auto out = [&](int my_spk, float m, float sacc) {
+						if (my_spk < A.S && tile_ok) {
+							const float l2 = m + lg2_approx(sacc);
+							float ll = l2 * TC_LN2;
+							if (A.clamp && !(ll >= -744.4400719213812f)) ll = -34.538776394910684f;
+							if (valid && A.frame_ll != nullptr) A.frame_ll[(size_t)my_spk * A.ldf + ft.x + row] = A.frame_log2 ? l2 : ll;
+							float local = valid ? ll : 0.f;
+#pragma unroll
+							for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+							if (lane == 0) A.partial[((size_t)tile * A.S + my_spk) * 4 + q] = (double)local;
+						}
+					};
+					auto merge2 = [](float2 a, float2 b) {
+						const float M = fmaxf(a.x, b.x);
+						return make_float2(M, a.y * ex2_approx(a.x - M) + b.y * ex2_approx(b.x - M));
+					};
+					if (seg >= TC_NB) {
+						const float2 r = merge2(merge2(g[0], g[1]), merge2(g[2], g[3]));
+						out(spk, r.x, r.y);
+					} else if (seg == 64) {
+						const float2 r0 = merge2(g[0], g[1]), r1 = merge2(g[2], g[3]);
+						out(spk, r0.x, r0.y);
+						out(spk + 1, r1.x, r1.y);
+					} else {
+#pragma unroll
+						for (int c = 0; c < 4; ++c) out(spk + c, g[c].x, g[c].y);
+					}
+				}
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&fin_empty[slot]);
+				spk += seg >= TC_NB ? 1 : (seg == 64 ? 2 : 4);
+			}
+		}
 	} else {
 		// ======================= epilogue (16 warps; thread = frame row; the 4 warps of a lane quarter take the 4 column groups) ====
 		const int ew = warp - 2;                      // 0..15
@@ -330,7 +397,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 		const int cg = ew >> 2;                       // 32-column group of every block this warp owns
 		const int row = q * 32 + lane;                // frame within the tile
 		const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-		float *my_scr = scr + (size_t)ew * 32 * 32 + lane;
+		float *my_scr = scr + ((size_t)ew * 32 + lane) * T2_SCR_STRIDE;      // this thread's flagged-column sums (slot p = p-th flagged column of the group)
 		float *xrow = sX + (size_t)row * XS;
 		const unsigned char *xrow_b = reinterpret_cast<const unsigned char *>(xrow);
 		unsigned char *scr_b = reinterpret_cast<unsigned char *>(my_scr) - 1;      // entry.w = 1 + byte offset of the scratch column
@@ -339,7 +406,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 		const int nch = Kp >> 4;                      // chunks of 16 k-values = 8 packed columns
 		const uint32_t a_ready_leader = tc2::mapa(smem_u32(a_ready), 0);
 		const uint32_t tm_empty_leader = tc2::mapa(smem_u32(tm_empty), 0);
-		uint32_t it_s = 0, it_h = 0, n_merge = 0;
+		uint32_t it_s = 0, it_h = 0, it_f = 0;
 #define SRB_TC2_QBAR() asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory")      /* the 4 warps of this lane quarter */
 		for (int u = cluster_id; u < n_units; u += n_clusters) {
 			const int pair = u / A.n_chunks, chunk = u - pair * A.n_chunks;
@@ -389,39 +456,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 
 			float m_run = -3.0e38f, s_run = 0.f;
 			int col_in_spk = 0;                       // columns of the current speaker consumed so far (by the quarter's warps together)
-			int spk = chunk * A.spk_per_chunk;        // first speaker of the current block
 
-			// close a speaker whose columns were shared by `width` (1, 2 or 4) adjacent warps of the quarter: merge, clamp,
-			// per-frame output, per-(tile, speaker, lane quarter) partial sum
-			auto finish = [&](int my_spk, int width) {
-				float m = m_run, sacc = s_run;
-				const bool leader = (cg & (width - 1)) == 0;
-				if (width > 1) {
-					// double-buffered hand-over (buffer = parity of the merge count): one barrier per speaker; the buffer written
-					// now is not written again before the NEXT merge's barrier, which every reader of it has passed by then
-					float2 *buf = ms_x + (size_t)(n_merge & 1) * 3 * TC_M;
-					++n_merge;
-					if (!leader) buf[(cg - 1) * TC_M + row] = make_float2(m, sacc);
-					SRB_TC2_QBAR();
-					if (leader) {
-						for (int o = 0; o < width - 1; ++o) {
-							const float2 other = buf[(cg + o) * TC_M + row];
-							const float M = fmaxf(m, other.x);
-							sacc = sacc * ex2_approx(m - M) + other.y * ex2_approx(other.x - M);
-							m = M;
-						}
-					}
-				}
-				if (leader && my_spk < A.S && tile_ok) {
-					const float l2 = m + lg2_approx(sacc);
-					float ll = l2 * TC_LN2;
-					if (A.clamp && !(ll >= -744.4400719213812f)) ll = -34.538776394910684f;
-					if (valid && A.frame_ll != nullptr) A.frame_ll[(size_t)my_spk * A.ldf + ft.x + row] = A.frame_log2 ? l2 : ll;
-					float local = valid ? ll : 0.f;
-#pragma unroll
-					for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-					if (lane == 0) A.partial[((size_t)tile * A.S + my_spk) * 4 + q] = (double)local;
-				}
+			// end of a speaker segment: this warp's running (max, sum) of its 32-column group goes to the finishers
+			auto handoff = [&]() {
+				const int slot = it_f % T2_FSLOTS;
+				tc2::wait(&fin_empty[slot], ((it_f / T2_FSLOTS) & 1) ^ 1);
+				fin[((size_t)slot * 4 + cg) * TC_M + row] = make_float2(m_run, s_run);
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&fin_full[slot]);
+				++it_f;
 				m_run = -3.0e38f;
 				s_run = 0.f;
 			};
@@ -436,7 +479,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				const int4 hmask = hl[0], hoff = hl[1], hval = hl[2];
 				const int e0 = cg == 0 ? 0 : (cg == 1 ? hoff.x : (cg == 2 ? hoff.y : hoff.z));
 				const int e1 = cg == 0 ? hoff.x : (cg == 1 ? hoff.y : (cg == 2 ? hoff.z : hoff.w));
-				const uint32_t mask = (uint32_t)(cg == 0 ? hmask.x : (cg == 1 ? hmask.y : (cg == 2 ? hmask.z : hmask.w)));
+				const int nflag = cg == 0 ? hmask.x : (cg == 1 ? hmask.y : (cg == 2 ? hmask.z : hmask.w));      // flagged columns: the group's first nflag (multiple of 4)
 				const uint32_t vmask = (uint32_t)(cg == 0 ? hval.x : (cg == 1 ? hval.y : (cg == 2 ? hval.z : hval.w)));
 				{
 					// four entries per step (the host pads every group's list to a multiple of four with null entries): all loads of a
@@ -483,11 +526,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				tc2::fence_before();
 				__syncwarp();
 				if (lane == 0) tc2::arrive_cluster(tm_empty_leader + 8u * (uint32_t)slot);
-				// ---- add-back, phase 2: only the flagged columns have a (fresh) scratch value
-				if (mask) {
+				// ---- add-back, phase 2: the flagged columns are the group's FIRST nflag columns (the packer orders the rows of a
+				// group that way; the log-sum-exp does not care), a multiple of four: one 128-bit load per four columns
 #pragma unroll
-					for (int j = 0; j < 32; ++j)
-						if (mask & (1u << j)) v[j] -= my_scr[j * 32];
+				for (int c = 0; c < T2_MAX_FLAGGED / 4; ++c) {
+					if (4 * c < nflag) {
+						const float4 t = *reinterpret_cast<const float4 *>(my_scr + 4 * c);
+						v[4 * c] -= t.x;
+						v[4 * c + 1] -= t.y;
+						v[4 * c + 2] -= t.z;
+						v[4 * c + 3] -= t.w;
+					}
 				}
 				// ---- columns beyond a speaker's mixtures (row padding) take no part in the sum
 				if (vmask != 0xffffffffu) {
@@ -498,18 +547,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				// column segmentation: seg >= 128 -> the block belongs to one speaker (quarter-wide merge at its end); seg == 64 ->
 				// two speakers per block, two warps each; seg == 32 -> every warp's group is its own speaker
 				tc2_lse_update(v, m_run, s_run);
-				if (seg == 32) {
-					finish(spk + cg, 1);
-					spk += 4;
-				} else if (seg == 64) {
-					finish(spk + (cg >> 1), 2);
-					spk += 2;
+				if (seg < TC_NB) {
+					handoff();
 				} else {
 					col_in_spk += TC_NB;
 					if (col_in_spk == cols_per_spk) {
-						finish(spk, 4);
+						handoff();
 						col_in_spk = 0;
-						++spk;
 					}
 				}
 			}

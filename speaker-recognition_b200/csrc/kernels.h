@@ -11,12 +11,7 @@ int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *ut
                  float *d_frame_ll, int ldf, int *d_best, int clamp, int frame_log2, cudaStream_t st);
 void score_tables_release();
 
-// ---- gmm_score_tc.cu: tensor-core route (tcgen05, 3xTF32) ----
-bool tc_supported(const PackedModels &pm, int D);
-int launch_score_tc(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, double *d_partial, float *d_frame_ll,
-                    int ldf, int clamp, int frame_log2, cudaStream_t st);
-
-// ---- gmm_score_tc2.cu: tensor-core route, second generation (tcgen05 cta_group::2, 3xFP16) ----
+// ---- gmm_score_tc2.cu: tensor-core route (tcgen05 cta_group::2, 3xFP16) ----
 bool tc2_supported(const PackedModels &pm, int D);
 int launch_score_tc2(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, double *d_partial, float *d_frame_ll,
                      int ldf, int clamp, int frame_log2, cudaStream_t st);
