@@ -184,13 +184,14 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 	struct RowPlan { bool real; double C; std::vector<double> av, nbv; std::vector<char> hard; int n_hard; };
 	bool overflow = false;
 	std::vector<int> order(D);
+	const int seg_cols = std::min(cols, NB), n_seg = NB / seg_cols, gps = seg_cols / 32;      // a segment = one speaker's columns inside a block
+	std::vector<RowPlan> rp(seg_cols);
 	for (int blk = 0; blk < blocks && !overflow; ++blk) {
 		int *hdr = pm.h_tc_hard.data() + (size_t)blk * TC_HSTRIDE * 4;
-		int pos = 0;                                    // entries of this block so far
-		for (int gi = 0; gi < 4 && !overflow; ++gi) {
-			RowPlan rp[32];
-			for (int j = 0; j < 32; ++j) {
-				const long long row = (long long)blk * NB + gi * 32 + j;
+		std::vector<HardEntry> glist[4];
+		for (int sg_i = 0; sg_i < n_seg && !overflow; ++sg_i) {
+			for (int j = 0; j < seg_cols; ++j) {
+				const long long row = (long long)blk * NB + sg_i * seg_cols + j;
 				const int s = (int)(row / cols), k = (int)(row % cols);
 				RowPlan &r = rp[j];
 				r.real = s < S && k < Ks[s];
@@ -221,45 +222,65 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 				}
 				r.C = (C < -1.0e30 || C != C) ? -1.0e30 : C;
 			}
-			// rows with exact entries first (stable), then the others, padding rows last
-			int perm[32], np = 0, nflag = 0;
-			for (int j = 0; j < 32; ++j)
-				if (rp[j].real && rp[j].n_hard > 0) perm[np++] = j;
-			nflag = np;
-			for (int j = 0; j < 32; ++j)
-				if (rp[j].real && rp[j].n_hard == 0) perm[np++] = j;
-			for (int j = 0; j < 32; ++j)
-				if (!rp[j].real) perm[np++] = j;
-			std::vector<HardEntry> g;
-			for (int p = 0; p < 32; ++p) {
-				const RowPlan &r = rp[perm[p]];
-				const int col = gi * 32 + p;
-				if (!r.real) {
-					put(blk, col, 2 * D, -T2_W_MAX);        // padded row; its column is masked out by header word 2 anyway
-					continue;
-				}
-				hdr[8 + gi] |= (int)(1u << p);              // header word 2: valid columns
-				for (int d = 0; d < D; ++d) {
-					if (r.hard[d]) {
-						g.push_back({4 * d, (float)r.av[d], (float)r.nbv[d], 0});
-					} else {
-						put(blk, col, d, -r.av[d] * r.av[d]);
-						put(blk, col, D + d, -2.0 * r.av[d] * r.nbv[d]);
-					}
-				}
-				if (r.n_hard > 0) g.back().w = 1 + 4 * p;   // last entry of this column: flush the sum to scratch slot p
-				put(blk, col, 2 * D, r.C);
-			}
-			// the epilogue corrects whole groups of four columns: null entries flush a zero into the unused slots of the last group
-			const int nflag4 = (nflag + 3) & ~3;
-			for (int p = nflag; p < nflag4; ++p) g.push_back({0, 0.f, 0.f, 1 + 4 * p});
-			while (g.size() % 4) g.push_back({0, 0.f, 0.f, 0});          // null entries: t = 0, no flush
-			if (nflag4 > T2_MAX_FLAGGED || pos + (int)g.size() > TC_HSTRIDE - TC_HHEAD) {
+			// Column order inside the segment (a log-sum-exp does not care): the rows that carry exact entries go FIRST into one
+			// 32-column group -- the group rotates with the block index, so that the epilogue warp that owns it is a different one
+			// from block to block -- up to T2_MAX_FLAGGED per group, spilling into the next group; plain rows fill up, padding last.
+			std::vector<int> flagged, plain, pad;
+			for (int j = 0; j < seg_cols; ++j) (!rp[j].real ? pad : (rp[j].n_hard > 0 ? flagged : plain)).push_back(j);
+			if ((int)flagged.size() > T2_MAX_FLAGGED * gps) {
 				overflow = true;
 				break;
 			}
-			hdr[gi] = nflag4;                               // header word 0: flagged columns of the group (its first nflag4)
-			for (const HardEntry &he : g) {
+			std::vector<int> members[4];
+			int nflag_g[4] = {0, 0, 0, 0};
+			size_t fi = 0;
+			for (int t = 0; t < gps; ++t) {
+				const int g = (t + blk) % gps;
+				while (fi < flagged.size() && nflag_g[g] < T2_MAX_FLAGGED) {
+					members[g].push_back(flagged[fi++]);
+					++nflag_g[g];
+				}
+			}
+			size_t pi = 0, di = 0;
+			for (int g = 0; g < gps; ++g)
+				while ((int)members[g].size() < 32) members[g].push_back(pi < plain.size() ? plain[pi++] : pad[di++]);
+			for (int g = 0; g < gps; ++g) {
+				const int gi = sg_i * gps + g;                  // group index inside the block
+				std::vector<HardEntry> &gl = glist[gi];
+				for (int p = 0; p < 32; ++p) {
+					const RowPlan &r = rp[members[g][p]];
+					const int col = gi * 32 + p;
+					if (!r.real) {
+						put(blk, col, 2 * D, -T2_W_MAX);        // padded row; its column is masked out by the valid mask anyway
+						continue;
+					}
+					hdr[gi * 4 + 3] |= (int)(1u << p);          // header word gi, .w: valid columns
+					for (int d = 0; d < D; ++d) {
+						if (r.hard[d]) {
+							gl.push_back({4 * d, (float)r.av[d], (float)r.nbv[d], 0});
+						} else {
+							put(blk, col, d, -r.av[d] * r.av[d]);
+							put(blk, col, D + d, -2.0 * r.av[d] * r.nbv[d]);
+						}
+					}
+					if (r.n_hard > 0) gl.back().w = 1 + 4 * p;   // last entry of this column: flush the sum to scratch slot p
+					put(blk, col, 2 * D, r.C);
+				}
+				// the epilogue corrects whole groups of four columns: null entries flush a zero into the unused slots of the last four
+				const int nflag4 = (nflag_g[g] + 3) & ~3;
+				for (int p = nflag_g[g]; p < nflag4; ++p) gl.push_back({0, 0.f, 0.f, 1 + 4 * p});
+				while (gl.size() % 4) gl.push_back({0, 0.f, 0.f, 0});          // null entries: t = 0, no flush
+				hdr[gi * 4 + 2] = nflag4;                       // .z: flagged columns of the group (its first nflag4)
+			}
+		}
+		int pos = 0;
+		for (int gi = 0; gi < 4 && !overflow; ++gi) {
+			if (pos + (int)glist[gi].size() > TC_HSTRIDE - TC_HHEAD) {
+				overflow = true;
+				break;
+			}
+			hdr[gi * 4 + 0] = pos;                              // .x, .y: the group's entries [e0, e1)
+			for (const HardEntry &he : glist[gi]) {
 				int *e = hdr + (size_t)(TC_HHEAD + pos) * 4;
 				e[0] = he.x;
 				memcpy(&e[1], &he.a, 4);
@@ -267,9 +288,8 @@ void pack_models_tc_host(PackedModels &pm, int S, int K, int D, const double *co
 				e[3] = he.w;
 				++pos;
 			}
-			if (gi < 3) hdr[4 + gi] = pos;                  // header word 1: first entry of the next group
+			hdr[gi * 4 + 1] = pos;
 		}
-		hdr[7] = pos;
 	}
 	if (overflow) {      // too many cancelling entries for the sparse list: this model set stays on the FMA route
 		pm.h_tc2.clear();
@@ -1049,7 +1069,7 @@ int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int 
 	if (ok)
 		for (int b = 0; b < pm.tc_blocks_total; ++b) {
 			int n = 0;
-			for (int e = 0; e < pm.h_tc_hard[(size_t)b * TC_HSTRIDE * 4 + 7]; ++e)
+			for (int e = 0; e < pm.h_tc_hard[(size_t)b * TC_HSTRIDE * 4 + 13]; ++e)
 				n += pm.h_tc_hard[((size_t)b * TC_HSTRIDE + TC_HHEAD + e) * 4 + 1] != 0;        // null padding entries have a = 0
 			hard += n;
 			mx = std::max(mx, n);

@@ -476,11 +476,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				// column's sum in the warp's scratch row (a dynamic column index cannot address registers).
 				tc2::wait(&full_h[hst], (it_h / T2_HSTAGES) & 1);
 				const int4 *hl = hring + (size_t)hst * TC_HSTRIDE;
-				const int4 hmask = hl[0], hoff = hl[1], hval = hl[2];
-				const int e0 = cg == 0 ? 0 : (cg == 1 ? hoff.x : (cg == 2 ? hoff.y : hoff.z));
-				const int e1 = cg == 0 ? hoff.x : (cg == 1 ? hoff.y : (cg == 2 ? hoff.z : hoff.w));
-				const int nflag = cg == 0 ? hmask.x : (cg == 1 ? hmask.y : (cg == 2 ? hmask.z : hmask.w));      // flagged columns: the group's first nflag (multiple of 4)
-				const uint32_t vmask = (uint32_t)(cg == 0 ? hval.x : (cg == 1 ? hval.y : (cg == 2 ? hval.z : hval.w)));
+				const int4 hd = hl[cg];                  // this warp's group: {first entry, end entry, flagged columns, valid-column mask}
+				const int e0 = hd.x, e1 = hd.y, nflag = hd.z;
+				const uint32_t vmask = (uint32_t)hd.w;
 				{
 					// four entries per step (the host pads every group's list to a multiple of four with null entries): all loads of a
 					// step are issued before its first scratch store

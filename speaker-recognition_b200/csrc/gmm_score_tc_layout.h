@@ -11,13 +11,12 @@ constexpr int TC_NB = 128;           // mixture rows per weight block = columns 
 constexpr float TC_LN2 = 0.69314718055994531f;
 
 // ---- the per-block list of exactly corrected ("hard") entries: TC_HSTRIDE int4 per 128-row block ----
-//   header word 0: flagged columns of the four 32-column groups -- the group's FIRST n columns, n a multiple of 4
-//   header word 1: {first entry of group 1, of group 2, of group 3, total number of entries}
-//   header word 2: bit masks of the VALID columns of the four groups (rows that are real mixtures, not speaker padding)
+//   header word g (g = 0..3, one per 32-column group): {first entry, end entry, flagged columns n (the group's FIRST n columns, a
+//       multiple of 4), bit mask of the VALID columns (rows that are real mixtures, not speaker padding)}
 //   entries, sorted by column, every group padded to a multiple of 4 with null entries:
 //       {4 * dim, float bits of a'', float bits of nb'', last entry of its column ? 1 + 4 * (scratch slot = column within the group) : 0}
-constexpr int TC_HHEAD = 3;
-constexpr int TC_HSTRIDE = TC_HHEAD + 125;  // 2 KB per block
+constexpr int TC_HHEAD = 4;
+constexpr int TC_HSTRIDE = TC_HHEAD + 124;  // 2 KB per block
 constexpr double TC_HARD_BUDGET = 1000.0;   // per mixture row: sum over the dims left in the GEMM of nb''^2 (the magnitude the expanded square cancels at);
                                             // the dims above it are added back exactly by the epilogue
 

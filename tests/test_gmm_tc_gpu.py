@@ -201,9 +201,9 @@ def test_tc_route_limits_and_fallbacks(tc_route):
     got = g.score(X)
     assert L.srb200_last_score_route() == 0
     assert np.max(rel_err(got, gmm_ref.score(w, m, s, X, gmm_ref.MODE_LOGDOMAIN))) < TOL
-    # a set just under the limit: 3 hard dims in every mixture of a 64-mixture model (a few dozen add-back entries per 128-row block) stays on route 1
+    # within the limits (16 exactly corrected rows per 32-column group): 3 hard dims in a third of the mixtures stays on route 1
     s2 = np.full((K, D), 0.7)
-    s2[:, :3] = 0.04
+    s2[::3, :3] = 0.04
     g2 = GMM(K).set_params(w, m, s2)
     X2 = m[rng.integers(0, K, 300)] + s2[0] * rng.normal(size=(300, D))
     got2 = g2.score(X2)

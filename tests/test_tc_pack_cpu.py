@@ -50,9 +50,7 @@ def emulate(P, X):
             W[col] = blk[off] + blk[off + NH * Kp]                    # head + tail
         l = phi @ W.T
         hl = P["hard"][b]
-        nflag, offs, vmask = hl[0], hl[1], hl[2]
-        starts = [0, offs[0], offs[1], offs[2]]
-        ends = [offs[0], offs[1], offs[2], offs[3]]
+        starts, ends, nflag, vmask = hl[:4, 0], hl[:4, 1], hl[:4, 2], hl[:4, 3]
         for g in range(4):
             assert nflag[g] % 4 == 0 and (ends[g] - starts[g]) % 4 == 0
             scratch = np.full((len(X), 16), np.nan)                    # stale slots must never be read
