@@ -92,8 +92,8 @@ __device__ __forceinline__ void wait(uint64_t *bar, uint32_t parity) {
 		if (++spins > 400000000LL) __trap();
 	}
 }
-__device__ __forceinline__ void ld32(uint32_t taddr, float *v) {
-	uint32_t r[32];
+// 32 accumulator columns of this thread's lane; the registers are valid after ld_wait()
+__device__ __forceinline__ void ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
 	asm volatile(
 	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
 	    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -103,10 +103,8 @@ __device__ __forceinline__ void ld32(uint32_t taddr, float *v) {
 	      "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
 	      "=r"(r[31])
 	    : "r"(taddr));
-	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-	for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&v)[8]) {
 	asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
 	             "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -195,7 +193,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 	float2 *fin = reinterpret_cast<float2 *>(scr + 16 * 32 * T2_SCR_STRIDE);                    // [T2_FSLOTS][4 groups][128 rows] (m, s) for the finishers
 	uint64_t *bars = reinterpret_cast<uint64_t *>(fin + T2_FSLOTS * 4 * TC_M);
 	uint64_t *full_b = bars, *peer_full = full_b + T2_BSTAGES_MAX, *empty_b = peer_full + T2_BSTAGES_MAX;
-	uint64_t *full_h = empty_b + T2_BSTAGES_MAX, *empty_h = full_h + T2_HSTAGES;
+	uint64_t *empty_h = empty_b + T2_BSTAGES_MAX;
 	uint64_t *tm_full = empty_h + T2_HSTAGES, *tm_empty = tm_full + T2_SLOTS;
 	uint64_t *a_ready = tm_empty + T2_SLOTS;
 	uint64_t *fin_full = a_ready + 1, *fin_empty = fin_full + T2_FSLOTS;
@@ -211,10 +209,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 			mbar_init(&peer_full[s], 1);
 			mbar_init(&empty_b[s], 1);
 		}
-		for (int s = 0; s < T2_HSTAGES; ++s) {
-			mbar_init(&full_h[s], 1);
-			mbar_init(&empty_h[s], 16);      // one arrival per epilogue warp of this CTA
-		}
+		for (int s = 0; s < T2_HSTAGES; ++s) mbar_init(&empty_h[s], 16);      // one arrival per epilogue warp of this CTA
 		for (int s = 0; s < T2_SLOTS; ++s) {
 			mbar_init(&tm_full[s], 1);
 			mbar_init(&tm_empty[s], 32);     // one arrival per epilogue warp of BOTH CTAs (used in the leader only)
@@ -251,16 +246,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				const int blk0 = chunk * blocks_per_chunk_full;
 				const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
 				for (int b = blk0; b < blk1; ++b, ++it_h) {
-					{   // the block's hard-entry list (needed first: the epilogue walks it while the block's MMAs run)
-						const int st = it_h % T2_HSTAGES;
-						tc2::wait(&empty_h[st], ((it_h / T2_HSTAGES) & 1) ^ 1);
-						mbar_expect_tx(&full_h[st], TC_HSTRIDE * 16);
-						bulk_g2s(hring + (size_t)st * TC_HSTRIDE, A.hard + (size_t)b * TC_HSTRIDE, TC_HSTRIDE * 16, &full_h[st]);
-					}
-					// this CTA's half of the block: head image then tail image, contiguous in HBM
-					const unsigned char *src = reinterpret_cast<const unsigned char *>(A.B) + ((size_t)b * 2 + rank) * stage_bytes;
+					// the block's hard-entry list and this CTA's half of the block (head image then tail image, contiguous in HBM) complete
+					// on ONE barrier: an epilogue warp that sees the block's accumulator (tm_full) knows the list has landed too -- the MMA
+					// warp waited for this barrier before it issued -- so the epilogue needs no wait of its own for the list
+					const int hst = it_h % T2_HSTAGES;
+					tc2::wait(&empty_h[hst], ((it_h / T2_HSTAGES) & 1) ^ 1);
 					tc2::wait(&empty_b[st_b], ph_b ^ 1);
-					mbar_expect_tx(&full_b[st_b], stage_bytes);
+					mbar_expect_tx(&full_b[st_b], stage_bytes + TC_HSTRIDE * 16);
+					bulk_g2s(hring + (size_t)hst * TC_HSTRIDE, A.hard + (size_t)b * TC_HSTRIDE, TC_HSTRIDE * 16, &full_b[st_b]);
+					const unsigned char *src = reinterpret_cast<const unsigned char *>(A.B) + ((size_t)b * 2 + rank) * stage_bytes;
 					bulk_g2s(sB + (size_t)st_b * stage_bytes, src, stage_bytes, &full_b[st_b]);
 					if (++st_b == NST) {
 						st_b = 0;
@@ -406,7 +400,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 		const int nch = Kp >> 4;                      // chunks of 16 k-values = 8 packed columns
 		const uint32_t a_ready_leader = tc2::mapa(smem_u32(a_ready), 0);
 		const uint32_t tm_empty_leader = tc2::mapa(smem_u32(tm_empty), 0);
-		uint32_t it_s = 0, it_h = 0, it_f = 0;
+		uint32_t it_f = 0, ph_s = 0;
+		int slot = 0, hst = 0;                        // accumulator slot / hard-list ring position of the next block (rings never reset)
 #define SRB_TC2_QBAR() asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory")      /* the 4 warps of this lane quarter */
 		for (int u = cluster_id; u < n_units; u += n_clusters) {
 			const int pair = u / A.n_chunks, chunk = u - pair * A.n_chunks;
@@ -452,15 +447,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				tc2::fence_before();
 				SRB_TC2_QBAR();                                // the quarter's x'' are in shared memory
 				if (lane == 0) tc2::arrive_cluster(a_ready_leader);
+				// the NEXT unit's frames towards L2 now: its PHI build sits between two units with the tensor pipe drained
+				const int un = u + n_clusters;
+				if (cg == 0 && un < n_units) {
+					const int tn = 2 * (un / A.n_chunks) + (int)rank;
+					if (tn != tile && tn < A.n_ftiles) {
+						const int4 fn = A.ftiles[tn];
+						if (row < fn.y) {
+							const float *pn = A.X + (size_t)(fn.x + row) * A.ld;
+							asm volatile("prefetch.global.L2 [%0];" ::"l"(pn));
+							if (A.ld > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + 32));
+						}
+					}
+				}
 			}
 
 			float m_run = -3.0e38f, s_run = 0.f;
 			int col_in_spk = 0;                       // columns of the current speaker consumed so far (by the quarter's warps together)
 
-			// end of a speaker segment: this warp's running (max, sum) of its 32-column group goes to the finishers
+			// end of a speaker segment: this warp's running (max, sum) of its 32-column group goes to the finishers.  The ring is
+			// checked once per FOUR hand-overs (the finishers release in order: the last slot of the next four being free means all are)
 			auto handoff = [&]() {
 				const int slot = it_f % T2_FSLOTS;
-				tc2::wait(&fin_empty[slot], ((it_f / T2_FSLOTS) & 1) ^ 1);
+				if ((it_f & 3) == 0) tc2::wait(&fin_empty[slot + 3], ((it_f / T2_FSLOTS) & 1) ^ 1);
 				fin[((size_t)slot * 4 + cg) * TC_M + row] = make_float2(m_run, s_run);
 				__syncwarp();
 				if (lane == 0) mbar_arrive(&fin_full[slot]);
@@ -469,24 +478,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				s_run = 0.f;
 			};
 
-			for (int b = blk0; b < blk1; ++b, ++it_s, ++it_h) {
-				const int slot = it_s % T2_SLOTS, hst = it_h % T2_HSTAGES;
-				// ---- exact add-back, phase 1 (the block's MMAs are still running): sum t^2 of this warp's hard entries per column --
-				// the list is uniform across the warp, sorted by column, `last` flag on a column's final entry -- and park each
-				// column's sum in the warp's scratch row (a dynamic column index cannot address registers).
-				tc2::wait(&full_h[hst], (it_h / T2_HSTAGES) & 1);
+			for (int b = blk0; b < blk1; ++b) {
+				// ---- accumulator -> registers.  The only wait of the block: tm_full also covers the block's hard-entry list (producer).
+				tc2::wait(&tm_full[slot], ph_s);
+				tc2::fence_after();
+				uint32_t vr[32];
+				tc2::ld32_issue(lane_base + (uint32_t)(slot * TC_NB + cg * 32), vr);
 				const int4 *hl = hring + (size_t)hst * TC_HSTRIDE;
 				const int4 hd = hl[cg];                  // this warp's group: {first entry, end entry, flagged columns, valid-column mask}
-				const int e0 = hd.x, e1 = hd.y, nflag = hd.z;
-				const uint32_t vmask = (uint32_t)hd.w;
-				{
-					// four entries per step (the host pads every group's list to a multiple of four with null entries): all loads of a
-					// step are issued before its first scratch store
-					const int4 *e = hl + TC_HHEAD + e0;
-					const int n = e1 - e0;
+				tc2::ld_wait();
+				tc2::fence_before();
+				__syncwarp();
+				if (lane == 0) tc2::arrive_cluster(tm_empty_leader + 8u * (uint32_t)slot);      // the leader's MMA warp overwrites both CTAs' slots
+				float v[32];
+#pragma unroll
+				for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vr[i]);
+				// ---- exact add-back (in one block only the warps of ONE column group have entries; the group rotates with the block):
+				// sum t^2 of the hard entries per column -- the list is uniform across the warp, sorted by column, `last` flag on a
+				// column's final entry -- park each column's sum in this thread's scratch slots (a dynamic column index cannot address
+				// registers), then subtract: the flagged columns are the group's FIRST hd.z columns, a multiple of four
+				if (hd.y > hd.x) {
+					const int4 *e = hl + TC_HHEAD + hd.x;
+					const int n = hd.y - hd.x;
 					float csum = 0.f;
 #pragma unroll 1
-					for (int i = 0; i < n; i += 4) {
+					for (int i = 0; i < n; i += 4) {      // four entries per step, all loads of a step ahead of its first scratch store
 						const int4 a0 = e[i], a1 = e[i + 1], a2 = e[i + 2], a3 = e[i + 3];
 						const float x0 = *reinterpret_cast<const float *>(xrow_b + a0.x), x1 = *reinterpret_cast<const float *>(xrow_b + a1.x);
 						const float x2 = *reinterpret_cast<const float *>(xrow_b + a2.x), x3 = *reinterpret_cast<const float *>(xrow_b + a3.x);
@@ -513,29 +529,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 							csum = 0.f;
 						}
 					}
-				}
-				__syncwarp();
-				if (lane == 0) mbar_arrive(&empty_h[hst]);
-				// ---- accumulator -> registers, slot released right away (to the leader's barrier: its MMA warp overwrites both CTAs' slots)
-				tc2::wait(&tm_full[slot], (it_s / T2_SLOTS) & 1);
-				tc2::fence_after();
-				float v[32];
-				tc2::ld32(lane_base + (uint32_t)(slot * TC_NB + cg * 32), v);
-				tc2::fence_before();
-				__syncwarp();
-				if (lane == 0) tc2::arrive_cluster(tm_empty_leader + 8u * (uint32_t)slot);
-				// ---- add-back, phase 2: the flagged columns are the group's FIRST nflag columns (the packer orders the rows of a
-				// group that way; the log-sum-exp does not care), a multiple of four: one 128-bit load per four columns
 #pragma unroll
-				for (int c = 0; c < T2_MAX_FLAGGED / 4; ++c) {
-					if (4 * c < nflag) {
-						const float4 t = *reinterpret_cast<const float4 *>(my_scr + 4 * c);
-						v[4 * c] -= t.x;
-						v[4 * c + 1] -= t.y;
-						v[4 * c + 2] -= t.z;
-						v[4 * c + 3] -= t.w;
+					for (int c = 0; c < T2_MAX_FLAGGED / 4; ++c) {
+						if (4 * c < hd.z) {
+							const float4 t = *reinterpret_cast<const float4 *>(my_scr + 4 * c);
+							v[4 * c] -= t.x;
+							v[4 * c + 1] -= t.y;
+							v[4 * c + 2] -= t.z;
+							v[4 * c + 3] -= t.w;
+						}
 					}
 				}
+				const uint32_t vmask = (uint32_t)hd.w;
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&empty_h[hst]);
+				if (++slot == T2_SLOTS) {
+					slot = 0;
+					ph_s ^= 1;
+				}
+				hst = (hst + 1) & (T2_HSTAGES - 1);
 				// ---- columns beyond a speaker's mixtures (row padding) take no part in the sum
 				if (vmask != 0xffffffffu) {
 #pragma unroll
