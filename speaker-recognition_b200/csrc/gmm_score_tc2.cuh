@@ -15,19 +15,22 @@
 // the stream of 128-row weight blocks.  Each CTA bulk-copies only ITS HALF of every block (64 rows: rank r supplies rows
 // [64 r, 64 r + 64) of the block -- verified by the probe) into its own shared memory, so the L2 -> SM traffic per frame is half
 // that of a single-CTA kernel (round 1 ran at the chip's ~6.3 KB/clk L2 limit: every SM streamed every block).
-//   warp 0  producer (both CTAs): cp.async.bulk of the block's hard-entry list and of this CTA's half block (fp16 head image and
+// Warp roles (the SM's issue arbiter favours the HIGHER warp id of a sub-partition: the light, latency-critical roles get the
+// highest ids -- with the MMA issuer as warp 1 below sixteen busy epilogue warps, its ~250 instructions per block were starved
+// to ~1400 cycles per block against 960 of tensor time, ncu):
+//   warp 18 producer (both CTAs): cp.async.bulk of the block's hard-entry list and of this CTA's half block (fp16 head image and
 //           tail image, one 256 Kp-byte copy) into a ring of up to 6 stages
-//   warp 1  leader CTA: MMA issuer -- waits for its own stage and for the peer's (relayed), issues 3 x Kp/16
+//   warp 19 leader CTA: MMA issuer -- waits for its own stage and for the peer's (relayed), issues 3 x Kp/16
 //           tcgen05.mma.cta_group::2.kind::f16 (M 256 = 2 x 128, N 128, K 16) with the A operand (PHI head | tail) in TENSOR MEMORY,
 //           tcgen05.commit multicast to both CTAs frees the stage and publishes the accumulator slot (three 128-column slots)
 //           peer CTA: relay -- forwards "my half of stage s has landed" to the leader with a remote mbarrier arrive
-//   warps 2-17 epilogue, thread = frame row = TMEM lane, the four warps of a lane quarter own the four 32-column groups of every
+//   warps 0-15 epilogue, thread = frame row = TMEM lane, the four warps of a lane quarter own the four 32-column groups of every
 //           block: per unit they build PHI (global -> registers -> tcgen05.st) and keep the raw x'' in shared memory; per block
 //           they sum the hard entries' t^2 per column while the MMAs run, tcgen05.ld the accumulator, release the slot (remote
 //           arrive on the leader's barrier), subtract the exact terms, and fold the 32 values into an online log2-sum-exp2;
 //           at a speaker's end every warp hands its (max, sum) to the finishers through a shared-memory ring -- no barrier
 //           between the epilogue warps (round 1: a named barrier per block and the merge on one of the four warps)
-//   warps 18-19 finishers (64 rows each): merge the four column groups of a speaker, log2, clamp, per-frame output and the
+//   warps 16-17 finishers (64 rows each): merge the four column groups of a speaker, log2, clamp, per-frame output and the
 //           per-(tile, speaker, lane quarter) partial sums
 // B images are K-major in the no-swizzle canonical layout (8-row x 16-byte core matrices = 8 rows x 8 halfs; LBO = 1024 B between
 // K-adjacent core matrices of a 64-row half block, SBO = 128 B between 8-row groups), stored in HBM in shared-memory order.
@@ -221,7 +224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 		}
 		fence_mbar_init();
 	}
-	if (warp == 1) {
+	if (warp == T2_WARP_MMA) {
 		asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
 	}
@@ -236,7 +239,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 	const int n_units = n_pairs * A.n_chunks;
 	const int blocks_per_chunk_full = (A.seg >= TC_NB) ? A.spk_per_chunk * A.blocks_per_spk : (A.spk_per_chunk * A.seg + TC_NB - 1) / TC_NB;
 
-	if (warp == 0) {
+	if (warp == T2_WARP_PRODUCER) {
 		// ======================= producer =======================
 		if (lane == 0) {
 			uint32_t it_h = 0, ph_b = 0;
@@ -263,7 +266,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				}
 			}
 		}
-	} else if (warp == 1 && rank != 0) {
+	} else if (warp == T2_WARP_MMA && rank != 0) {
 		// ======================= peer CTA: relay "my half of the stage has landed" to the leader =======================
 		if (lane == 0) {
 			uint32_t ph_b = 0;
@@ -282,7 +285,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				}
 			}
 		}
-	} else if (warp == 1) {
+	} else if (warp == T2_WARP_MMA) {
 		// ======================= leader CTA: MMA issuer (whole warp converged; one lane elected per instruction) =======================
 		// instruction descriptor: D = F32 (bits 4-5 = 1), A/B = F16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24 (M = 256: the pair)
 		const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_NB >> 3) << 17) | ((uint32_t)((2 * TC_M) >> 4) << 24);
@@ -325,9 +328,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				}
 			}
 		}
-	} else if (warp >= 18) {
-		// ======================= finishers: warp 18 rows 0-63, warp 19 rows 64-127 =======================
-		const int f = warp - 18;
+	} else if (warp >= T2_WARP_FIN0) {
+		// ======================= finishers: warp 16 rows 0-63, warp 17 rows 64-127 =======================
+		const int f = warp - T2_WARP_FIN0;
 		const int seg = A.seg;
 		uint32_t it_f = 0;
 		for (int u = cluster_id; u < n_units; u += n_clusters) {
@@ -386,7 +389,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 		}
 	} else {
 		// ======================= epilogue (16 warps; thread = frame row; the 4 warps of a lane quarter take the 4 column groups) ====
-		const int ew = warp - 2;                      // 0..15
+		const int ew = warp;                          // 0..15
 		const int q = warp & 3;                       // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
 		const int cg = ew >> 2;                       // 32-column group of every block this warp owns
 		const int row = q * 32 + lane;                // frame within the tile
@@ -573,7 +576,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 	tc2::fence_before();
 	__syncthreads();
 	tc2::cluster_sync_all();           // the peer's tensor memory and barriers stay alive until the leader's last MMA / commit has landed
-	if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+	if (warp == T2_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
 }  // namespace srb

@@ -28,7 +28,8 @@ constexpr int T2_KP_MAX = 128;       // 2 D + 1 <= 127
 constexpr int T2_BSTAGES_MAX = 6;    // ring of half-block stages (head | tail image of 64 rows: 256 Kp bytes)
 constexpr int T2_HSTAGES = 8;        // ring of per-block hard-entry lists: the producer runs this many blocks ahead of the SLOWEST epilogue warp, and the
                                      // epilogue may lag the MMA warp by the three accumulator slots -- the B loads need the difference to cover the L2 latency
-constexpr int T2_THREADS = 640;      // producer warp, MMA / relay warp, 16 epilogue warps, 2 finisher warps
+constexpr int T2_THREADS = 640;      // 16 epilogue warps (0-15: TMEM lane quarter = warp % 4), 2 finisher warps, producer warp, MMA / relay warp
+constexpr int T2_WARP_FIN0 = 16, T2_WARP_PRODUCER = 18, T2_WARP_MMA = 19;
 constexpr int T2_FSLOTS = 8;         // ring of (max, sum) hand-overs from the epilogue warps to the finishers: [slot][4 groups][128 rows] float2
 constexpr int T2_MAX_FLAGGED = 16;   // flagged (exactly corrected) columns per 32-column group; the packer orders them first
 constexpr int T2_SCR_STRIDE = 20;    // floats per thread of add-back scratch: 16 slots, stride 20 keeps the 128-bit loads conflict-free
