@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsrb200.so")
+LIB_PATH = os.environ.get("SRB200_LIB") or os.path.join(_HERE, "csrc", "libsrb200.so")   # SRB200_LIB: A/B builds of the same library (experiments)
 
 
 class Parameter(C.Structure):

@@ -144,7 +144,46 @@ __device__ __forceinline__ void split_pack(float v0, float v1, uint32_t &hi, uin
 
 }  // namespace tc2
 
-// online log2-sum-exp2 update with 32 new values (one chunk of accumulator columns) for one frame
+// 2^x for two x <= 0 on the FMA pipe (the MUFU unit does 4 ex2 per clock and sub-partition and is the epilogue's busiest pipe):
+// round-to-nearest split x = n + f by the magic-number add, degree-4 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error
+// 2.7e-6, mean 4e-8: fitted in experiments/f16x3_numerics.py's sibling script, checked in tests), 2^n spliced into the exponent.
+__device__ __forceinline__ unsigned long long tc2_exp2_poly2(unsigned long long x01) {
+	float a, b;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x01));
+	a = fmaxf(a, -126.f);                             // below: the exponent splice would wrap; such terms are 0 against a sum >= 1
+	b = fmaxf(b, -126.f);
+	unsigned long long x, t, n, f, p;
+	const float MAGIC = 12582912.f;                   // 1.5 * 2^23: the integer part lands in the low mantissa bits
+	unsigned long long mg, nmg, neg1, c0, c1, c2, c3, c4;
+	asm("mov.b64 %0, {%1, %1};" : "=l"(mg) : "f"(MAGIC));
+	asm("mov.b64 %0, {%1, %1};" : "=l"(nmg) : "f"(-MAGIC));
+	asm("mov.b64 %0, {%1, %1};" : "=l"(neg1) : "f"(-1.f));
+	asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(0.9999992624f));
+	asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.693121851f));
+	asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(0.2402474484f));
+	asm("mov.b64 %0, {%1, %1};" : "=l"(c3) : "f"(0.0559175783f));
+	asm("mov.b64 %0, {%1, %1};" : "=l"(c4) : "f"(0.009569989201f));
+	asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(mg));
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(n) : "l"(t), "l"(nmg));
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f) : "l"(n), "l"(neg1), "l"(x));
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(c4), "l"(f), "l"(c3));
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c2));
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c1));
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c0));
+	uint32_t p0, p1, t0, t1;
+	asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(p));
+	asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
+	p0 += t0 << 23;                                   // (0x4B400000 + n) << 23 == n << 23 (mod 2^32)
+	p1 += t1 << 23;
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(p0), "r"(p1));
+	return r;
+}
+
+// online log2-sum-exp2 update with 32 new values (one chunk of accumulator columns) for one frame; the first NP of the 32
+// exponentials are evaluated on the FMA pipe, the others by MUFU.EX2
+template <int NP>
 __device__ __forceinline__ void tc2_lse_update(const float *v, float &m_run, float &s_run) {
 	float t[16];                                   // tree reduction (ptxas fuses the pairs into three-input FMNMX3)
 #pragma unroll
@@ -161,17 +200,21 @@ __device__ __forceinline__ void tc2_lse_update(const float *v, float &m_run, flo
 	asm("mov.b64 %0, {%1, %1};" : "=l"(nm2) : "f"(nm));
 #pragma unroll
 	for (int i = 0; i < 32; i += 4) {
-		unsigned long long p01, p23, d01, d23;
+		unsigned long long p01, p23, d01, d23, e01, e23;
 		asm("mov.b64 %0, {%1, %2};" : "=l"(p01) : "f"(v[i]), "f"(v[i + 1]));
 		asm("mov.b64 %0, {%1, %2};" : "=l"(p23) : "f"(v[i + 2]), "f"(v[i + 3]));
 		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d01) : "l"(p01), "l"(nm2));
 		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d23) : "l"(p23), "l"(nm2));
-		float a, b, c, d;
-		asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(d01));
-		asm("mov.b64 {%0, %1}, %2;" : "=f"(c), "=f"(d) : "l"(d23));
-		unsigned long long e01, e23;
-		asm("mov.b64 %0, {%1, %2};" : "=l"(e01) : "f"(ex2_approx(a)), "f"(ex2_approx(b)));
-		asm("mov.b64 %0, {%1, %2};" : "=l"(e23) : "f"(ex2_approx(c)), "f"(ex2_approx(d)));
+		if (i < NP) {
+			e01 = tc2_exp2_poly2(d01);
+			e23 = tc2_exp2_poly2(d23);
+		} else {
+			float a, b, c, d;
+			asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(d01));
+			asm("mov.b64 {%0, %1}, %2;" : "=f"(c), "=f"(d) : "l"(d23));
+			asm("mov.b64 %0, {%1, %2};" : "=l"(e01) : "f"(ex2_approx(a)), "f"(ex2_approx(b)));
+			asm("mov.b64 %0, {%1, %2};" : "=l"(e23) : "f"(ex2_approx(c)), "f"(ex2_approx(d)));
+		}
 		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc01) : "l"(acc01), "l"(e01));
 		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc23) : "l"(acc23), "l"(e23));
 	}
@@ -559,7 +602,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				}
 				// column segmentation: seg >= 128 -> the block belongs to one speaker (quarter-wide merge at its end); seg == 64 ->
 				// two speakers per block, two warps each; seg == 32 -> every warp's group is its own speaker
-				tc2_lse_update(v, m_run, s_run);
+				tc2_lse_update<T2_POLY_EXP>(v, m_run, s_run);
 				if (seg < TC_NB) {
 					handoff();
 				} else {
