@@ -35,9 +35,11 @@ constexpr int T2_FSLOTS = 8;         // ring of (max, sum) hand-overs from the e
 constexpr int T2_MAX_FLAGGED = 16;   // flagged (exactly corrected) columns per 32-column group; the packer orders them first
 constexpr int T2_SCR_STRIDE = 20;    // floats per thread of add-back scratch: 16 slots, stride 20 keeps the 128-bit loads conflict-free
 #ifndef SRB_T2_POLY_EXP
-#define SRB_T2_POLY_EXP 8
+#define SRB_T2_POLY_EXP 0
 #endif
-constexpr int T2_POLY_EXP = SRB_T2_POLY_EXP;   // of every 32 exponentials of the epilogue, this many run as a polynomial on the FMA pipe instead of MUFU.EX2
+constexpr int T2_POLY_EXP = SRB_T2_POLY_EXP;   // of every 32 exponentials of the epilogue, this many run as a polynomial on the FMA pipe instead of MUFU.EX2.
+                                               // Measured on B200 (C2 x 64 utterances): 0 -> 3.28 ms, 8 -> 3.34 ms, 16 -> 3.65 ms: the epilogue is bound by
+                                               // issue slots (0.58 IPC, 63 % MUFU), not by the MUFU unit, so the extra FMA instructions lose; kept switchable.
 constexpr float T2_X_CLAMP = 240.f;  // |x''| bound before squaring (fp16 max 65504)
 constexpr double T2_W_MAX = 60000.0; // |W| bound of an fp16 image entry; larger terms are added back exactly instead
 __host__ __device__ static inline int t2_kp(int D) { return ((2 * D + 1 + 15) / 16) * 16; }
