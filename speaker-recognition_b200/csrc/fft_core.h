@@ -157,85 +157,72 @@ SRB_HD void dft16(const cpx *v, cpx *o) {
 	}
 }
 
-constexpr int FAST_TSTRIDE = 17;        // padded row of the 16x16 transpose tile (complex elements)
-constexpr int FAST_ZSTRIDE = 260;       // row stride of Zs[r][q] (complex): 260 = 4 mod 16 makes the 64-bit reads of
-                                        // Z[4q + r] by consecutive k conflict-free (16 lanes x 8 B = 16 distinct bank pairs)
-constexpr int FAST_PSTRIDE = 1028;      // power spectrum row (floats): bins 0..1024, natural order
+// ---- warp-per-frame layout (mfcc.cu mfcc_frames_warp_kernel): one warp owns one frame; lane = (h, u), h = lane >> 4 the half,
+// u = lane & 15; the half-warps run the sub-transforms r = h (round 0) and r = h + 2 (round 1).  All buffers are per warp:
+//   T / Zs   4 tiles of 256 complex elements, tile r at r * 256.  Transpose tile: element (row, col) at row * 16 + (col ^ row)
+//            (XOR swizzle: both the column writes of step A and the column reads of step B touch 16 distinct bank pairs);
+//            sub-transform output Y_r[q] IN PLACE over the same tile at q ^ (4 r) (the XOR makes the four r of neighbouring bins
+//            fall into different bank pairs when the power stage reads Z[k] = Y_{k & 3}[k >> 2] with consecutive k per lane)
+//   P        power spectrum, bins 0..1024, bin k at k + 4 (k >> 4): every run of 16 bins is skewed by 16 bytes, so that the
+//            128-bit reads of the mel stage (lanes on segments that start 16 bins apart) spread over the banks
+constexpr int WF_TILE = 256;
+constexpr int WF_PLEN = 1284;           // floats: 1024 + 4 * 64 + 1, rounded up to a multiple of 4
+SRB_HD int wf_t_index(int row, int col) { return row * 16 + (col ^ row); }
+SRB_HD int wf_z_index(int r, int q) { return r * WF_TILE + (q ^ (4 * r)); }
+SRB_HD int wf_p_index(int k) { return k + 4 * (k >> 4); }
 
-// step A of the 256-point sub-transform owned by (r, u): inputs z[u + 16 n2] (packed complex frame, zero for
-// n >= 256 by construction), first twiddle tw1[r][n] = W_1024^{n r}, radix-16 over n2, second twiddle
-// twA[q2][u] = W_256^{u q2}, result into the transpose tile T[u][q2].
-SRB_HD void fast_step_a(const cpx *z, const cpx *tw1, const cpx *twA, cpx *T, int r, int u) {
+// step A for (r, u): z[n2] = packed frame element u + 16 n2 (loaded once by the caller and used for both rounds), tw1r = row r of
+// the first twiddle table W_1024^{n r} (row 0 is all ones), twA[q2][u] = W_256^{u q2}; result into tile r of T
+SRB_HD void wf_step_a(const cpx (&z)[16], const cpx *tw1r, const cpx *twA, cpx *Ttile, int u) {
 	cpx in[16], out[16];
 #pragma unroll
-	for (int n2 = 0; n2 < 16; ++n2) {
-		const int n = u + 16 * n2;
-		const cpx zz = z[n];
-		in[n2] = (r == 0) ? zz : cmul(zz, tw1[(r - 1) * 256 + n]);
-	}
+	for (int n2 = 0; n2 < 16; ++n2) in[n2] = cmul(z[n2], tw1r[u + 16 * n2]);
 	dft16(in, out);
 #pragma unroll
-	for (int q2 = 0; q2 < 16; ++q2) T[u * FAST_TSTRIDE + q2] = cmul(out[q2], twA[q2 * 16 + u]);
+	for (int q2 = 0; q2 < 16; ++q2) Ttile[wf_t_index(u, q2)] = cmul(out[q2], twA[q2 * 16 + u]);
 }
-
-// step B: radix-16 over n1 of T[n1][u] -> Y_r[16 q1 + u], stored as Zr[16 q1 + u] (Zr = Zs + r * FAST_ZSTRIDE).
-// Split into a load and a compute/store half so that the kernel can run it IN PLACE (Zs aliasing the transpose tiles,
-// with a CTA barrier between the halves); fast_step_b is the two halves back to back for distinct buffers.
-SRB_HD void fast_step_b_load(const cpx *T, int u, cpx (&in)[16]) {
+// step B for (r, u), in place: all 16 lanes of the half-warp load, (warp barrier), then transform and store Y_r[16 q1 + u]
+SRB_HD void wf_step_b_load(const cpx *Ttile, int u, cpx (&in)[16]) {
 #pragma unroll
-	for (int n1 = 0; n1 < 16; ++n1) in[n1] = T[n1 * FAST_TSTRIDE + u];
+	for (int n1 = 0; n1 < 16; ++n1) in[n1] = Ttile[wf_t_index(n1, u)];
 }
-SRB_HD void fast_step_b_store(const cpx (&in)[16], cpx *Zr, int u) {
+SRB_HD void wf_step_b_store(const cpx (&in)[16], cpx *Z, int r, int u) {
 	cpx out[16];
 	dft16(in, out);
 #pragma unroll
-	for (int q1 = 0; q1 < 16; ++q1) Zr[16 * q1 + u] = out[q1];
+	for (int q1 = 0; q1 < 16; ++q1) Z[wf_z_index(r, 16 * q1 + u)] = out[q1];
 }
-SRB_HD void fast_step_b(const cpx *T, cpx *Zr, int u) {
-	cpx in[16];
-	fast_step_b_load(T, u, in);
-	fast_step_b_store(in, Zr, u);
-}
-
-// one bin of the real 2048-point power spectrum from Zs[r][q] = Z[4q + r]; w = exp(-2 pi i k / 2048)
-SRB_HD float fast_power_bin(const cpx *Zs, int k, cpx w) {
+// bins k and 1024 - k of the real 2048-point power spectrum from ONE pair of packed results: with e = Z[k] + conj(Z[1024-k]),
+// o = Z[k] - conj(Z[1024-k]), w = exp(-2 pi i k / 2048), (a, b) = w o:
+//     Y[k] = (e.x + b, e.y - a) / 2,        Y[1024 - k] = (e.x - b, -e.y - a) / 2          (Z[1024] := Z[0])
+SRB_HD void wf_power_pair(const cpx *Z, int k, cpx w, float &pk, float &pmk) {
 	const int km = (1024 - k) & 1023;
-	const cpx zk = Zs[(k & 3) * FAST_ZSTRIDE + ((k >> 2) & 255)];
-	cpx zc = Zs[(km & 3) * FAST_ZSTRIDE + (km >> 2)];
+	const cpx zk = Z[wf_z_index(k & 3, k >> 2)];
+	cpx zc = Z[wf_z_index(km & 3, km >> 2)];
 	zc.y = -zc.y;
 	const cpx e = cadd(zk, zc), o = csub(zk, zc);
 	const cpx wo = cmul(w, o);
 	const float yr = 0.5f * (e.x + wo.y), yi = 0.5f * (e.y - wo.x);
-	return yr * yr + yi * yi;
+	const float mr = 0.5f * (e.x - wo.y), mi = 0.5f * (e.y + wo.x);
+	pk = yr * yr + yi * yi;
+	pmk = mr * mr + mi * mi;
 }
-
-// power spectrum P[0..1024] (natural order) of one frame by 64 workers: worker w owns k = w + 64 i, i = 0..15
-// (consecutive workers -> consecutive k: conflict-free shared-memory traffic), worker 0 also k = 1024.
-// The unpack twiddle exp(-2 pi i k/2048) = tw2[w] * exp(-2 pi i i/32): one table load per worker, 16 constants.
-SRB_HD void fast_power_unpack(const cpx *Zs, float *P, const cpx *tw2, int worker) {
-	const float W32[16][2] = {{1.f, -0.f},
-	                          {0.98078528040323044913f, -0.19509032201612826785f},
-	                          {0.92387953251128675613f, -0.38268343236508977173f},
-	                          {0.83146961230254523708f, -0.55557023301960222474f},
-	                          {0.70710678118654752440f, -0.70710678118654752440f},
-	                          {0.55557023301960222474f, -0.83146961230254523708f},
-	                          {0.38268343236508977173f, -0.92387953251128675613f},
-	                          {0.19509032201612826785f, -0.98078528040323044913f},
-	                          {0.f, -1.f},
-	                          {-0.19509032201612826785f, -0.98078528040323044913f},
-	                          {-0.38268343236508977173f, -0.92387953251128675613f},
-	                          {-0.55557023301960222474f, -0.83146961230254523708f},
-	                          {-0.70710678118654752440f, -0.70710678118654752440f},
-	                          {-0.83146961230254523708f, -0.55557023301960222474f},
-	                          {-0.92387953251128675613f, -0.38268343236508977173f},
-	                          {-0.98078528040323044913f, -0.19509032201612826785f}};
-	const cpx base = tw2[worker];
+// the whole power stage of one frame as the 32 lanes do it: lane l owns the pairs k = l + 32 i, i = 0..15 (k = 0..511), lane 0 also
+// the self-paired bin 512; tw2[k] = exp(-2 pi i k / 2048), k = 0..512
+SRB_HD void wf_power_lane(const cpx *Z, float *P, const cpx *tw2, int lane) {
 #pragma unroll
 	for (int i = 0; i < 16; ++i) {
-		const cpx w = (i == 0) ? base : cmul(base, cpx{W32[i][0], W32[i][1]});
-		P[worker + 64 * i] = fast_power_bin(Zs, worker + 64 * i, w);
+		const int k = lane + 32 * i;
+		float pk, pmk;
+		wf_power_pair(Z, k, tw2[k], pk, pmk);
+		P[wf_p_index(k)] = pk;
+		P[wf_p_index(1024 - k)] = pmk;
 	}
-	if (worker == 0) P[1024] = fast_power_bin(Zs, 1024, cpx{-1.f, 0.f});
+	if (lane == 0) {
+		float pk, pmk;
+		wf_power_pair(Z, 512, tw2[512], pk, pmk);
+		P[wf_p_index(512)] = pk;
+	}
 }
 
 }  // namespace srbfft

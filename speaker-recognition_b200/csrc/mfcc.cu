@@ -26,15 +26,18 @@ using srbfft::cpx;
 constexpr int MF_THREADS = 256;
 constexpr double POWER_SPECTRUM_FLOOR = 1e-100;   // MFCC.py:7
 
-struct MfccShape {                 // cached per batch shape
+struct MfccShape {                 // cached per batch shape (slots are REUSED on eviction: their buffers only grow)
 	std::vector<long long> key;    // smp_off + nd
-	int n_utt = 0, n_cta = 0, frames_total = 0, rows_total = 0;
+	int n_utt = 0, n_cta = 0, frames_total = 0, rows_total = 0, NF = 0;
 	std::vector<int> feat_off;     // host copy [n_utt+1]
+	// one device allocation + its pinned host image: smp_off[n_utt+1] (int64) | cta_start | frame_off | feat_off [n_utt+1] (int32) |
+	// chunk records [n_cta] (int4: first sample lo, hi, first output frame row, frames)
+	unsigned char *d_meta = nullptr, *h_meta = nullptr;
+	size_t meta_cap = 0;
+	cudaEvent_t copied = nullptr;  // the upload of h_meta has executed (h_meta may be rewritten)
 	long long *d_smp_off = nullptr;
 	int *d_cta_start = nullptr, *d_frame_off = nullptr, *d_feat_off = nullptr;
-	float *d_ceps = nullptr;
-	double *d_partials = nullptr, *d_stats = nullptr;
-	int4 *d_cta_rec = nullptr;      // fast path, per CTA: {first sample lo, hi, first output frame row, frames (1..NF)}
+	int4 *d_cta_rec = nullptr;
 	uint64_t stamp = 0;
 };
 
@@ -47,14 +50,15 @@ struct MfccPlan {
 	int *d_mel_ptr = nullptr, *d_mel_col = nullptr;
 	double *d_dct = nullptr, *d_dct_t = nullptr;
 	double *d_win_d = nullptr, *d_win2_d = nullptr;   // float64 window / pre-emphasised window (LPC path)
-	// fast path (M == 1024, frame length <= 512): register-resident 4 x 256-point transforms
+	// fast path (M == 1024, frame length <= 512): one warp per frame, register-resident 4 x 256-point transforms
 	bool fast = false;
 	cpx *d_tw1 = nullptr, *d_twA = nullptr;
-	int2 *d_mel_seg = nullptr;       // 16-bin segments of the bands' runs: {first bin, band}; weights d_mel_w16[seg][16]
-	float *d_mel_w16 = nullptr;
+	int2 *d_mel_seg = nullptr;       // 16-bin segments of the bands' runs, starting on 4-bin boundaries: {first bin, band}
+	float *d_mel_w16 = nullptr;      // their weights, [4 quarters][n_seg] float4 (zero outside the band's run)
 	int *d_mel_segptr = nullptr;     // [nb + 1] first segment of every band
 	int n_seg = 0;
-	size_t smem_fast = 0;
+	// work buffers shared by all shapes, grow-only: raw cepstra [frames][CL], CMVN partials [chunks][2 nc], stats [utt][2 nc]
+	DevBuf ceps, partials, stats;
 	std::vector<MfccShape> shapes;
 	uint64_t stamp = 0;
 };
@@ -207,146 +211,210 @@ __global__ void __launch_bounds__(MF_THREADS) mfcc_frames_kernel(const MfccArgs 
 
 
 // ------------------------------------------------------------------------------------------------
-// Fast path: FFT_SIZE = 2048 (M = 1024) and frame length <= 512, i.e. at most 256 non-zero packed inputs -- the
-// reference's default geometry at 16 kHz and 8 kHz.  The zero-padded transform is four 256-point transforms of
-// pre-twiddled inputs, each done by 16 threads x 16 points in registers (fft_core.h: fast_step_a/b), so a frame costs
-// two shared-memory round trips instead of five radix-4 passes, the pruned first pass disappears, and the mel sums are
-// computed by 8-lane groups.  CTA = 256 threads = 4 frames x (4 sub-transforms x 16 lanes).
+// Fast path: FFT_SIZE = 2048 (M = 1024) and frame length <= 512, i.e. at most 256 non-zero packed inputs -- the reference's
+// default geometry at 16 kHz and 8 kHz.  ONE WARP OWNS ONE FRAME (and walks a chunk of consecutive frames of one utterance):
+//   * persistent CTAs of 12 warps, one per SM; a warp's buffers are private, so the only synchronisation is __syncwarp -- round 1
+//     ran 4 frames per CTA of 256 threads with six CTA barriers per frame group and 160 064 CTAs per step
+//   * the audio is streamed: consecutive frames overlap (shift <= frame length), so a frame needs only `shift` NEW samples; the
+//     warp keeps a 1024-sample ring of floats in shared memory and fetches the next 256 samples as ONE 128-bit load per lane
+//     (int16; two for float input), issued a whole frame ahead of its use (round 1: scalar 2-byte loads, I2F stalled on them)
+//   * window and pre-emphasis as the 2-tap form y[i] = w[i] x[i] - w2[i] x[i-1] with the lane's 32 coefficients in registers
+//   * the zero-padded 1024-point packed transform = four 256-point transforms of pre-twiddled inputs, each two radix-16 steps in
+//     registers (16 lanes x 16 points); the half-warps take r = h and r = h + 2, the packed frame is loaded once for both;
+//     XOR-swizzled transpose tiles, second step in place (fft_core.h wf_*; replayed on the CPU by tests/test_fft_schedule_cpu.py)
+//   * bins k and 1024 - k of the power spectrum come from ONE pair of packed results (half the unpack work)
+//   * sparse mel: every band is one contiguous run of bins, cut into 16-bin segments that start on 4-bin boundaries: a lane does
+//     one segment with four 128-bit loads of the (bank-skewed) spectrum and four of the weights; band sums in fixed order, log
+//   * DCT rows 1..n_ceps with float64 accumulation, raw cepstra to HBM, float64 CMVN partial sums per chunk
 // ------------------------------------------------------------------------------------------------
-constexpr int MFF_NF = 4;
-constexpr int MFF_YLEN = 512;
+constexpr int MFW_WARPS = 12;
+constexpr int MFW_THREADS = MFW_WARPS * 32;
+constexpr int MFW_RING = 1024;                    // samples (floats) of the per-warp ring
+constexpr int MFW_YLEN = 512;                     // longest frame of the fast path
+constexpr int MFW_TW2 = 520;                      // unpack twiddles k = 0..512 (padded)
+constexpr size_t MFW_TABLE_BYTES = (size_t)(4 * 256 + 256 + MFW_TW2) * sizeof(cpx);
+constexpr size_t MFW_WARP_BYTES = (size_t)(MFW_RING + srbfft::WF_PLEN) * sizeof(float) + (size_t)4 * srbfft::WF_TILE * sizeof(cpx);
+constexpr size_t MFW_SMEM = MFW_TABLE_BYTES + MFW_WARPS * MFW_WARP_BYTES;
 
-__global__ void __launch_bounds__(MF_THREADS, 4) mfcc_frames_fast_kernel(const MfccArgs A) {
+template <bool F32>
+__global__ void __launch_bounds__(MFW_THREADS, 1) mfcc_frames_warp_kernel(const MfccArgs A, int n_chunks, long long n_total) {
 	extern __shared__ __align__(16) unsigned char mf_smem[];
-	const int tid = threadIdx.x;
-	const int L = A.L, nb = A.nb, nc = A.nc;
-	// Two regions, 51 KB together (4 CTAs per SM at 64 registers).  Region A: sample span -> transpose tiles T -> sub-transform
-	// outputs Zs, written IN PLACE over T after a barrier -> later the mel / log / cepstrum scratch.  Region B: windowed
-	// frames ybuf -> later the power spectrum P.
-	cpx *T = reinterpret_cast<cpx *>(mf_smem);                                   // [NF][4][16*17]
-	cpx *Zs = T;                                                                 // [NF][4][260]  (aliases T)
-	float *ybuf = reinterpret_cast<float *>(T + MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE);   // [NF][512], then P [NF][1028]
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int L = A.L, nb = A.nb, nc = A.nc, shift = A.shift;
+	cpx *s_tw1 = reinterpret_cast<cpx *>(mf_smem);          // [4][256] W_1024^{n r} (row 0 = 1)
+	cpx *s_twA = s_tw1 + 4 * 256;                           // [16][16]  W_256^{u q2}
+	cpx *s_tw2 = s_twA + 256;                               // [0..512]  exp(-2 pi i k / 2048)
+	unsigned char *wb = mf_smem + MFW_TABLE_BYTES + (size_t)warp * MFW_WARP_BYTES;
+	float *ring = reinterpret_cast<float *>(wb);            // [1024] raw samples as floats, position = (index - base) & 1023
+	float *Pb = ring + MFW_RING;                            // [WF_PLEN] windowed frame (first 512 floats), then the skewed power spectrum
+	cpx *TZ = reinterpret_cast<cpx *>(Pb + srbfft::WF_PLEN);    // [4][256] transpose tiles / sub-transform outputs, later the mel scratch
 
-	// one 16-byte record per CTA (built on the host with the shape; a binary search over the utterance table cost six
-	// dependent global loads before the first sample could be requested)
-	const int4 rec = __ldg(A.cta_rec + blockIdx.x);
-	const long long s0 = ((long long)(unsigned)rec.x) | ((long long)rec.y << 32);
-	const int row0 = rec.z, nfr = rec.w;
-
-	// window then pre-emphasis (MFCC.py:61-64) as a 2-tap form y[i] = w[i] x[i] - w2[i] x[i-1] (w2[0] = 0).  The CTA's frames
-	// overlap, so its whole sample span (plus the sample before it) is staged once in shared memory as floats: one coalesced
-	// pass, (NF-1) shift + L + 1 conversions instead of 2 NF L scattered 2-byte loads.
-	{
-		float *span = reinterpret_cast<float *>(T);                              // region A is free until the first FFT step
-		const int n_span = (nfr - 1) * A.shift + L + 1;                          // span[j] = sample s0 - 1 + j
-		for (int j = tid; j < n_span; j += MF_THREADS) {
-			const long long g = s0 - 1 + j;
-			float v = 0.f;
-			if (g >= 0) v = A.is_f32 ? __ldg(reinterpret_cast<const float *>(A.pcm) + g) : (float)__ldg(reinterpret_cast<const int16_t *>(A.pcm) + g);
-			span[j] = v;
-		}
-		__syncthreads();
-		const float w0 = tid < L ? __ldg(A.win + tid) : 0.f, w1 = tid + 256 < L ? __ldg(A.win + tid + 256) : 0.f;
-		const float v0 = tid < L ? __ldg(A.win2 + tid) : 0.f, v1 = tid + 256 < L ? __ldg(A.win2 + tid + 256) : 0.f;
+	for (int i = tid; i < 4 * 256; i += MFW_THREADS) s_tw1[i] = i < 256 ? cpx{1.f, 0.f} : A.tw1[i - 256];
+	for (int i = tid; i < 256; i += MFW_THREADS) s_twA[i] = A.twA[i];
+	for (int i = tid; i <= 512; i += MFW_THREADS) s_tw2[i] = A.tw2[i];
+	for (int i = lane; i < srbfft::WF_PLEN; i += 32) Pb[i] = 0.f;      // the bins beyond 1024 a last mel segment may touch stay 0 (weights 0)
+	// this lane's window coefficients for the frame positions i = lane + 32 j (zero beyond the frame length)
+	float wr[16], w2r[16];
 #pragma unroll
-		for (int it = 0; it < 8; ++it) {
-			const int ff = it >> 1, i = tid + ((it & 1) << 8);
-			float y = 0.f;
-			if (ff < nfr && i < L) {
-				const float *sp = span + ff * A.shift + i;
-				y = fmaf(-((it & 1) ? v1 : v0), sp[0], ((it & 1) ? w1 : w0) * sp[1]);
-			}
-			ybuf[ff * MFF_YLEN + i] = y;
-		}
+	for (int j = 0; j < 16; ++j) {
+		const int i = lane + 32 * j;
+		wr[j] = i < L ? __ldg(A.win + i) : 0.f;
+		w2r[j] = i < L ? __ldg(A.win2 + i) : 0.f;
 	}
-	__syncthreads();
-	const int f = tid >> 6, r = (tid >> 4) & 3, u = tid & 15;
-	cpx *Tfr = T + (f * 4 + r) * 16 * srbfft::FAST_TSTRIDE;
-	srbfft::fast_step_a(reinterpret_cast<const cpx *>(ybuf + f * MFF_YLEN), A.tw1, A.twA, Tfr, r, u);
-	__syncthreads();
-	{
-		cpx in[16];
-		srbfft::fast_step_b_load(Tfr, u, in);
-		__syncthreads();                                                         // every tile has been read: Zs may overwrite them
-		srbfft::fast_step_b_store(in, Zs + (f * 4 + r) * srbfft::FAST_ZSTRIDE, u);
-	}
-	__syncthreads();
-	float *P = ybuf;                                                             // [NF][1028], natural bin order (the frames are consumed)
-	constexpr int PSTR = srbfft::FAST_PSTRIDE;
-	srbfft::fast_power_unpack(Zs + f * 4 * srbfft::FAST_ZSTRIDE, P + f * PSTR, A.tw2, tid & 63);
 	__syncthreads();
 
-	// mel + log.  A band's non-zeros are one contiguous run of bins (triangular filters; checked on the host).  The runs are cut
-	// into 16-bin segments (the last one end-aligned, weights zero where it overlaps its predecessor): one thread per
-	// (frame, segment) does 16 multiply-adds on consecutive P values with its weights in four 128-bit loads, all items carry
-	// the same work; then one thread per (frame, band) adds the band's segment sums in segment order (deterministic) and
-	// takes the log.  (The first version walked (frame, band) items with 8-lane groups: 25 instructions per multiply-add.)
-	float *logE = reinterpret_cast<float *>(T);                                  // [NF][nb]   (region A: Zs is consumed)
-	float *segsum = logE + 512;                                                  // [NF][n_seg]  (n_seg <= 384, host-checked)
-	{
-		const int n_seg = A.n_seg, items = MFF_NF * n_seg;
-		for (int item = tid; item < items; item += MF_THREADS) {
-			const int ff = item / n_seg, sg = item - ff * n_seg;
-			const int2 d = __ldg(A.mel_seg + sg);
-			const float4 *w4 = reinterpret_cast<const float4 *>(A.mel_w16 + (size_t)sg * 16);
-			const float *Pp = P + ff * PSTR + d.x;
-			const float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1), w2 = __ldg(w4 + 2), w3 = __ldg(w4 + 3);
-			float e0 = w0.x * Pp[0], e1 = w0.y * Pp[1], e2 = w0.z * Pp[2], e3 = w0.w * Pp[3];
-			e0 = fmaf(w1.x, Pp[4], e0);
-			e1 = fmaf(w1.y, Pp[5], e1);
-			e2 = fmaf(w1.z, Pp[6], e2);
-			e3 = fmaf(w1.w, Pp[7], e3);
-			e0 = fmaf(w2.x, Pp[8], e0);
-			e1 = fmaf(w2.y, Pp[9], e1);
-			e2 = fmaf(w2.z, Pp[10], e2);
-			e3 = fmaf(w2.w, Pp[11], e3);
-			e0 = fmaf(w3.x, Pp[12], e0);
-			e1 = fmaf(w3.y, Pp[13], e1);
-			e2 = fmaf(w3.z, Pp[14], e2);
-			e3 = fmaf(w3.w, Pp[15], e3);
-			segsum[item] = (e0 + e1) + (e2 + e3);
+	const int h = lane >> 4, u = lane & 15;
+	constexpr int G = F32 ? 4 : 8;                            // elements per 16 bytes
+	const long long ptr_elems = (long long)(reinterpret_cast<uintptr_t>(A.pcm) / (F32 ? 4 : 2));
+
+	// 8 consecutive samples starting at absolute index i0 (a multiple of G past `base`), zeros outside [0, n_total)
+	auto load8 = [&](long long i0, float (&v)[8]) {
+		if (i0 >= 0 && i0 + 8 <= n_total) {
+			if (F32) {
+				const float4 a = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(A.pcm) + i0));
+				const float4 b = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(A.pcm) + i0) + 1);
+				v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+			} else {
+				const int4 q = __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const int16_t *>(A.pcm) + i0));
+				const int w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+				for (int t = 0; t < 4; ++t) {
+					v[2 * t] = (float)(short)(w4[t] & 0xffff);
+					v[2 * t + 1] = (float)(short)(w4[t] >> 16);
+				}
+			}
+		} else {
+#pragma unroll
+			for (int t = 0; t < 8; ++t) {
+				const long long g = i0 + t;
+				float x = 0.f;
+				if (g >= 0 && g < n_total) x = F32 ? __ldg(reinterpret_cast<const float *>(A.pcm) + g) : (float)__ldg(reinterpret_cast<const int16_t *>(A.pcm) + g);
+				v[t] = x;
+			}
 		}
-		__syncthreads();
-		for (int t = tid; t < MFF_NF * nb; t += MF_THREADS) {
-			const int ff = t / nb, b = t - ff * nb;
-			const int s0 = __ldg(A.mel_segptr + b), s1 = __ldg(A.mel_segptr + b + 1);
-			float e = 0.f;
-			for (int sg = s0; sg < s1; ++sg) e += segsum[ff * n_seg + sg];
-			logE[t] = e > 0.f ? logf(e) : __ldg(A.logfloor + b);
+	};
+	auto commit8 = [&](long long i0, long long base, const float (&v)[8]) {
+		float4 *dst = reinterpret_cast<float4 *>(ring + ((i0 - base) & (MFW_RING - 1)));
+		dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+		dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+	};
+
+	for (int c = blockIdx.x * MFW_WARPS + warp; c < n_chunks; c += gridDim.x * MFW_WARPS) {
+		const int4 rec = __ldg(A.cta_rec + c);
+		const long long a0 = ((long long)(unsigned)rec.x) | ((long long)rec.y << 32);
+		const int row0 = rec.z, nfr = rec.w;
+		// ring origin: the last index <= a0 - 1 whose address is 16-byte aligned
+		long long m = (ptr_elems + a0 - 1) % G;
+		if (m < 0) m += G;
+		const long long base = a0 - 1 - m;
+		long long loaded_end = base;                           // samples [base, loaded_end) are in the ring
+		float pend[8];                                         // the NEXT 256-sample block's share of this lane, in flight
+		{
+			float v0[8], v1[8], v2[8];
+			load8(base + 8 * lane, v0);
+			load8(base + 256 + 8 * lane, v1);
+			load8(base + 512 + 8 * lane, v2);
+			load8(base + 768 + 8 * lane, pend);
+			__syncwarp();                                      // the previous chunk's last frame has left the ring
+			commit8(base + 8 * lane, base, v0);
+			commit8(base + 256 + 8 * lane, base, v1);
+			commit8(base + 512 + 8 * lane, base, v2);
+			loaded_end = base + 768;
 		}
-	}
-	__syncthreads();
-	// DCT rows 1..n_ceps, float64 accumulate.  One warp per frame: lane = (band parity, coefficient), the table is stored
-	// transposed [band][16 coefficients] so that a request reads two contiguous 128-byte rows (the row-major table cost
-	// eight 32-byte sectors per request: a fifth of the kernel's L1 wavefronts); the two parities are added by one shuffle
-	// (fixed order -> deterministic).
-	float *cep = logE + MFF_NF * nb;                                             // [NF][nc]
-	if (tid < MFF_NF * 32) {
-		const int ff = tid >> 5, h = (tid >> 4) & 1, i = tid & 15;
-		const float *le = logE + ff * nb;
-		double acc = 0.0;
-		for (int b2 = h; b2 < nb; b2 += 2) acc = fma(__ldg(A.dct_t + b2 * 16 + i), (double)le[b2], acc);
-		acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-		if (h == 0 && i < nc) {
-			const float c = (float)acc;
-			cep[ff * nc + i] = c;
-			if (ff < nfr) A.ceps[(size_t)(row0 + ff) * A.CL + i] = c;
+		double cs = 0.0, css = 0.0;                            // CMVN partial sums of coefficient `lane`
+		for (int f = 0; f < nfr; ++f) {
+			const long long a = a0 + (long long)f * shift;
+			while (loaded_end < a + L) {                       // at most once per frame in the steady state (shift <= 256)
+				commit8(loaded_end + 8 * lane, base, pend);
+				loaded_end += 256;
+				load8(loaded_end + 8 * lane, pend);
+			}
+			__syncwarp();
+			// ---- window, then pre-emphasis (MFCC.py:61-64) as the 2-tap form
+			{
+				const int o = (int)((a - base) & (MFW_RING - 1));
+#pragma unroll
+				for (int j = 0; j < 16; ++j) {
+					const int i = lane + 32 * j;
+					const float x1 = ring[(o + i) & (MFW_RING - 1)], x0 = ring[(o + i - 1) & (MFW_RING - 1)];
+					Pb[i] = fmaf(-w2r[j], x0, wr[j] * x1);
+				}
+			}
+			__syncwarp();
+			// ---- first radix-16 step of the two sub-transforms of this half-warp (r = h, h + 2)
+			{
+				cpx z[16];
+				const cpx *yb = reinterpret_cast<const cpx *>(Pb);
+#pragma unroll
+				for (int n2 = 0; n2 < 16; ++n2) z[n2] = yb[u + 16 * n2];
+				srbfft::wf_step_a(z, s_tw1 + h * 256, s_twA, TZ + h * srbfft::WF_TILE, u);
+				srbfft::wf_step_a(z, s_tw1 + (h + 2) * 256, s_twA, TZ + (h + 2) * srbfft::WF_TILE, u);
+			}
+			__syncwarp();
+			// ---- second radix-16 step, in place tile by tile
+#pragma unroll
+			for (int round = 0; round < 2; ++round) {
+				const int r = h + 2 * round;
+				cpx in[16];
+				srbfft::wf_step_b_load(TZ + r * srbfft::WF_TILE, u, in);
+				__syncwarp();
+				srbfft::wf_step_b_store(in, TZ, r, u);
+			}
+			__syncwarp();
+			// ---- power spectrum, bins k and 1024 - k from one pair
+			srbfft::wf_power_lane(TZ, Pb, s_tw2, lane);
+			__syncwarp();
+			// ---- sparse mel + log.  Floor semantics: the reference clamps each bin to 1e-100, which fp32 cannot hold; a band whose
+			// fp32 energy is exactly 0 takes log(1e-100 * sum of its weights) instead.
+			float *segsum = reinterpret_cast<float *>(TZ);         // [n_seg]   (the sub-transform outputs are consumed)
+			float *logE = segsum + 512;                            // [nb]
+			{
+				const int n_seg = A.n_seg;
+				const float4 *w4 = reinterpret_cast<const float4 *>(A.mel_w16);
+				for (int sg = lane; sg < n_seg; sg += 32) {
+					const int g0 = __ldg(A.mel_seg + sg).x >> 2;       // first bin / 4
+					float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+#pragma unroll
+					for (int q = 0; q < 4; ++q) {
+						const int g = g0 + q;
+						const float4 pv = *reinterpret_cast<const float4 *>(Pb + 4 * (g + (g >> 2)));
+						const float4 wv = __ldg(w4 + (size_t)q * n_seg + sg);
+						e0 = fmaf(wv.x, pv.x, e0);
+						e1 = fmaf(wv.y, pv.y, e1);
+						e2 = fmaf(wv.z, pv.z, e2);
+						e3 = fmaf(wv.w, pv.w, e3);
+					}
+					segsum[sg] = (e0 + e1) + (e2 + e3);
+				}
+				__syncwarp();
+				for (int b = lane; b < nb; b += 32) {
+					const int s0 = __ldg(A.mel_segptr + b), s1 = __ldg(A.mel_segptr + b + 1);
+					float e = 0.f;
+					for (int sg = s0; sg < s1; ++sg) e += segsum[sg];
+					logE[b] = e > 0.f ? logf(e) : __ldg(A.logfloor + b);
+				}
+			}
+			__syncwarp();
+			// ---- DCT rows 1..n_ceps, float64 accumulate: lane = (band parity, coefficient); the table is transposed [band][16]
+			{
+				const int i = lane & 15;
+				double acc = 0.0;
+				for (int b2 = h; b2 < nb; b2 += 2) acc = fma(__ldg(A.dct_t + b2 * 16 + i), (double)logE[b2], acc);
+				acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+				if (lane < A.CL) {
+					const float cf = lane < nc ? (float)acc : 0.f;
+					A.ceps[(size_t)(row0 + f) * A.CL + lane] = cf;
+					if (lane < nc) {
+						cs += (double)cf;
+						css = fma((double)cf, (double)cf, css);
+					}
+				}
+			}
 		}
-	}
-	for (int t = tid; t < MFF_NF * (A.CL - nc); t += MF_THREADS) {
-		const int ff = t / (A.CL - nc), i = nc + t - ff * (A.CL - nc);
-		if (ff < nfr) A.ceps[(size_t)(row0 + ff) * A.CL + i] = 0.f;
-	}
-	__syncthreads();
-	if (tid < nc) {
-		double s = 0.0, ss = 0.0;
-		for (int ff = 0; ff < nfr; ++ff) {
-			const double c = (double)cep[ff * nc + tid];
-			s += c;
-			ss = fma(c, c, ss);
+		if (lane < nc) {
+			A.partials[(size_t)c * 2 * nc + lane] = cs;
+			A.partials[(size_t)c * 2 * nc + nc + lane] = css;
 		}
-		A.partials[(size_t)blockIdx.x * 2 * nc + tid] = s;
-		A.partials[(size_t)blockIdx.x * 2 * nc + nc + tid] = ss;
 	}
 }
 
@@ -512,29 +580,30 @@ static int build_tables(MfccPlan *p) {
 				tw1[(r - 1) * 256 + n] = cpx{(float)cos(-2.0 * M_PI * n * r / 1024), (float)sin(-2.0 * M_PI * n * r / 1024)};
 		for (int q2 = 0; q2 < 16; ++q2)
 			for (int u = 0; u < 16; ++u) twA[q2 * 16 + u] = cpx{(float)cos(-2.0 * M_PI * u * q2 / 256), (float)sin(-2.0 * M_PI * u * q2 / 256)};
-		// 16-bin segments of the runs (see the mel stage of mfcc_frames_fast_kernel)
+		// 16-bin segments of the runs, each starting on a 4-bin boundary (see the mel stage of mfcc_frames_warp_kernel)
 		std::vector<int2> seg;
 		std::vector<float> w16;
 		std::vector<int> segptr(nb + 1, 0);
 		for (int b = 0; b < nb; ++b) {
 			const int n = ptr[b + 1] - ptr[b], c0 = n > 0 ? col[ptr[b]] : 0;
-			int covered = c0;                                    // bins of the run below this index are already in a segment
-			for (int st = c0; covered < c0 + n;) {
-				int first = st;
-				if (first + 16 > c0 + n) first = std::max(0, c0 + n - 16);   // end-align the last segment
+			for (int first = c0 & ~3; first < c0 + n; first += 16) {
 				seg.push_back(make_int2(first, b));
 				for (int i = 0; i < 16; ++i) {
 					const int bin = first + i;
-					const bool in = bin >= covered && bin < c0 + n;
-					w16.push_back(in ? val[ptr[b] + (bin - c0)] : 0.f);
+					w16.push_back(bin >= c0 && bin < c0 + n ? val[ptr[b] + (bin - c0)] : 0.f);
 				}
-				covered = first + 16;
-				st = covered;
 			}
 			segptr[b + 1] = (int)seg.size();
 		}
+		{   // [seg][16] -> [4 quarters][seg] float4: the lanes of a warp read consecutive 16-byte words
+			const size_t ns = seg.size();
+			std::vector<float> t(w16.size());
+			for (size_t sg = 0; sg < ns; ++sg)
+				for (int i = 0; i < 16; ++i) t[((size_t)(i >> 2) * ns + sg) * 4 + (i & 3)] = w16[sg * 16 + i];
+			w16.swap(t);
+		}
 		p->n_seg = (int)seg.size();
-		if (p->n_seg > 384 || p->n_seg == 0) p->fast = false;   // the segment sums share a 1.5 K-float shared-memory region
+		if (p->n_seg > 512 || p->n_seg == 0) p->fast = false;   // the segment sums share a shared-memory region of 512 floats
 		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_seg, seg) ||
 		    to_device(&p->d_mel_w16, w16) || to_device(&p->d_mel_segptr, segptr))
 			return 1;
@@ -570,8 +639,8 @@ MfccPlan *mfcc_plan_create(int fs, double win_ms, double shift_ms, int nfft, int
 		delete p;
 		return nullptr;
 	}
-	p->fast = (p->M == 1024 && p->L <= MFF_YLEN && n_filters + n_ceps <= MFF_YLEN);
-	p->NF = p->fast ? MFF_NF : std::max(1, std::min(16, 4096 / p->M));
+	p->fast = (p->M == 1024 && p->L <= MFW_YLEN && n_ceps <= 16);
+	p->NF = std::max(1, std::min(16, 4096 / p->M));      // generic kernel: frames per CTA (the fast path sizes its chunks per batch)
 	// the log/cepstra scratch reuses one FFT buffer: NF*(nb+nc) floats must fit in NF*M*2 floats
 	if ((p->nb + p->nc) > 2 * p->M) {
 		set_error("mfcc: FFT_SIZE %d too small for %d filters", nfft, n_filters);
@@ -579,8 +648,7 @@ MfccPlan *mfcc_plan_create(int fs, double win_ms, double shift_ms, int nfft, int
 		return nullptr;
 	}
 	p->smem = (size_t)2 * p->NF * p->M * sizeof(cpx) + ((size_t)(p->NF - 1) * p->shift + p->L) * sizeof(float);
-	p->smem_fast = (size_t)MFF_NF * 4 * 16 * srbfft::FAST_TSTRIDE * sizeof(cpx) + (size_t)MFF_NF * srbfft::FAST_PSTRIDE * sizeof(float);
-	if (p->smem > 200 * 1024 || (p->fast && p->smem_fast > 110 * 1024)) {
+	if (p->smem > 200 * 1024) {
 		set_error("mfcc: frame shift %d too large for the shared-memory staging", p->shift);
 		delete p;
 		return nullptr;
@@ -590,7 +658,8 @@ MfccPlan *mfcc_plan_create(int fs, double win_ms, double shift_ms, int nfft, int
 		return nullptr;
 	}
 	if (cudaFuncSetAttribute(mfcc_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-	    cudaFuncSetAttribute(mfcc_frames_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+	    cudaFuncSetAttribute(mfcc_frames_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+	    cudaFuncSetAttribute(mfcc_frames_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
 		set_error("mfcc: cudaFuncSetAttribute failed");
 		mfcc_plan_free(p);
 		return nullptr;
@@ -599,20 +668,18 @@ MfccPlan *mfcc_plan_create(int fs, double win_ms, double shift_ms, int nfft, int
 }
 
 static void free_shape(MfccShape &s) {
-	cudaFree(s.d_smp_off);
-	cudaFree(s.d_cta_start);
-	cudaFree(s.d_frame_off);
-	cudaFree(s.d_feat_off);
-	cudaFree(s.d_ceps);
-	cudaFree(s.d_partials);
-	cudaFree(s.d_stats);
-	cudaFree(s.d_cta_rec);
+	if (s.d_meta) cudaFree(s.d_meta);
+	if (s.h_meta) cudaFreeHost(s.h_meta);
+	if (s.copied) cudaEventDestroy(s.copied);
 	s = MfccShape();
 }
 
 void mfcc_plan_free(MfccPlan *p) {
 	if (!p) return;
 	for (auto &s : p->shapes) free_shape(s);
+	p->ceps.release();
+	p->partials.release();
+	p->stats.release();
 	cudaFree(p->d_win);
 	cudaFree(p->d_win2);
 	cudaFree(p->d_mel_val);
@@ -637,6 +704,31 @@ int mfcc_frame_len(const MfccPlan *p) { return p->L; }
 int mfcc_frame_shift(const MfccPlan *p) { return p->shift; }
 int mfcc_n_ceps(const MfccPlan *p) { return p->nc; }
 
+static bool mfcc_force_generic() {      // A/B switch: run the generic shared-memory-FFT kernel on fast-path geometries too
+	static const bool f = [] { const char *e = getenv("SRB200_MFCC_GENERIC"); return e && e[0] == '1'; }();
+	return f;
+}
+
+// frames per chunk of the warp-per-frame kernel: chunks are dealt round-robin to the (SMs x 12) resident warps, so pick the
+// chunk length in [32, 96] for which the number of chunks is closest below a whole number of rounds
+static int pick_chunk_frames(const std::vector<long long> &T, int n_warps) {
+	int best = 64;
+	double best_eff = -1.0;
+	for (int nf = 96; nf >= 32; --nf) {
+		long long chunks = 0;
+		for (long long t : T) chunks += (t + nf - 1) / nf;
+		const long long rounds = (chunks + n_warps - 1) / n_warps;
+		const double eff = (double)chunks / (double)(rounds * n_warps) - 0.002 * (96 - nf) / 64.0;      // slight preference for long chunks
+		if (eff > best_eff) {
+			best_eff = eff;
+			best = nf;
+		}
+	}
+	return best;
+}
+
+// Shape bookkeeping WITHOUT steady-state allocations: up to 16 shapes are cached; on a miss the least recently used slot is
+// rewritten in place (pinned host image -> one async copy on the caller's stream); every buffer only ever grows.
 static int get_shape(MfccPlan *p, const long long *smp_off, int n_utt, int nd, cudaStream_t st, MfccShape **out) {
 	std::vector<long long> key(smp_off, smp_off + n_utt + 1);
 	key.push_back(nd);
@@ -646,62 +738,76 @@ static int get_shape(MfccPlan *p, const long long *smp_off, int n_utt, int nd, c
 			*out = &s;
 			return 0;
 		}
-	std::vector<int> cta_start(n_utt + 1), frame_off(n_utt + 1), feat_off(n_utt + 1);
-	cta_start[0] = frame_off[0] = feat_off[0] = 0;
+	std::vector<long long> T(n_utt);
 	for (int u = 0; u < n_utt; ++u) {
 		const long long n = smp_off[u + 1] - smp_off[u];
 		SRB_REQUIRE(n > 5LL * p->L, "mfcc: Signal too short! (utterance %d has %lld samples, need > 5*%d; MFCC.py:56)", u, n, p->L);
-		const long long T = (n - p->L) / p->shift + 1;   // MFCC.py:57
-		SRB_REQUIRE(T - nd >= 1, "mfcc: utterance %d has too few frames for nd=%d", u, nd);
-		SRB_REQUIRE((long long)frame_off[u] + T < (1LL << 31) - 64, "mfcc: batch too large (frame index overflows int32)");
-		frame_off[u + 1] = frame_off[u] + (int)T;
-		feat_off[u + 1] = feat_off[u] + (int)(T - nd);
-		cta_start[u + 1] = cta_start[u] + (int)((T + p->NF - 1) / p->NF);
+		T[u] = (n - p->L) / p->shift + 1;   // MFCC.py:57
+		SRB_REQUIRE(T[u] - nd >= 1, "mfcc: utterance %d has too few frames for nd=%d", u, nd);
 	}
-	if (p->shapes.size() >= 16) {
-		size_t lru = 0;
-		for (size_t i = 1; i < p->shapes.size(); ++i)
-			if (p->shapes[i].stamp < p->shapes[lru].stamp) lru = i;
-		SRB_CUDA(cudaStreamSynchronize(st));
-		free_shape(p->shapes[lru]);
-		p->shapes.erase(p->shapes.begin() + lru);
+	const int NF = (p->fast && !mfcc_force_generic()) ? pick_chunk_frames(T, ctx().sm_count * MFW_WARPS) : p->NF;
+	std::vector<int> cta_start(n_utt + 1), frame_off(n_utt + 1), feat_off(n_utt + 1);
+	cta_start[0] = frame_off[0] = feat_off[0] = 0;
+	for (int u = 0; u < n_utt; ++u) {
+		SRB_REQUIRE((long long)frame_off[u] + T[u] < (1LL << 31) - 64, "mfcc: batch too large (frame index overflows int32)");
+		frame_off[u + 1] = frame_off[u] + (int)T[u];
+		feat_off[u + 1] = feat_off[u] + (int)(T[u] - nd);
+		cta_start[u + 1] = cta_start[u] + (int)((T[u] + NF - 1) / NF);
 	}
-	MfccShape s;
-	s.key = key;
-	s.n_utt = n_utt;
-	s.n_cta = cta_start[n_utt];
-	s.frames_total = frame_off[n_utt];
-	s.rows_total = feat_off[n_utt];
-	s.feat_off = feat_off;
-	s.stamp = ++p->stamp;
+	MfccShape *s = nullptr;
+	if (p->shapes.size() < 16) {
+		p->shapes.reserve(16);                 // pointers handed out earlier stay valid
+		p->shapes.emplace_back();
+		s = &p->shapes.back();
+		SRB_CUDA(cudaEventCreateWithFlags(&s->copied, cudaEventDisableTiming));
+	} else {
+		s = &p->shapes[0];
+		for (auto &c : p->shapes)
+			if (c.stamp < s->stamp) s = &c;
+		SRB_CUDA(cudaEventSynchronize(s->copied));      // its previous upload has executed: the pinned image may be rewritten
+	}
+	s->key = key;
+	s->n_utt = n_utt;
+	s->n_cta = cta_start[n_utt];
+	s->frames_total = frame_off[n_utt];
+	s->rows_total = feat_off[n_utt];
+	s->NF = NF;
+	s->feat_off = feat_off;
+	s->stamp = ++p->stamp;
 	const size_t nu = (size_t)n_utt + 1;
-	SRB_CUDA(cudaMalloc(&s.d_smp_off, nu * sizeof(long long)));
-	SRB_CUDA(cudaMalloc(&s.d_cta_start, nu * sizeof(int)));
-	SRB_CUDA(cudaMalloc(&s.d_frame_off, nu * sizeof(int)));
-	SRB_CUDA(cudaMalloc(&s.d_feat_off, nu * sizeof(int)));
-	SRB_CUDA(cudaMalloc(&s.d_ceps, (size_t)s.frames_total * p->CL * sizeof(float)));
-	SRB_CUDA(cudaMalloc(&s.d_partials, (size_t)s.n_cta * 2 * p->nc * sizeof(double)));
-	SRB_CUDA(cudaMalloc(&s.d_stats, (size_t)n_utt * 2 * p->nc * sizeof(double)));
-	{
-		std::vector<int4> rec((size_t)s.n_cta);
-		for (int u = 0; u < n_utt; ++u) {
-			const int T = frame_off[u + 1] - frame_off[u];
-			for (int c = cta_start[u]; c < cta_start[u + 1]; ++c) {
-				const int fr0 = (c - cta_start[u]) * p->NF;
-				const long long s0 = smp_off[u] + (long long)fr0 * p->shift;
-				rec[c] = make_int4((int)(unsigned)(s0 & 0xFFFFFFFFll), (int)(s0 >> 32), frame_off[u] + fr0, std::min(p->NF, T - fr0));
-			}
+	const size_t off_cta = nu * sizeof(long long), off_frame = off_cta + nu * sizeof(int), off_feat = off_frame + nu * sizeof(int);
+	const size_t off_rec = (off_feat + nu * sizeof(int) + 15) & ~(size_t)15, bytes = off_rec + (size_t)s->n_cta * sizeof(int4);
+	if (bytes > s->meta_cap) {
+		if (s->d_meta) {
+			SRB_CUDA(cudaStreamSynchronize(st));
+			cudaFree(s->d_meta);
+			cudaFreeHost(s->h_meta);
+			s->d_meta = s->h_meta = nullptr;
 		}
-		SRB_CUDA(cudaMalloc(&s.d_cta_rec, rec.size() * sizeof(int4)));
-		SRB_CUDA(cudaMemcpy(s.d_cta_rec, rec.data(), rec.size() * sizeof(int4), cudaMemcpyHostToDevice));
+		const size_t want = bytes + bytes / 2 + 4096;
+		SRB_CUDA(cudaMalloc(&s->d_meta, want));
+		SRB_CUDA(cudaMallocHost(&s->h_meta, want));
+		s->meta_cap = want;
 	}
-	SRB_CUDA(cudaMemcpyAsync(s.d_smp_off, smp_off, nu * sizeof(long long), cudaMemcpyHostToDevice, st));
-	SRB_CUDA(cudaMemcpyAsync(s.d_cta_start, cta_start.data(), nu * sizeof(int), cudaMemcpyHostToDevice, st));
-	SRB_CUDA(cudaMemcpyAsync(s.d_frame_off, frame_off.data(), nu * sizeof(int), cudaMemcpyHostToDevice, st));
-	SRB_CUDA(cudaMemcpyAsync(s.d_feat_off, feat_off.data(), nu * sizeof(int), cudaMemcpyHostToDevice, st));
-	SRB_CUDA(cudaStreamSynchronize(st));
-	p->shapes.push_back(s);
-	*out = &p->shapes.back();
+	memcpy(s->h_meta, smp_off, nu * sizeof(long long));
+	memcpy(s->h_meta + off_cta, cta_start.data(), nu * sizeof(int));
+	memcpy(s->h_meta + off_frame, frame_off.data(), nu * sizeof(int));
+	memcpy(s->h_meta + off_feat, feat_off.data(), nu * sizeof(int));
+	int4 *rec = reinterpret_cast<int4 *>(s->h_meta + off_rec);
+	for (int u = 0; u < n_utt; ++u)
+		for (int c = cta_start[u]; c < cta_start[u + 1]; ++c) {
+			const int fr0 = (c - cta_start[u]) * NF;
+			const long long s0 = smp_off[u] + (long long)fr0 * p->shift;
+			rec[c] = make_int4((int)(unsigned)(s0 & 0xFFFFFFFFll), (int)(s0 >> 32), frame_off[u] + fr0, (int)std::min<long long>(NF, T[u] - fr0));
+		}
+	s->d_smp_off = reinterpret_cast<long long *>(s->d_meta);
+	s->d_cta_start = reinterpret_cast<int *>(s->d_meta + off_cta);
+	s->d_frame_off = reinterpret_cast<int *>(s->d_meta + off_frame);
+	s->d_feat_off = reinterpret_cast<int *>(s->d_meta + off_feat);
+	s->d_cta_rec = reinterpret_cast<int4 *>(s->d_meta + off_rec);
+	SRB_CUDA(cudaMemcpyAsync(s->d_meta, s->h_meta, bytes, cudaMemcpyHostToDevice, st));
+	SRB_CUDA(cudaEventRecord(s->copied, st));
+	*out = s;
 	return 0;
 }
 
@@ -715,6 +821,9 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	SRB_REQUIRE(ld >= out_dim, "mfcc: ld %d < feature dim %d", ld, out_dim);
 	MfccShape *s = nullptr;
 	if (get_shape(p, smp_off, n_utt, nd, st, &s)) return 1;
+	if (p->ceps.ensure((size_t)s->frames_total * p->CL * sizeof(float)) || p->partials.ensure((size_t)s->n_cta * 2 * p->nc * sizeof(double)) ||
+	    p->stats.ensure((size_t)n_utt * 2 * p->nc * sizeof(double)))
+		return 1;
 	MfccArgs a;
 	a.pcm = d_pcm;
 	a.is_f32 = is_f32;
@@ -729,7 +838,7 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.nb = p->nb;
 	a.nc = p->nc;
 	a.CL = p->CL;
-	a.NF = p->NF;
+	a.NF = s->NF;
 	a.win = p->d_win;
 	a.win2 = p->d_win2;
 	a.tw = p->d_tw;
@@ -740,8 +849,8 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.logfloor = p->d_logfloor;
 	a.dct = p->d_dct;
 	a.dct_t = p->d_dct_t;
-	a.ceps = s->d_ceps;
-	a.partials = s->d_partials;
+	a.ceps = p->ceps.as<float>();
+	a.partials = p->partials.as<double>();
 	a.tw1 = p->d_tw1;
 	a.twA = p->d_twA;
 	a.cta_rec = s->d_cta_rec;
@@ -749,17 +858,20 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	a.mel_w16 = p->d_mel_w16;
 	a.mel_segptr = p->d_mel_segptr;
 	a.n_seg = p->n_seg;
-	static const bool force_generic = [] { const char *e = getenv("SRB200_MFCC_GENERIC"); return e && e[0] == '1'; }();
-	if (p->fast && !force_generic) mfcc_frames_fast_kernel<<<s->n_cta, MF_THREADS, p->smem_fast, st>>>(a);
-	else mfcc_frames_kernel<<<s->n_cta, MF_THREADS, p->smem, st>>>(a);
+	if (p->fast && !mfcc_force_generic()) {
+		const int grid = std::min(ctx().sm_count, (s->n_cta + MFW_WARPS - 1) / MFW_WARPS);
+		const long long n_total = smp_off[n_utt];
+		if (is_f32) mfcc_frames_warp_kernel<true><<<grid, MFW_THREADS, MFW_SMEM, st>>>(a, s->n_cta, n_total);
+		else mfcc_frames_warp_kernel<false><<<grid, MFW_THREADS, MFW_SMEM, st>>>(a, s->n_cta, n_total);
+	} else mfcc_frames_kernel<<<s->n_cta, MF_THREADS, p->smem, st>>>(a);
 	SRB_CUDA(cudaGetLastError());
 	if (cmvn) {
-		mfcc_stats_kernel<<<n_utt, 1024, 0, st>>>(s->d_partials, s->d_cta_start, s->d_frame_off, p->nc, s->d_stats);
+		mfcc_stats_kernel<<<n_utt, 1024, 0, st>>>(p->partials.as<double>(), s->d_cta_start, s->d_frame_off, p->nc, p->stats.as<double>());
 		SRB_CUDA(cudaGetLastError());
 	}
 	const long long total = (long long)s->rows_total * ld;
 	const int blocks = (int)((total + 255) / 256);
-	mfcc_norm_kernel<<<blocks, 256, 0, st>>>(s->d_ceps, p->CL, s->d_stats, s->d_frame_off, s->d_feat_off, n_utt, p->nc, nd, cmvn,
+	mfcc_norm_kernel<<<blocks, 256, 0, st>>>(p->ceps.as<float>(), p->CL, p->stats.as<double>(), s->d_frame_off, s->d_feat_off, n_utt, p->nc, nd, cmvn,
 	                                        d_feat, ld, total);
 	SRB_CUDA(cudaGetLastError());
 	if (feat_off) memcpy(feat_off, s->feat_off.data(), sizeof(int) * (n_utt + 1));

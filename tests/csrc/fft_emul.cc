@@ -30,23 +30,34 @@ extern "C" int emul_power_spectrum(const float *y, int N, int batch, int n_worke
 	return num_passes(M);
 }
 
-// replay of the fast path (M = 1024, <= 256 non-zero packed inputs): y = real frames [batch][2048] with zeros
-// beyond 512; P = power spectrum [batch][FAST_PSTRIDE], natural order
-extern "C" void emul_fast_power_spectrum(const float *y, int batch, float *P) {
+// replay of the warp-per-frame path (mfcc_frames_warp_kernel): 32 lanes = 2 halves x 16, two rounds of sub-transforms, swizzled
+// transpose tiles, in-place step B, paired power unpack; P = power spectrum [batch][1025] natural order (de-skewed here)
+extern "C" void emul_warp_power_spectrum(const float *y, int batch, float *P) {
 	const int N = 2048, M = 1024;
-	std::vector<cpx> tw1(3 * 256), twA(256), tw2(M + 1);
-	for (int r = 1; r < 4; ++r)
-		for (int n = 0; n < 256; ++n) tw1[(r - 1) * 256 + n] = cpx{(float)std::cos(-2.0 * M_PI * n * r / 1024), (float)std::sin(-2.0 * M_PI * n * r / 1024)};
+	std::vector<cpx> tw1(4 * 256), twA(256), tw2(513);
+	for (int r = 0; r < 4; ++r)
+		for (int n = 0; n < 256; ++n) tw1[r * 256 + n] = cpx{(float)std::cos(-2.0 * M_PI * n * r / 1024), (float)std::sin(-2.0 * M_PI * n * r / 1024)};
 	for (int q2 = 0; q2 < 16; ++q2)
 		for (int u = 0; u < 16; ++u) twA[q2 * 16 + u] = cpx{(float)std::cos(-2.0 * M_PI * u * q2 / 256), (float)std::sin(-2.0 * M_PI * u * q2 / 256)};
-	for (int k = 0; k <= M; ++k) tw2[k] = cpx{(float)std::cos(-2.0 * M_PI * k / N), (float)std::sin(-2.0 * M_PI * k / N)};
+	for (int k = 0; k <= 512; ++k) tw2[k] = cpx{(float)std::cos(-2.0 * M_PI * k / N), (float)std::sin(-2.0 * M_PI * k / N)};
+	(void)M;
 	for (int b = 0; b < batch; ++b) {
-		std::vector<cpx> z(256), T(4 * 16 * FAST_TSTRIDE), Zs(4 * FAST_ZSTRIDE);
-		for (int n = 0; n < 256; ++n) z[n] = cpx{y[(size_t)b * N + 2 * n], y[(size_t)b * N + 2 * n + 1]};
-		for (int r = 0; r < 4; ++r)
-			for (int u = 0; u < 16; ++u) fast_step_a(z.data(), tw1.data(), twA.data(), T.data() + r * 16 * FAST_TSTRIDE, r, u);
-		for (int r = 0; r < 4; ++r)
-			for (int u = 0; u < 16; ++u) fast_step_b(T.data() + r * 16 * FAST_TSTRIDE, Zs.data() + r * FAST_ZSTRIDE, u);
-		for (int w = 0; w < 64; ++w) fast_power_unpack(Zs.data(), P + (size_t)b * FAST_PSTRIDE, tw2.data(), w);
+		std::vector<cpx> ybuf(256), TZ(4 * WF_TILE);
+		std::vector<float> Ps(WF_PLEN, -1.f);
+		for (int n = 0; n < 256; ++n) ybuf[n] = cpx{y[(size_t)b * N + 2 * n], y[(size_t)b * N + 2 * n + 1]};
+		for (int round = 0; round < 2; ++round)
+			for (int lane = 0; lane < 32; ++lane) {
+				const int h = lane >> 4, u = lane & 15, r = h + 2 * round;
+				cpx z[16];
+				for (int n2 = 0; n2 < 16; ++n2) z[n2] = ybuf[u + 16 * n2];
+				wf_step_a(z, tw1.data() + r * 256, twA.data(), TZ.data() + r * WF_TILE, u);
+			}
+		for (int round = 0; round < 2; ++round) {
+			cpx regs[32][16];
+			for (int lane = 0; lane < 32; ++lane) wf_step_b_load(TZ.data() + ((lane >> 4) + 2 * round) * WF_TILE, lane & 15, regs[lane]);
+			for (int lane = 0; lane < 32; ++lane) wf_step_b_store(regs[lane], TZ.data(), (lane >> 4) + 2 * round, lane & 15);
+		}
+		for (int lane = 0; lane < 32; ++lane) wf_power_lane(TZ.data(), Ps.data(), tw2.data(), lane);
+		for (int k = 0; k <= 1024; ++k) P[(size_t)b * 1025 + k] = Ps[wf_p_index(k)];
 	}
 }

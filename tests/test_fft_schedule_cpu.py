@@ -36,19 +36,21 @@ def test_power_spectrum_matches_numpy(emul, N, workers):
     assert np.max(np.abs(P - ref) / ref.max(axis=1, keepdims=True)) < 2e-6
 
 
-def test_fast_path_power_spectrum_matches_numpy(emul):
-    """the register-resident fast path (4 x 256-point transforms of the zero-padded 2048-point frame, fft_core.h
-    fast_step_a / fast_step_b / fast_power_unpack) replayed thread by thread"""
-    rng = np.random.default_rng(5)
+def test_warp_per_frame_power_spectrum_matches_numpy(emul):
+    """the warp-per-frame schedule (fft_core.h wf_step_a / wf_step_b_* / wf_power_lane: swizzled transpose tiles, in-place second
+    step, bins k and 1024 - k from one pair) replayed lane by lane; every bin 0..1024 must be written exactly once"""
+    rng = np.random.default_rng(6)
     batch = 5
     y = np.zeros((batch, 2048), np.float32)
     y[:, :512] = (rng.standard_normal((batch, 512)) * 3000).astype(np.float32)
-    y[1, 300:512] = 0           # shorter frame (8 kHz geometry)
+    y[1, 256:512] = 0           # shorter frame (8 kHz geometry)
     y[2, :] = 0                 # digital silence
-    P = np.zeros((batch, 1028), np.float32)
+    y[3, :512] = 12000.0        # DC: one dominant bin
+    P = np.full((batch, 1025), -1.0, np.float32)
     fp = C.POINTER(C.c_float)
-    emul.emul_fast_power_spectrum(y.ctypes.data_as(fp), batch, P.ctypes.data_as(fp))
+    emul.emul_warp_power_spectrum(y.ctypes.data_as(fp), batch, P.ctypes.data_as(fp))
     ref = np.abs(np.fft.fft(y.astype(np.float64), axis=1)[:, :1025]) ** 2
     scale = np.maximum(ref.max(axis=1, keepdims=True), 1e-30)
-    assert np.max(np.abs(P[:, :1025] - ref) / scale) < 2e-6
-    assert np.all(P[2, :1025] == 0)
+    assert np.all(P >= 0)
+    assert np.max(np.abs(P - ref) / scale) < 2e-6
+    assert np.all(P[2] == 0)
