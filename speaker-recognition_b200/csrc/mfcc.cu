@@ -215,9 +215,9 @@ __global__ void __launch_bounds__(MF_THREADS) mfcc_frames_kernel(const MfccArgs 
 // default geometry at 16 kHz and 8 kHz.  ONE WARP OWNS ONE FRAME (and walks a chunk of consecutive frames of one utterance):
 //   * persistent CTAs of 12 warps, one per SM; a warp's buffers are private, so the only synchronisation is __syncwarp -- round 1
 //     ran 4 frames per CTA of 256 threads with six CTA barriers per frame group and 160 064 CTAs per step
-//   * the audio is streamed: consecutive frames overlap (shift <= frame length), so a frame needs only `shift` NEW samples; the
-//     warp keeps a 1024-sample ring of floats in shared memory and fetches the next 256 samples as ONE 128-bit load per lane
-//     (int16; two for float input), issued a whole frame ahead of its use (round 1: scalar 2-byte loads, I2F stalled on them)
+//   * a frame's samples come in as 16-byte asynchronous copies (LDGSTS: global -> shared memory without registers), issued a whole
+//     frame ahead into the second of two staging buffers (round 1: scalar 2-byte loads with the I2F stalled on them); the 50 %
+//     overlap of consecutive frames is served by L2; every table of the kernel lives in shared memory (L1 is 3 KB here)
 //   * window and pre-emphasis as the 2-tap form y[i] = w[i] x[i] - w2[i] x[i-1] with the lane's 32 coefficients in registers
 //   * the zero-padded 1024-point packed transform = four 256-point transforms of pre-twiddled inputs, each two radix-16 steps in
 //     registers (16 lanes x 16 points); the half-warps take r = h and r = h + 2, the packed frame is loaded once for both;
@@ -229,30 +229,54 @@ __global__ void __launch_bounds__(MF_THREADS) mfcc_frames_kernel(const MfccArgs 
 // ------------------------------------------------------------------------------------------------
 constexpr int MFW_WARPS = 12;
 constexpr int MFW_THREADS = MFW_WARPS * 32;
-constexpr int MFW_RING = 1024;                    // samples (floats) of the per-warp ring
 constexpr int MFW_YLEN = 512;                     // longest frame of the fast path
 constexpr int MFW_TW2 = 520;                      // unpack twiddles k = 0..512 (padded)
-constexpr size_t MFW_TABLE_BYTES = (size_t)(4 * 256 + 256 + MFW_TW2) * sizeof(cpx);
-constexpr size_t MFW_WARP_BYTES = (size_t)(MFW_RING + srbfft::WF_PLEN) * sizeof(float) + (size_t)4 * srbfft::WF_TILE * sizeof(cpx);
-constexpr size_t MFW_SMEM = MFW_TABLE_BYTES + MFW_WARPS * MFW_WARP_BYTES;
+constexpr int MFW_STAGE_SAMPLES = 544;            // raw samples of one frame incl. the one before it, rounded out to 16-byte blocks (<= 67 x 8)
+constexpr size_t MFW_STAGE_BYTES = 2 * MFW_STAGE_SAMPLES * sizeof(int16_t);      // two int16 buffers (double-buffered), or one float buffer
+constexpr size_t MFW_CTAB_BYTES = (size_t)(4 * 256 + 256 + MFW_TW2) * sizeof(cpx);
+constexpr size_t MFW_WARP_BYTES = MFW_STAGE_BYTES + (size_t)srbfft::WF_PLEN * sizeof(float) + (size_t)4 * srbfft::WF_TILE * sizeof(cpx);
+// mel / DCT tables in shared memory: first bins int[n_segp] | weights float4[4][n_segp] | segptr int[nbp] | logfloor float[nbp] | dct double[nb][16]
+static inline size_t mfw_mel_bytes(int n_seg, int nb) {
+	const size_t n_segp = (size_t)(n_seg + 3) & ~(size_t)3, nbp = (size_t)(nb + 1 + 3) & ~(size_t)3;
+	return n_segp * 4 + 4 * n_segp * 16 + nbp * 4 + nbp * 4 + (size_t)nb * 16 * 8;
+}
+static inline size_t mfw_smem_bytes(int n_seg, int nb) { return MFW_CTAB_BYTES + mfw_mel_bytes(n_seg, nb) + MFW_WARPS * MFW_WARP_BYTES; }
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <bool F32>
 __global__ void __launch_bounds__(MFW_THREADS, 1) mfcc_frames_warp_kernel(const MfccArgs A, int n_chunks, long long n_total) {
 	extern __shared__ __align__(16) unsigned char mf_smem[];
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	const int L = A.L, nb = A.nb, nc = A.nc, shift = A.shift;
+	const int L = A.L, nb = A.nb, nc = A.nc, shift = A.shift, n_seg = A.n_seg;
+	const int n_segp = (n_seg + 3) & ~3, nbp = (nb + 1 + 3) & ~3;
 	cpx *s_tw1 = reinterpret_cast<cpx *>(mf_smem);          // [4][256] W_1024^{n r} (row 0 = 1)
 	cpx *s_twA = s_tw1 + 4 * 256;                           // [16][16]  W_256^{u q2}
 	cpx *s_tw2 = s_twA + 256;                               // [0..512]  exp(-2 pi i k / 2048)
-	unsigned char *wb = mf_smem + MFW_TABLE_BYTES + (size_t)warp * MFW_WARP_BYTES;
-	float *ring = reinterpret_cast<float *>(wb);            // [1024] raw samples as floats, position = (index - base) & 1023
-	float *Pb = ring + MFW_RING;                            // [WF_PLEN] windowed frame (first 512 floats), then the skewed power spectrum
-	cpx *TZ = reinterpret_cast<cpx *>(Pb + srbfft::WF_PLEN);    // [4][256] transpose tiles / sub-transform outputs, later the mel scratch
+	int *s_segfirst = reinterpret_cast<int *>(s_tw2 + MFW_TW2);             // [n_segp] first bin of every 16-bin segment (multiple of 4)
+	float4 *s_w16 = reinterpret_cast<float4 *>(s_segfirst + n_segp);        // [4][n_segp] segment weights, quarter-major
+	int *s_segptr = reinterpret_cast<int *>(s_w16 + 4 * n_segp);            // [nb + 1]
+	float *s_logfloor = reinterpret_cast<float *>(s_segptr + nbp);          // [nb]
+	double *s_dct = reinterpret_cast<double *>(s_logfloor + nbp);           // [nb][16] transposed DCT rows 1..n_ceps
+	unsigned char *wb = reinterpret_cast<unsigned char *>(s_dct + (size_t)nb * 16) + (size_t)warp * MFW_WARP_BYTES;
+	unsigned char *stage = wb;                              // raw samples of the current / next frame, exactly as they lie in HBM
+	float *Pb = reinterpret_cast<float *>(wb + MFW_STAGE_BYTES);            // [WF_PLEN] windowed frame (first 512 floats), then the skewed power spectrum
+	cpx *TZ = reinterpret_cast<cpx *>(Pb + srbfft::WF_PLEN);                // [4][256] transpose tiles / sub-transform outputs, later the mel scratch
 
 	for (int i = tid; i < 4 * 256; i += MFW_THREADS) s_tw1[i] = i < 256 ? cpx{1.f, 0.f} : A.tw1[i - 256];
 	for (int i = tid; i < 256; i += MFW_THREADS) s_twA[i] = A.twA[i];
 	for (int i = tid; i <= 512; i += MFW_THREADS) s_tw2[i] = A.tw2[i];
-	for (int i = lane; i < srbfft::WF_PLEN; i += 32) Pb[i] = 0.f;      // the bins beyond 1024 a last mel segment may touch stay 0 (weights 0)
+	for (int i = tid; i < n_seg; i += MFW_THREADS) s_segfirst[i] = A.mel_seg[i].x;
+	for (int i = tid; i < 4 * n_seg; i += MFW_THREADS) s_w16[(i / n_seg) * n_segp + (i % n_seg)] = reinterpret_cast<const float4 *>(A.mel_w16)[i];
+	for (int i = tid; i <= nb; i += MFW_THREADS) s_segptr[i] = A.mel_segptr[i];
+	for (int i = tid; i < nb; i += MFW_THREADS) s_logfloor[i] = A.logfloor[i];
+	for (int i = tid; i < nb * 16; i += MFW_THREADS) s_dct[i] = A.dct_t[i];
+	for (int i = lane; i < srbfft::WF_PLEN; i += 32) Pb[i] = 0.f;          // the bins beyond 1024 a last mel segment may touch stay 0 (weights 0)
+	for (int i = lane; i < (int)(MFW_STAGE_BYTES / 4); i += 32) reinterpret_cast<uint32_t *>(stage)[i] = 0u;
 	// this lane's window coefficients for the frame positions i = lane + 32 j (zero beyond the frame length)
 	float wr[16], w2r[16];
 #pragma unroll
@@ -265,82 +289,64 @@ __global__ void __launch_bounds__(MFW_THREADS, 1) mfcc_frames_warp_kernel(const 
 
 	const int h = lane >> 4, u = lane & 15;
 	constexpr int G = F32 ? 4 : 8;                            // elements per 16 bytes
-	const long long ptr_elems = (long long)(reinterpret_cast<uintptr_t>(A.pcm) / (F32 ? 4 : 2));
+	constexpr int ES = F32 ? 4 : 2;                           // bytes per sample
+	const long long ptr_elems = (long long)(reinterpret_cast<uintptr_t>(A.pcm) / ES);
+	const unsigned char *pcm_b = reinterpret_cast<const unsigned char *>(A.pcm);
 
-	// 8 consecutive samples starting at absolute index i0 (a multiple of G past `base`), zeros outside [0, n_total)
-	auto load8 = [&](long long i0, float (&v)[8]) {
-		if (i0 >= 0 && i0 + 8 <= n_total) {
-			if (F32) {
-				const float4 a = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(A.pcm) + i0));
-				const float4 b = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(A.pcm) + i0) + 1);
-				v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
-			} else {
-				const int4 q = __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const int16_t *>(A.pcm) + i0));
-				const int w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-				for (int t = 0; t < 4; ++t) {
-					v[2 * t] = (float)(short)(w4[t] & 0xffff);
-					v[2 * t + 1] = (float)(short)(w4[t] >> 16);
+	// Stage the samples [b0, b0 + 8 nblk) of the frame that starts at sample a (b0 = the last 16-byte-aligned index <= a - 1) into
+	// `dst`, asynchronously (LDGSTS: global -> shared without registers); pieces that stick out of [0, n_total) are filled by hand.
+	auto stage_frame = [&](long long a, unsigned char *dst) -> int {
+		long long m = (ptr_elems + a - 1) % G;
+		if (m < 0) m += G;
+		const long long b0 = a - 1 - m;
+		const int npiece = (int)((a + L - b0 + G - 1) / G);           // 16-byte pieces
+		for (int t = lane; t < npiece; t += 32) {
+			const long long e0 = b0 + (long long)t * G;
+			unsigned char *d = dst + (size_t)t * 16;
+			if (e0 >= 0 && e0 + G <= n_total) cp_async16(d, pcm_b + e0 * ES);
+			else
+				for (int q = 0; q < G; ++q) {
+					const long long g = e0 + q;
+					if (F32) reinterpret_cast<float *>(d)[q] = (g >= 0 && g < n_total) ? reinterpret_cast<const float *>(A.pcm)[g] : 0.f;
+					else reinterpret_cast<int16_t *>(d)[q] = (g >= 0 && g < n_total) ? reinterpret_cast<const int16_t *>(A.pcm)[g] : (int16_t)0;
 				}
-			}
-		} else {
-#pragma unroll
-			for (int t = 0; t < 8; ++t) {
-				const long long g = i0 + t;
-				float x = 0.f;
-				if (g >= 0 && g < n_total) x = F32 ? __ldg(reinterpret_cast<const float *>(A.pcm) + g) : (float)__ldg(reinterpret_cast<const int16_t *>(A.pcm) + g);
-				v[t] = x;
-			}
 		}
-	};
-	auto commit8 = [&](long long i0, long long base, const float (&v)[8]) {
-		float4 *dst = reinterpret_cast<float4 *>(ring + ((i0 - base) & (MFW_RING - 1)));
-		dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-		dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+		cp_async_commit();
+		return (int)(a - b0);                                        // position of sample a in the buffer (1..G)
 	};
 
 	for (int c = blockIdx.x * MFW_WARPS + warp; c < n_chunks; c += gridDim.x * MFW_WARPS) {
 		const int4 rec = __ldg(A.cta_rec + c);
 		const long long a0 = ((long long)(unsigned)rec.x) | ((long long)rec.y << 32);
 		const int row0 = rec.z, nfr = rec.w;
-		// ring origin: the last index <= a0 - 1 whose address is 16-byte aligned
-		long long m = (ptr_elems + a0 - 1) % G;
-		if (m < 0) m += G;
-		const long long base = a0 - 1 - m;
-		long long loaded_end = base;                           // samples [base, loaded_end) are in the ring
-		float pend[8];                                         // the NEXT 256-sample block's share of this lane, in flight
-		{
-			float v0[8], v1[8], v2[8];
-			load8(base + 8 * lane, v0);
-			load8(base + 256 + 8 * lane, v1);
-			load8(base + 512 + 8 * lane, v2);
-			load8(base + 768 + 8 * lane, pend);
-			__syncwarp();                                      // the previous chunk's last frame has left the ring
-			commit8(base + 8 * lane, base, v0);
-			commit8(base + 256 + 8 * lane, base, v1);
-			commit8(base + 512 + 8 * lane, base, v2);
-			loaded_end = base + 768;
-		}
 		double cs = 0.0, css = 0.0;                            // CMVN partial sums of coefficient `lane`
+		int cur = 0;
+		__syncwarp();                                          // the previous chunk's last frame has left the staging buffers
+		int off = stage_frame(a0, stage);
 		for (int f = 0; f < nfr; ++f) {
-			const long long a = a0 + (long long)f * shift;
-			while (loaded_end < a + L) {                       // at most once per frame in the steady state (shift <= 256)
-				commit8(loaded_end + 8 * lane, base, pend);
-				loaded_end += 256;
-				load8(loaded_end + 8 * lane, pend);
-			}
+			cp_async_wait_all();
 			__syncwarp();
-			// ---- window, then pre-emphasis (MFCC.py:61-64) as the 2-tap form
-			{
-				const int o = (int)((a - base) & (MFW_RING - 1));
+			const unsigned char *sb = stage + (F32 ? 0 : (size_t)cur * MFW_STAGE_SAMPLES * 2);
+			int off_next = 0;
+			if (!F32 && f + 1 < nfr) {                         // the next frame's samples start their way now, into the other buffer
+				off_next = stage_frame(a0 + (long long)(f + 1) * shift, stage + (size_t)(cur ^ 1) * MFW_STAGE_SAMPLES * 2);
+			}
+			// ---- window, then pre-emphasis (MFCC.py:61-64) as the 2-tap form y[i] = w[i] x[i] - w2[i] x[i-1]
 #pragma unroll
-				for (int j = 0; j < 16; ++j) {
-					const int i = lane + 32 * j;
-					const float x1 = ring[(o + i) & (MFW_RING - 1)], x0 = ring[(o + i - 1) & (MFW_RING - 1)];
-					Pb[i] = fmaf(-w2r[j], x0, wr[j] * x1);
+			for (int j = 0; j < 16; ++j) {
+				const int i = lane + 32 * j;
+				float x1, x0;
+				if (F32) {
+					x1 = reinterpret_cast<const float *>(sb)[off + i];
+					x0 = reinterpret_cast<const float *>(sb)[off + i - 1];
+				} else {
+					x1 = (float)reinterpret_cast<const int16_t *>(sb)[off + i];
+					x0 = (float)reinterpret_cast<const int16_t *>(sb)[off + i - 1];
 				}
+				Pb[i] = fmaf(-w2r[j], x0, wr[j] * x1);
 			}
 			__syncwarp();
+			if (F32 && f + 1 < nfr) off_next = stage_frame(a0 + (long long)(f + 1) * shift, stage);     // single float buffer: refill once it is consumed
 			// ---- first radix-16 step of the two sub-transforms of this half-warp (r = h, h + 2)
 			{
 				cpx z[16];
@@ -368,41 +374,45 @@ __global__ void __launch_bounds__(MFW_THREADS, 1) mfcc_frames_warp_kernel(const 
 			// fp32 energy is exactly 0 takes log(1e-100 * sum of its weights) instead.
 			float *segsum = reinterpret_cast<float *>(TZ);         // [n_seg]   (the sub-transform outputs are consumed)
 			float *logE = segsum + 512;                            // [nb]
-			{
-				const int n_seg = A.n_seg;
-				const float4 *w4 = reinterpret_cast<const float4 *>(A.mel_w16);
-				for (int sg = lane; sg < n_seg; sg += 32) {
-					const int g0 = __ldg(A.mel_seg + sg).x >> 2;       // first bin / 4
-					float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+			for (int sg = lane; sg < n_seg; sg += 32) {
+				const int g0 = s_segfirst[sg] >> 2;                // first bin / 4
+				float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
 #pragma unroll
-					for (int q = 0; q < 4; ++q) {
-						const int g = g0 + q;
-						const float4 pv = *reinterpret_cast<const float4 *>(Pb + 4 * (g + (g >> 2)));
-						const float4 wv = __ldg(w4 + (size_t)q * n_seg + sg);
-						e0 = fmaf(wv.x, pv.x, e0);
-						e1 = fmaf(wv.y, pv.y, e1);
-						e2 = fmaf(wv.z, pv.z, e2);
-						e3 = fmaf(wv.w, pv.w, e3);
-					}
-					segsum[sg] = (e0 + e1) + (e2 + e3);
+				for (int q = 0; q < 4; ++q) {
+					const int g = g0 + q;
+					const float4 pv = *reinterpret_cast<const float4 *>(Pb + 4 * (g + (g >> 2)));
+					const float4 wv = s_w16[q * n_segp + sg];
+					e0 = fmaf(wv.x, pv.x, e0);
+					e1 = fmaf(wv.y, pv.y, e1);
+					e2 = fmaf(wv.z, pv.z, e2);
+					e3 = fmaf(wv.w, pv.w, e3);
 				}
-				__syncwarp();
-				for (int b = lane; b < nb; b += 32) {
-					const int s0 = __ldg(A.mel_segptr + b), s1 = __ldg(A.mel_segptr + b + 1);
-					float e = 0.f;
-					for (int sg = s0; sg < s1; ++sg) e += segsum[sg];
-					logE[b] = e > 0.f ? logf(e) : __ldg(A.logfloor + b);
-				}
+				segsum[sg] = (e0 + e1) + (e2 + e3);
 			}
 			__syncwarp();
-			// ---- DCT rows 1..n_ceps, float64 accumulate: lane = (band parity, coefficient); the table is transposed [band][16]
+			for (int b = lane; b < nb; b += 32) {
+				const int s0 = s_segptr[b], s1 = s_segptr[b + 1];
+				float e = 0.f;
+				for (int sg = s0; sg < s1; ++sg) e += segsum[sg];
+				logE[b] = e > 0.f ? logf(e) : s_logfloor[b];
+			}
+			__syncwarp();
+			// ---- DCT rows 1..n_ceps, float64 accumulate: lane = (band parity, coefficient), four independent partial sums per lane
+			// (a fixed order, so the result is deterministic); the table is transposed [band][16]
 			{
 				const int i = lane & 15;
-				double acc = 0.0;
-				for (int b2 = h; b2 < nb; b2 += 2) acc = fma(__ldg(A.dct_t + b2 * 16 + i), (double)logE[b2], acc);
-				acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+				double acc[4] = {0.0, 0.0, 0.0, 0.0};
+				for (int b2 = h; b2 < nb; b2 += 8) {
+#pragma unroll
+					for (int t = 0; t < 4; ++t) {
+						const int bb = b2 + 2 * t;
+						if (bb < nb) acc[t] = fma(s_dct[bb * 16 + i], (double)logE[bb], acc[t]);
+					}
+				}
+				double tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+				tot += __shfl_xor_sync(0xffffffffu, tot, 16);
 				if (lane < A.CL) {
-					const float cf = lane < nc ? (float)acc : 0.f;
+					const float cf = lane < nc ? (float)tot : 0.f;
 					A.ceps[(size_t)(row0 + f) * A.CL + lane] = cf;
 					if (lane < nc) {
 						cs += (double)cf;
@@ -410,6 +420,8 @@ __global__ void __launch_bounds__(MFW_THREADS, 1) mfcc_frames_warp_kernel(const 
 					}
 				}
 			}
+			off = off_next;
+			cur ^= 1;
 		}
 		if (lane < nc) {
 			A.partials[(size_t)c * 2 * nc + lane] = cs;
@@ -603,7 +615,7 @@ static int build_tables(MfccPlan *p) {
 			w16.swap(t);
 		}
 		p->n_seg = (int)seg.size();
-		if (p->n_seg > 512 || p->n_seg == 0) p->fast = false;   // the segment sums share a shared-memory region of 512 floats
+		if (p->n_seg > 512 || p->n_seg == 0 || mfw_smem_bytes(p->n_seg, nb) > 227 * 1024) p->fast = false;   // segment sums: 512 floats; tables: shared memory
 		if (to_device(&p->d_tw1, tw1) || to_device(&p->d_twA, twA) || to_device(&p->d_mel_seg, seg) ||
 		    to_device(&p->d_mel_w16, w16) || to_device(&p->d_mel_segptr, segptr))
 			return 1;
@@ -861,8 +873,8 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 	if (p->fast && !mfcc_force_generic()) {
 		const int grid = std::min(ctx().sm_count, (s->n_cta + MFW_WARPS - 1) / MFW_WARPS);
 		const long long n_total = smp_off[n_utt];
-		if (is_f32) mfcc_frames_warp_kernel<true><<<grid, MFW_THREADS, MFW_SMEM, st>>>(a, s->n_cta, n_total);
-		else mfcc_frames_warp_kernel<false><<<grid, MFW_THREADS, MFW_SMEM, st>>>(a, s->n_cta, n_total);
+		if (is_f32) mfcc_frames_warp_kernel<true><<<grid, MFW_THREADS, mfw_smem_bytes(p->n_seg, p->nb), st>>>(a, s->n_cta, n_total);
+		else mfcc_frames_warp_kernel<false><<<grid, MFW_THREADS, mfw_smem_bytes(p->n_seg, p->nb), st>>>(a, s->n_cta, n_total);
 	} else mfcc_frames_kernel<<<s->n_cta, MF_THREADS, p->smem, st>>>(a);
 	SRB_CUDA(cudaGetLastError());
 	if (cmvn) {
