@@ -83,6 +83,7 @@ int srb200_get_compat_clamp(void);
 int srb200_set_score_path(int path);
 int srb200_get_score_path(void);
 int srb200_last_score_route(void);
+long long srb200_score_launch_count(void);          /* scoring launches issued by this process so far */
 int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int *hard_entries_out, int *max_hard_per_block_out);
 /* the packed operands of route 1 (host only): info_out[8] = {Kp, blocks, columns per speaker, halfs per block, ints per block
  * list, header words, 0, 0}; arrays copied when non-NULL (blocks * info[3] uint16, blocks * info[4] int32, 2 * dim float).
@@ -122,6 +123,9 @@ srb200_gmmset *srb200_gmmset_create(GMM *const *models, int n_models);   /* copi
 void srb200_gmmset_free(srb200_gmmset *set);
 int srb200_gmmset_size(srb200_gmmset *set);
 int srb200_gmmset_dim(srb200_gmmset *set);
+/* only the first n_ranked models take part in the per-utterance argmax (d_best); the others are scored all the same.  Used to carry a
+ * UBM as model S + 1 of a speaker set: predict_one_with_rejection (src/testbench/gmmset.py:69-84) becomes one launch. */
+int srb200_gmmset_set_ranked(srb200_gmmset *set, int n_ranked);
 /* host matrix, one utterance: sums[s] = sum_t log p_s(x_t) */
 int srb200_gmmset_score_f64(srb200_gmmset *set, const double *X, int n, int dim, double *sums);
 int srb200_gmmset_score_f32(srb200_gmmset *set, const float *X, int n, int dim, double *sums);
@@ -194,6 +198,10 @@ int srb200_remove_silence_i16(int fs, const int16_t *pcm, long long n_samples, d
                               int16_t *out, long long *n_out);
 int srb200_remove_silence_u8(int fs, const uint8_t *pcm, long long n_samples, double frame_duration, double frame_shift, double perc,
                              uint8_t *out, long long *n_out);
+
+/* streaming (BASELINE config 5): d_window_out[b] = [d_window_in[b][hop:], d_fresh[b]] for n_streams windows of `window` int16 samples,
+ * 0 < hop < window, one launch (the reference GUI re-slices a Python list per tick, src/gui/gui.py:179-190).  In and out must differ. */
+int srb200_stream_push_i16(const int16_t *d_window_in, const int16_t *d_fresh, int16_t *d_window_out, int n_streams, int window, int hop, void *stream);
 
 #ifdef __cplusplus
 }

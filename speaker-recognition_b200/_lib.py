@@ -54,6 +54,7 @@ PROTOTYPES = {
     "srb200_set_score_path": (_ci, [_ci]),
     "srb200_get_score_path": (_ci, []),
     "srb200_last_score_route": (_ci, []),
+    "srb200_score_launch_count": (_cll, []),
     "srb200_tc_pack_stats": (_ci, [C.POINTER(_vp), _ci, _ip, _ip, _ip]),
     "srb200_tc_pack_export": (_ci, [C.POINTER(_vp), _ci, _ip, C.POINTER(C.c_uint16), _ip, _fp]),
     "srb200_gmm_set_params": (_ci, [_vp, _ci, _ci, _dp, _dp, _dp]),
@@ -70,6 +71,7 @@ PROTOTYPES = {
     "srb200_gmmset_free": (None, [_vp]),
     "srb200_gmmset_size": (_ci, [_vp]),
     "srb200_gmmset_dim": (_ci, [_vp]),
+    "srb200_gmmset_set_ranked": (_ci, [_vp, _ci]),
     "srb200_gmmset_score_f64": (_ci, [_vp, _dp, _ci, _ci, _dp]),
     "srb200_gmmset_score_f32": (_ci, [_vp, _fp, _ci, _ci, _dp]),
     "srb200_gmmset_score_dev": (_ci, [_vp, _vp, _ci, _ci, _ip, _ci, _vp, _vp, _ci, _vp, _vp]),
@@ -92,6 +94,7 @@ PROTOTYPES = {
     "srb200_lpc_extract_f32": (_ci, [_vp, _fp, _cll, _ci, _dp, _ip]),
     "srb200_lpc_extract_f64": (_ci, [_vp, _dp, _cll, _ci, _dp, _ip]),
     "srb200_lpc_extract_dev": (_ci, [_vp, _vp, _llp, _ci, _ci, _vp, _ci, _ci, _ip, _vp]),
+    "srb200_stream_push_i16": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _vp]),
     "srb200_remove_silence_i16": (_ci, [_ci, _i16p, _cll, _cd, _cd, _cd, _i16p, _llp]),
     "srb200_remove_silence_u8": (_ci, [_ci, C.POINTER(C.c_uint8), _cll, _cd, _cd, _cd, C.POINTER(C.c_uint8), _llp]),
 }

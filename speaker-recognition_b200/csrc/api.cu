@@ -759,6 +759,7 @@ int srb200_set_score_path(int path) {
 }
 int srb200_get_score_path(void) { return ctx().score_path; }
 int srb200_last_score_route(void) { return ctx().last_score_route; }
+long long srb200_score_launch_count(void) { return ctx().score_launches; }
 
 GMM *new_gmm(int nr_mixture, int covariance_type) {
 	API_ENTER();
@@ -1106,6 +1107,12 @@ void srb200_gmmset_free(srb200_gmmset *set) {
 	}
 }
 int srb200_gmmset_size(srb200_gmmset *set) { return set ? set->S : 0; }
+int srb200_gmmset_set_ranked(srb200_gmmset *set, int n_ranked) {
+	API_ENTER();
+	SRB_REQUIRE(set != nullptr && n_ranked >= 1 && n_ranked <= set->S, "gmmset_set_ranked: need 1 <= n_ranked <= %d", set ? set->S : 0);
+	set->packed.S_arg = n_ranked;
+	return 0;
+}
 int srb200_gmmset_dim(srb200_gmmset *set) { return set ? set->D : 0; }
 
 static int gmmset_score_host(srb200_gmmset *set, const RowSrc &src, int n, int dim, double *sums) {
@@ -1317,6 +1324,13 @@ int srb200_remove_silence_u8(int fs, const uint8_t *pcm, long long n, double fra
                              long long *n_out) {
 	API_ENTER();
 	return remove_silence_host(fs, pcm, 1, n, frame_duration, frame_shift, perc, out, n_out);
+}
+
+// ---- streaming: slide B device windows by `hop` samples and append the fresh samples (one launch) ----
+int srb200_stream_push_i16(const int16_t *d_window_in, const int16_t *d_fresh, int16_t *d_window_out, int n_streams, int window, int hop, void *stream) {
+	API_ENTER();
+	if (ctx().init()) return 1;
+	return launch_ring_shift_append(d_window_in, d_fresh, d_window_out, n_streams, window, hop, (cudaStream_t)stream);
 }
 
 }  // extern "C"

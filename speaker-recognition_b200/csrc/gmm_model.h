@@ -26,6 +26,7 @@ static inline size_t tile_floats(int D) { return (size_t)64 * D + 32; }
 
 struct PackedModels {             // device-resident packed parameters of S models sharing D and Kpad
 	int S = 0, K = 0, Kpad = 0, D = 0, tiles_per_model = 0;
+	int S_arg = 0;                // models that take part in the per-utterance argmax (0 = all): a set may carry its UBM as an extra model
 	float *d_tiles = nullptr;     // S * tiles_per_model * tile_floats(D)
 	size_t bytes = 0;
 	// tensor-core path (gmm_score_tc2.cuh), built on the host with the FMA tiles, uploaded on first use

@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 }
 
 // sums[u][s] = sum over the frame tiles of utterance u (deterministic order); best[u] = first argmax_s
-__global__ void score_reduce_kernel(const double *__restrict__ partial, const int *__restrict__ utt_tile_start, int S, int parts,
+// (over the first S_arg models: a speaker set may carry its UBM as an extra, unranked model at the end)
+__global__ void score_reduce_kernel(const double *__restrict__ partial, const int *__restrict__ utt_tile_start, int S, int S_arg, int parts,
                                     double *__restrict__ sums, int *__restrict__ best) {
 	const int u = blockIdx.x;
 	const int t0 = utt_tile_start[u], t1 = utt_tile_start[u + 1];
@@ -310,7 +311,7 @@ __global__ void score_reduce_kernel(const double *__restrict__ partial, const in
 		for (int t = t0; t < t1; ++t)
 			for (int w = 0; w < parts; ++w) acc += partial[((size_t)t * S + s) * parts + w];
 		sums[(size_t)u * S + s] = acc;
-		if (acc > bestv) {   // strict: keeps the first maximum within a thread's ascending s sequence
+		if (s < S_arg && acc > bestv) {   // strict: keeps the first maximum within a thread's ascending s sequence
 			bestv = acc;
 			besti = s;
 		}
@@ -461,12 +462,13 @@ int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *ut
 		path = (et && et[0] == '0') ? 0 : 1;
 	}
 	c.last_score_route = 0;
+	++c.score_launches;
 	if (path == 1 && !frame_log2 && tc2_supported(pm, D)) {
 		c.last_score_route = 1;
 		TileTable *tt = nullptr;
 		if (get_table(utt_off, n_utt, pm.S, 128, st, &tt)) return 1;
 		if (launch_score_tc2(pm, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;
-		score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, 4, d_sums, d_best);
+		score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, pm.S_arg > 0 ? pm.S_arg : pm.S, 4, d_sums, d_best);
 		SRB_CUDA(cudaGetLastError());
 		return 0;
 	}
@@ -506,7 +508,7 @@ int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *ut
 		else gmm_score_kernel<true, 4><<<grid, 128, smem, st>>>(a);
 		SRB_CUDA(cudaGetLastError());
 	}
-	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, warps, d_sums, d_best);
+	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, pm.S_arg > 0 ? pm.S_arg : pm.S, warps, d_sums, d_best);
 	SRB_CUDA(cudaGetLastError());
 	return 0;
 }

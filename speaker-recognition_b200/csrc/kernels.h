@@ -55,4 +55,6 @@ int kmeans_lloyd_device(const float *dX, int n, int ld, int D, int K, const doub
 int launch_remove_silence(const void *d_pcm, int is_u8, long long n, int frame_len, int shift_len, double perc, long long *d_ps,
                           long long *d_block, longlong3 *d_segs, long long *d_counts, void *d_out, cudaStream_t st);
 
+int launch_ring_shift_append(const int16_t *d_src, const int16_t *d_fresh, int16_t *d_dst, int n_streams, int W, int hop, cudaStream_t st);
+
 }  // namespace srb

@@ -9,6 +9,7 @@
 // loads; (2) the walk itself is a data-dependent chain (the next position depends on the decision), run by one thread
 // per utterance, emitting (src, dst, len) segments; (3) segment gather.  uint8 input is re-centred like the reference
 // (:18-19, :48-49, including its (max+1)/2 vs max/2 asymmetry).
+#include <algorithm>
 #include "kernels.h"
 
 namespace srb {
@@ -127,6 +128,23 @@ int launch_remove_silence(const void *d_pcm, int is_u8, long long n, int frame_l
 	silence_walk_kernel<<<1, 32, 0, st>>>(d_ps, n, frame_len, shift_len, perc, d_segs, d_counts);
 	SRB_CUDA(cudaGetLastError());
 	silence_gather_kernel<<<ctx().sm_count * 4, 128, 0, st>>>(d_pcm, is_u8, d_segs, d_counts, d_out);
+	SRB_CUDA(cudaGetLastError());
+	return 0;
+}
+
+// ---- streaming windows: dst[b] = [src[b][hop:], fresh[b]] for B streams of W samples (one launch per tick; the reference GUI
+// re-slices a Python list per tick, gui.py:179-190)
+__global__ void ring_shift_append_kernel(const int16_t *__restrict__ src, const int16_t *__restrict__ fresh, int16_t *__restrict__ dst, int W, int hop) {
+	const int b = blockIdx.y;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W; i += gridDim.x * blockDim.x)
+		dst[(size_t)b * W + i] = i < W - hop ? src[(size_t)b * W + i + hop] : fresh[(size_t)b * hop + (i - (W - hop))];
+}
+
+int launch_ring_shift_append(const int16_t *d_src, const int16_t *d_fresh, int16_t *d_dst, int n_streams, int W, int hop, cudaStream_t st) {
+	SRB_REQUIRE(d_src && d_fresh && d_dst && d_src != d_dst, "stream_push: null or aliased buffers");
+	SRB_REQUIRE(n_streams >= 1 && W >= 2 && hop >= 1 && hop < W, "stream_push: need 0 < hop < window (hop %d, window %d)", hop, W);
+	dim3 grid((unsigned)std::min(64, (W + 255) / 256), (unsigned)n_streams);
+	ring_shift_append_kernel<<<grid, 256, 0, st>>>(d_src, d_fresh, d_dst, W, hop);
 	SRB_CUDA(cudaGetLastError());
 	return 0;
 }

@@ -34,6 +34,7 @@ class GMM(object):
         self.seed = seed                        # None: per-process call counter (the reference seeds from rand())
         self.last_iterations = None
         self.last_log_likelihood = None
+        self._version = 0                       # bumped whenever the parameters change (GMMSet keys its packed device copy on it)
         self.gmm = _lib.check_ptr(_lib.lib().new_gmm(int(nr_mixture), int(covariance_type)), "GMM")
 
     # ---- lifetime ----
@@ -54,6 +55,7 @@ class GMM(object):
         txt = st.pop("model_text")
         self.__dict__.update(st)
         self.last_iterations = self.last_log_likelihood = None
+        self._version = 0
         if txt is None:
             self.gmm = _lib.check_ptr(_lib.lib().new_gmm(int(self.nr_mixture), int(self.covariance_type)), "GMM")
         else:
@@ -76,6 +78,7 @@ class GMM(object):
         g.init_with_kmeans, g.concurrency, g.verbosity, g.seed = 0, cpu_count(), 0, None
         g.nr_mixture = 10
         g.last_iterations = g.last_log_likelihood = None
+        g._version = 0
 
     def dump(self, model_file, precision=6):
         """precision=6 is the reference's ostream default (lossy); 17 is lossless."""
@@ -122,6 +125,7 @@ class GMM(object):
         assert w.shape == (K,) and s.shape == (K, D)
         _lib.check(_lib.lib().srb200_gmm_set_params(self.gmm, K, D, _lib.dptr(w), _lib.dptr(m), _lib.dptr(s)), "GMM.set_params")
         self.nr_mixture = K
+        self._version += 1
         return self
 
     def get_params(self):
@@ -160,6 +164,7 @@ class GMM(object):
         _lib.check(rc, "GMM.fit")
         self.nr_mixture = L.get_nr_mixtures(self.gmm)
         self.last_iterations, self.last_log_likelihood = it.value, ll.value
+        self._version += 1
         return self
 
     _seed_counter = [0]

@@ -43,14 +43,29 @@ class GMMSet(object):
             pass
 
     def _ensure_set(self):
-        ids = tuple(id(g) for g in self.gmms)
+        """the device-packed set: every enrolled model and, when a UBM is attached, the UBM as one extra model at the end (so that
+        predict_one_with_rejection is ONE scoring launch).  The C side copies the parameters at creation, so the cache key carries
+        every model's identity AND its parameter version (a refit / set_params on an enrolled GMM rebuilds the set)."""
+        models = list(self.gmms) + ([self.ubm] if self.ubm is not None else [])
+        ids = tuple((id(g), getattr(g, "_version", 0)) for g in models)
         if self._set is not None and ids == self._set_ids:
             return self._set
         self._drop_set()
-        arr = (C.c_void_p * len(self.gmms))(*[g.gmm for g in self.gmms])
-        self._set = _lib.check_ptr(_lib.lib().srb200_gmmset_create(arr, len(self.gmms)), "GMMSet")
+        arr = (C.c_void_p * len(models))(*[g.gmm for g in models])
+        self._set = _lib.check_ptr(_lib.lib().srb200_gmmset_create(arr, len(models)), "GMMSet")
+        if self.ubm is not None and self.gmms:
+            _lib.check(_lib.lib().srb200_gmmset_set_ranked(self._set, len(self.gmms)), "GMMSet")      # the UBM is scored, never ranked
         self._set_ids = ids
         return self._set
+
+    def _score_all_models(self, x):
+        """[sum_t log p_s(x_t) for the enrolled speakers ..., (the UBM's, if one is attached)] in one launch"""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = len(self.gmms) + (1 if self.ubm is not None else 0)
+        sums = np.empty(n, dtype=np.float64)
+        _lib.check(_lib.lib().srb200_gmmset_score_f64(self._ensure_set(), _lib.dptr(x), x.shape[0], x.shape[1], _lib.dptr(sums)),
+                   "GMMSet.predict_one_scores")
+        return sums
 
     def __getstate__(self):
         st = dict(self.__dict__)
@@ -92,11 +107,7 @@ class GMMSet(object):
         """sum_t log p_s(x_t) for every enrolled speaker s, one launch (gmmset.py:59-60)"""
         if not self.gmms:
             return []
-        x = np.ascontiguousarray(x, dtype=np.float64)
-        sums = np.empty(len(self.gmms), dtype=np.float64)
-        _lib.check(_lib.lib().srb200_gmmset_score_f64(self._ensure_set(), _lib.dptr(x), x.shape[0], x.shape[1], _lib.dptr(sums)),
-                   "GMMSet.predict_one_scores")
-        return list(sums)
+        return list(self._score_all_models(x)[:len(self.gmms)])
 
     def predict_one(self, x):
         scores = self.predict_one_scores(x)
@@ -106,12 +117,14 @@ class GMMSet(object):
         return list(map(self.predict_one, X))
 
     def predict_one_with_rejection(self, x):
+        """gmmset.py:69-81: reject when the best speaker's mean log-likelihood is less than reject_threshold above the UBM's.
+        The UBM rides in the same launch as model S + 1 (the reference makes a second pass over x for it)."""
         assert self.ubm is not None, "UBM must be given prior to conduct reject prediction."
-        scores = self.predict_one_scores(x)
+        allsc = self._score_all_models(x)
         x_len = len(x)  # normalize score
-        scores = [v / x_len for v in scores]
+        scores = [v / x_len for v in allsc[:len(self.gmms)]]
         max_tup = max(enumerate(scores), key=operator.itemgetter(1))
-        ubm_score = self.gmm_score(self.ubm, x) / x_len
+        ubm_score = allsc[len(self.gmms)] / x_len
         if max_tup[1] - ubm_score < self.reject_threshold:
             return None
         return self.y[max_tup[0]]

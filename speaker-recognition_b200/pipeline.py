@@ -27,16 +27,25 @@ class BatchScorer(object):
         _lib.require_gpu()
         self.L = _lib.lib()
         self.gmmset = gmmset
-        self.set_h = gmmset._ensure_set()
-        self.S = self.L.srb200_gmmset_size(self.set_h)
+        self.S = self.L.srb200_gmmset_size(self._set())
         self.ex = _MFCC.get_mfcc_extractor(fs, **mfcc_kwargs)
         self.nd = nd
         self.dim = self.L.srb200_mfcc_out_dim(self.ex._h, nd)
-        if self.dim != self.L.srb200_gmmset_dim(self.set_h):
-            raise ValueError("feature dim %d != model dim %d" % (self.dim, self.L.srb200_gmmset_dim(self.set_h)))
+        if self.dim != self.L.srb200_gmmset_dim(self._set()):
+            raise ValueError("feature dim %d != model dim %d" % (self.dim, self.L.srb200_gmmset_dim(self._set())))
         self.ld = (self.dim + 3) & ~3
         self.device = torch.device("cuda", self.L.srb200_get_device()) if device is None else device
         self._shape = None
+
+    def _set(self):
+        """the GMMSet's packed device set, re-validated on every use: enrolling / loading / refitting a speaker after this scorer
+        was built frees and rebuilds that set, and a cached raw pointer would dangle"""
+        h = self.gmmset._ensure_set()
+        S = self.L.srb200_gmmset_size(h)
+        if getattr(self, "S", S) != S:
+            self.S = S
+            self._shape = None              # the sums buffer is sized by S
+        return h
 
     def _prepare(self, lengths):
         torch = self.torch
@@ -94,7 +103,7 @@ class BatchScorer(object):
 
     def score(self):
         st = self.torch.cuda.current_stream().cuda_stream
-        _lib.check(self.L.srb200_gmmset_score_dev(self.set_h, self.d_feat.data_ptr(), self.ld, self.dim, self.feat_off, self.B,
+        _lib.check(self.L.srb200_gmmset_score_dev(self._set(), self.d_feat.data_ptr(), self.ld, self.dim, self.feat_off, self.B,
                                                   self.d_sums.data_ptr(), None, 0, self.d_best.data_ptr(), st), "gmmset_score_dev")
 
     def step_device(self):
@@ -106,6 +115,7 @@ class BatchScorer(object):
         """end to end: pinned host PCM in, speaker indices (host int32 tensor, pinned) out.  The batch is cut into
         sub-batches of utterances; the H2D copy of sub-batch c+1 (copy stream) overlaps the kernels of sub-batch c."""
         torch = self.torch
+        set_h = self._set()
         self._prepare(lengths)
         cur = torch.cuda.current_stream()
         self.copy_stream.wait_stream(cur)              # previous users of d_pcm are done
@@ -120,7 +130,7 @@ class BatchScorer(object):
             _lib.check(self.L.srb200_mfcc_extract_dev(self.ex._h, self.d_pcm.data_ptr() + 2 * c["s0"], c["smp"], nu, self.nd,
                                                       self.d_feat.data_ptr() + 4 * self.ld * c["row0"], self.ld, c["feat_off"], st),
                        "mfcc_extract_dev")
-            _lib.check(self.L.srb200_gmmset_score_dev(self.set_h, self.d_feat.data_ptr() + 4 * self.ld * c["row0"], self.ld, self.dim,
+            _lib.check(self.L.srb200_gmmset_score_dev(set_h, self.d_feat.data_ptr() + 4 * self.ld * c["row0"], self.ld, self.dim,
                                                       c["feat_off"], nu, self.d_sums.data_ptr() + 8 * self.S * c["u0"], None, 0,
                                                       self.d_best.data_ptr() + 4 * c["u0"], st), "gmmset_score_dev")
         self.h_best.copy_(self.d_best, non_blocking=True)

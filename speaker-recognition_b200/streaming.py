@@ -3,8 +3,8 @@
 Semantics follow the reference GUI (src/gui/gui.py:46-47,169-190): on every tick the trailing WINDOW seconds of each
 stream are re-extracted (MFCC + CMVN over the window only) and re-scored against all enrolled speakers -- there is no
 incremental state in the reference and none here, so results equal ModelInterface.predict on the same window.  What
-changes is the mechanics: all streams share ONE launch sequence per tick (H2D of the new samples, a device-side ring
-shift, srb200_mfcc_extract_dev over the B windows as B utterances, srb200_gmmset_score_dev, D2H of B labels).
+changes is the mechanics: all streams share ONE launch sequence per tick (H2D of the new samples, one window-slide
+launch (srb200_stream_push_i16), srb200_mfcc_extract_dev over the B windows as B utterances, srb200_gmmset_score_dev, D2H of B labels).
 A window must exceed 5*FRAME_LEN samples or the extractor refuses it (MFCC.py:56), as in the reference.
 """
 import ctypes as C
@@ -22,13 +22,12 @@ class StreamingPredictor(object):
         _lib.require_gpu()
         self.L = _lib.lib()
         self.gmmset = gmmset
-        self.set_h = gmmset._ensure_set()
-        self.S = self.L.srb200_gmmset_size(self.set_h)
+        self.S = self.L.srb200_gmmset_size(gmmset._ensure_set())
         self.ex = _MFCC.get_mfcc_extractor(fs, **mfcc_kwargs)
         self.nd = nd
         self.dim = self.L.srb200_mfcc_out_dim(self.ex._h, nd)
-        if self.dim != self.L.srb200_gmmset_dim(self.set_h):
-            raise ValueError("feature dim %d != model dim %d" % (self.dim, self.L.srb200_gmmset_dim(self.set_h)))
+        if self.dim != self.L.srb200_gmmset_dim(gmmset._ensure_set()):
+            raise ValueError("feature dim %d != model dim %d" % (self.dim, self.L.srb200_gmmset_dim(gmmset._ensure_set())))
         self.ld = (self.dim + 3) & ~3
         self.B = int(n_streams)
         self.W = int(round(window_s * fs))
@@ -45,6 +44,7 @@ class StreamingPredictor(object):
         self.best = torch.empty(self.B, dtype=torch.int32, device=dev)
         self.h_best = torch.empty(self.B, dtype=torch.int32).pin_memory()
         self.h_new = None
+        self.h2d_done = torch.cuda.Event()      # the previous tick's H2D copy has read the pinned staging buffer
         self.filled = 0
 
     def push(self, chunk):
@@ -53,22 +53,31 @@ class StreamingPredictor(object):
         torch = self.torch
         chunk = np.ascontiguousarray(chunk, dtype=np.int16)
         hop = chunk.shape[1]
+        assert chunk.shape[0] == self.B and 0 < hop < self.W, "need [n_streams, hop] samples with 0 < hop < window"
         if self.h_new is None or self.h_new.shape[1] != hop:
+            torch.cuda.current_stream().synchronize()
             self.h_new = torch.empty((self.B, hop), dtype=torch.int16).pin_memory()
             self.d_new = torch.empty((self.B, hop), dtype=torch.int16, device=self.ring.device)
+        else:
+            self.h2d_done.synchronize()         # warm-up ticks return without a sync: do not overwrite a staging buffer still being read
         self.h_new.numpy()[:] = chunk
         self.d_new.copy_(self.h_new, non_blocking=True)
-        # ring shift on the device: [old[hop:], new]
-        self.tmp[:, :self.W - hop] = self.ring[:, hop:]
-        self.tmp[:, self.W - hop:] = self.d_new
+        self.h2d_done.record()
+        st = torch.cuda.current_stream().cuda_stream
+        # slide every window and append the new samples: one launch, [old[hop:], new]
+        _lib.check(self.L.srb200_stream_push_i16(self.ring.data_ptr(), self.d_new.data_ptr(), self.tmp.data_ptr(), self.B, self.W, hop, st),
+                   "stream_push")
         self.ring, self.tmp = self.tmp, self.ring
         self.filled = min(self.W, self.filled + hop)
         if self.filled < self.W:
             return None
-        st = torch.cuda.current_stream().cuda_stream
+        set_h = self.gmmset._ensure_set()       # re-validated every tick: enrolling a speaker rebuilds the packed set
+        if self.L.srb200_gmmset_size(set_h) != self.S:
+            self.S = self.L.srb200_gmmset_size(set_h)
+            self.sums = torch.empty((self.B, self.S), dtype=torch.float64, device=self.ring.device)
         _lib.check(self.L.srb200_mfcc_extract_dev(self.ex._h, self.ring.data_ptr(), self.smp_off, self.B, self.nd,
                                                   self.feat.data_ptr(), self.ld, self.feat_off, st), "mfcc_extract_dev")
-        _lib.check(self.L.srb200_gmmset_score_dev(self.set_h, self.feat.data_ptr(), self.ld, self.dim, self.feat_off, self.B,
+        _lib.check(self.L.srb200_gmmset_score_dev(set_h, self.feat.data_ptr(), self.ld, self.dim, self.feat_off, self.B,
                                                   self.sums.data_ptr(), None, 0, self.best.data_ptr(), st), "gmmset_score_dev")
         self.h_best.copy_(self.best, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import gmm_ref, lpc_ref, mfcc_ref
-from speaker_recognition_b200 import synth
+from speaker_recognition_b200 import _lib, synth
 from speaker_recognition_b200.interface import ModelInterface
 
 pytestmark = pytest.mark.gpu
@@ -67,9 +67,9 @@ def test_batch_scorer_matches_per_utterance_path_and_oracle():
         assert np.max(np.abs(np.array(ex) - sums[i]) / np.abs(np.array(ex))) < 2e-3     # features differ at 1e-4 -> sums at ~1e-3
 
 
-def test_streaming_predictor_equals_window_predict():
-    """config-5 semantics: each tick's label == predict() on the trailing 1.5 s window (gui.py:179-190)"""
-    from speaker_recognition_b200.feature import MFCC
+def test_streaming_predictor_equals_the_oracle_on_the_trailing_window():
+    """config-5 semantics (gui.py:179-190): each tick's label == the ORACLE's label (NumPy restatement of MFCC.py + exact float64
+    GMM scores) on the trailing 1.5 s window of every stream -- checked on several ticks, not only the last one"""
     from speaker_recognition_b200.gmm.pygmm import GMM
     from speaker_recognition_b200.gmmset import GMMSet
     from speaker_recognition_b200.streaming import StreamingPredictor
@@ -80,17 +80,65 @@ def test_streaming_predictor_equals_window_predict():
         gs.gmms.append(GMM(K).set_params(W[i], M[i], Sg[i]))
         gs.y.append(i)
     sp = StreamingPredictor(gs, n_streams=B, fs=16000, window_s=1.5, nd=2)
-    n_ticks = 24000 // hop + 3
+    n_ticks = 24000 // hop + 7
     audio = np.stack([synth.audio(hop * n_ticks, seed=700 + b) for b in range(B)])
-    out = None
+    checked = 0
     for t in range(n_ticks):
         out = sp.push(audio[:, t * hop:(t + 1) * hop])
         assert (out is None) == ((t + 1) * hop < 24000)
-    for b in range(B):
-        win = audio[b, hop * n_ticks - 24000:]
-        feat = MFCC.extract(16000, win, nd=2)
-        assert feat.shape == (90, 39)
-        assert int(out[b]) == int(np.argmax(gs.predict_one_scores(feat)))
+        if out is None or (t % 3 and t != n_ticks - 1):
+            continue
+        for b in range(B):
+            win = audio[b, (t + 1) * hop - 24000:(t + 1) * hop]
+            feat = mfcc_ref.extract39(16000, win)
+            assert feat.shape == (90, 39)
+            ex = np.array([gmm_ref.score_all(W[k], M[k], Sg[k], feat, gmm_ref.MODE_LOGDOMAIN) for k in range(S)])
+            srt = np.sort(ex)
+            if srt[-1] - srt[-2] > 1e-3 * abs(srt[-1]):          # a near-tie may legitimately flip at the 1e-4 feature tolerance
+                assert int(out[b]) == int(np.argmax(ex)), (t, b)
+                checked += 1
+            got = sp.sums[b].cpu().numpy()
+            assert np.max(np.abs(got - ex) / np.abs(ex)) < 2e-3     # features differ at 1e-4 -> sums at ~1e-3
+    assert checked >= 3 * B
+    with pytest.raises(AssertionError):
+        sp.push(audio[:, :24000])                                   # hop must be shorter than the window
+
+
+def test_rejection_is_one_launch_and_matches_the_oracle():
+    """predict_one_with_rejection (src/testbench/gmmset.py:69-84): the UBM rides in the speakers' launch as model S + 1; the
+    accept / reject decision and the margin equal the float64 oracle's"""
+    from speaker_recognition_b200.gmm.pygmm import GMM
+    from speaker_recognition_b200.gmmset import GMMSet
+    L = _lib.lib()
+    S, K, D = 5, 32, 13
+    wu, mu, su = synth.model(K, D, seed=4000, floor_frac=0.0)
+    su = su * 1.5                                                    # a broad "world" model
+    ubm = GMM(K).set_params(wu, mu, su)
+    rng = np.random.default_rng(3)
+    spk = [(wu, mu + 0.8 * rng.standard_normal(mu.shape), su * 0.6) for _ in range(S)]      # MAP-like: moved means, tighter
+    gs = GMMSet(ubm=ubm, reject_threshold=0.8)
+    for i, (w, m, s) in enumerate(spk):
+        gs.gmms.append(GMM(K).set_params(w, m, s))
+        gs.y.append("spk%d" % i)
+    cases = [synth.draw(*spk[2], 400, seed=1), synth.draw(*spk[4], 250, seed=2), synth.draw(wu, mu, su, 400, seed=3),
+             synth.draw(wu, mu + 2.0, su, 300, seed=4)]
+    outcomes = set()
+    for x in cases:
+        n0 = L.srb200_score_launch_count()
+        got = gs.predict_one_with_rejection(x)
+        assert L.srb200_score_launch_count() - n0 == 1               # speakers and UBM in ONE scoring launch
+        sc = np.array([gmm_ref.score_all(w, m, s, x, gmm_ref.MODE_LOGDOMAIN) for (w, m, s) in spk]) / len(x)
+        margin = sc.max() - gmm_ref.score_all(wu, mu, su, x, gmm_ref.MODE_LOGDOMAIN) / len(x)
+        assert abs(margin - gs.reject_threshold) > 1e-3              # the case is not on the decision boundary
+        want = None if margin < gs.reject_threshold else "spk%d" % int(np.argmax(sc))
+        assert got == want
+        outcomes.add(got is None)
+        # the plain prediction ignores the UBM even though it is in the packed set
+        assert gs.predict_one(x) == "spk%d" % int(np.argmax(sc))
+    assert outcomes == {True, False}                                  # both branches exercised
+    # the batched device path ranks only the speakers as well
+    from speaker_recognition_b200.pipeline import BatchScorer
+    assert L.srb200_gmmset_size(gs._ensure_set()) == S + 1
 
 
 def test_cli_enroll_and_predict(tmp_path, capsys):
