@@ -105,6 +105,13 @@ int srb200_score_batch_f32(GMM *gmm, const float *X, int n, int dim, float *prob
  * (either may be NULL). */
 int srb200_train_f64(GMM *gmm, const double *X, const Parameter *param, uint64_t seed, int *iters_out, double *ll_out);
 int srb200_train_from_ubm_f64(GMM *gmm, GMM *ubm, const double *X, const Parameter *param, int *iters_out, double *ll_out);
+/* BATCHED MAP enrolment: models[s] becomes the UBM adapted to the frames X[frame_off[s] .. frame_off[s+1]) (rows of `dim` float64),
+ * exactly as n_models calls of train_model_from_ubm would (src/gmm/src/gmmubm.cc:17-81 inside the loop of gmm.cc:613-652; what
+ * ModelInterface.train does per name, src/gui/interface.py:77-83) -- but with ONE host->device copy of all frames, the speakers'
+ * kernels enqueued back to back, and one synchronisation per log-likelihood check for all speakers together.
+ * param->nr_instance / nr_mixture are ignored (taken from frame_off / the UBM); iters_out, ll_out: [n_models], may be NULL. */
+int srb200_train_many_from_ubm_f64(GMM *const *models, int n_models, GMM *ubm, const double *X, const int *frame_off, int dim, const Parameter *param,
+                                   int *iters_out, double *ll_out);
 
 /* K-MeansII initialisation (the reference's init_with_kmeans = 1: gmm.cc:331-344 -> kmeansII.cc:80-172, kmeans++.cc:157-213,
  * kmeans.cc:150-340), also what train_model / srb200_train_f64 run when param->init_with_kmeans != 0.  X is [n][dim] HOST memory,

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "srb200_score_batch_f32": (_ci, [_vp, _fp, _ci, _ci, _fp]),
     "srb200_train_f64": (_ci, [_vp, _dp, _PP, C.c_uint64, _ip, _dp]),
     "srb200_train_from_ubm_f64": (_ci, [_vp, _vp, _dp, _PP, _ip, _dp]),
+    "srb200_train_many_from_ubm_f64": (_ci, [C.POINTER(_vp), _ci, _vp, _dp, _ip, _ci, _PP, _ip, _dp]),
     "srb200_kmeans_init_f64": (_ci, [_dp, _ci, _ci, _ci, C.c_uint64, _dp, _dp]),
     "srb200_kmeans_lloyd_f64": (_ci, [_dp, _ci, _ci, _ci, _dp, _dp, _dp, _ip]),
     "srb200_gmmset_create": (_vp, [C.POINTER(_vp), _ci]),

@@ -584,7 +584,7 @@ static int gmm_score_host(GMM *g, const RowSrc &src, int n, int dim, double *fra
 // ---------------------------------------------------------------------------------------------
 static int em_estep(GMM *g, const float *dX, int n, int ld, int D, double *d_stats, cudaStream_t st) {
 	Context &c = ctx();
-	if (c.d_frame.ensure((size_t)n * sizeof(float)) || c.d_sums.ensure(sizeof(double))) return 1;
+	if (c.d_frame.ensure((size_t)n * sizeof(float)) || c.d_sums.ensure(sizeof(double))) return 1;      // no-ops once the workspaces are large enough
 	const int utt_off[2] = {0, n};
 	// pass A: per-frame log2 p(x) (unclamped) + total log-likelihood (clamped like the reference's monitor, gmm.cc:635)
 	if (launch_score(g->packed, dX, ld, D, utt_off, 1, c.d_sums.as<double>(), c.d_frame.as<float>(), n, nullptr, c.compat_clamp, 1, st)) return 1;
@@ -639,6 +639,102 @@ static int train_driver(GMM *g, const float *dX, int n, int ld, int D, const Par
 	if (gmm_pull_device_master(g)) return 1;
 	if (iters_out) *iters_out = iters;
 	if (ll_out) *ll_out = ll;
+	return 0;
+}
+
+static void print_param(const Parameter *p);
+
+// Batched MAP enrolment (what ModelInterface.train does with a UBM, src/gui/interface.py:77-83 -> gmmset.py:30-34 ->
+// train_model_from_ubm per speaker): every speaker's model starts as a copy of the UBM and runs GMMUBMTrainerBaseline's loop
+// (gmmubm.cc:40-81 inside GMMTrainerBaseline::train, gmm.cc:613-652) on its own frames.  Here ALL speakers' frames are staged by ONE
+// host -> device copy and the speakers advance in lockstep: per iteration the E-step / M-step / repack kernels of every still-active
+// speaker are enqueued back to back on one stream, and the log-likelihood monitor of the odd iterations is ONE device -> host copy
+// of all speakers' values -- the host synchronises nr_iteration / 2 times in total instead of once per speaker and check.
+static int train_many_from_ubm(GMM *const *models, int n_models, GMM *ubm, const RowSrc &src, const int *frame_off, int D, const Parameter *p,
+                               int *iters_out, double *ll_out) {
+	Context &c = ctx();
+	SRB_REQUIRE(models && n_models >= 1 && ubm && frame_off && p, "train_many: null argument");
+	if (c.init()) return 1;
+	if (gmm_pull_device_master(ubm)) return 1;
+	SRB_REQUIRE(ubm->dim == D && (int)ubm->weights.size() == ubm->nr_mixtures && ubm->nr_mixtures >= 1, "train_many: UBM dim %d != data dim %d (or empty UBM)", ubm->dim, D);
+	SRB_REQUIRE(D >= 1 && D <= MAX_DIM, "train_many: nr_dim %d outside [1,%d]", D, MAX_DIM);
+	const int n_total = frame_off[n_models];
+	int n_max = 0;
+	for (int s = 0; s < n_models; ++s) {
+		SRB_REQUIRE(models[s] != nullptr && models[s] != ubm, "train_many: model %d is null or the UBM itself", s);
+		SRB_REQUIRE(frame_off[s + 1] > frame_off[s], "X.size() == 0");       // gmm.cc:582-586, per speaker
+		n_max = std::max(n_max, frame_off[s + 1] - frame_off[s]);
+	}
+	if (p->verbosity >= 1) print_param(p);
+	int ld = 0;
+	if (stage_frames(src, n_total, D, &ld)) return 1;
+	const float *dX = c.d_x.as<float>();
+	const int K = ubm->nr_mixtures;
+	ubm->master_valid = ubm->master_valid && !ubm->host_stale;
+	if (gmm_ensure_device_master(ubm)) return 1;
+	// workspaces sized once for the largest speaker: nothing below reallocates, so nothing below synchronises
+	if (c.d_frame.ensure((size_t)n_max * sizeof(float)) || c.d_sums.ensure(sizeof(double)) || c.d_stats.ensure((size_t)em_stats_len(K, D) * sizeof(double)) ||
+	    c.d_misc.ensure((size_t)n_models * sizeof(double)) || c.h_misc.ensure((size_t)n_models * sizeof(double)))
+		return 1;
+	double *d_stats = c.d_stats.as<double>(), *d_ll = c.d_misc.as<double>(), *h_ll = c.h_misc.as<double>();
+	for (int s = 0; s < n_models; ++s) {                              // gmm_replace_with (gmmubm.cc:29-38): deep copy of the UBM
+		GMM *g = models[s];
+		g->nr_mixtures = K;
+		g->dim = D;
+		g->weights = ubm->weights;
+		g->means = ubm->means;
+		g->sigmas = ubm->sigmas;
+		g->invalidate();
+		if (gmm_ensure_device_master(g)) return 1;
+		if (launch_pack_from_master(g->d_params, K, D, g->packed, c.stream)) return 1;
+		g->packed_valid = true;
+	}
+	std::vector<char> active(n_models, 1);
+	std::vector<double> last_ll(n_models, -DBL_MAX), ll(n_models, 0.0);
+	std::vector<int> iters(n_models, 0);
+	int n_active = n_models;
+	for (int i = 0; i < p->nr_iteration && n_active > 0; ++i) {
+		for (int s = 0; s < n_models; ++s) {
+			if (!active[s]) continue;
+			GMM *g = models[s];
+			const int n = frame_off[s + 1] - frame_off[s];
+			const float *xs = dX + (size_t)frame_off[s] * ld;
+			if (em_estep(g, xs, n, ld, D, d_stats, c.stream)) return 1;
+			if (launch_mstep(g->d_params, ubm->d_params, K, D, d_stats, (long long)n, p->min_covar, 1, c.stream)) return 1;
+			if (launch_pack_from_master(g->d_params, K, D, g->packed, c.stream)) return 1;
+			++iters[s];
+		}
+		if (i % 2 == 0) continue;                                     // gmm.cc:622
+		for (int s = 0; s < n_models; ++s) {                         // log-likelihood of the UPDATED models (gmm.cc:631-651)
+			if (!active[s]) continue;
+			const int n = frame_off[s + 1] - frame_off[s];
+			const int utt_off[2] = {0, n};
+			if (launch_score(models[s]->packed, dX + (size_t)frame_off[s] * ld, ld, D, utt_off, 1, d_ll + s, nullptr, 0, nullptr, c.compat_clamp, 0, c.stream))
+				return 1;
+		}
+		SRB_CUDA(cudaMemcpyAsync(h_ll, d_ll, (size_t)n_models * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+		SRB_CUDA(cudaStreamSynchronize(c.stream));                   // the ONE synchronisation of this monitoring round
+		for (int s = 0; s < n_models; ++s) {
+			if (!active[s]) continue;
+			ll[s] = h_ll[s];
+			if (p->verbosity >= 1) printf("model %d iter %d: ll %lf\n", s, i, ll[s]);
+			const double ll_diff = ll[s] - last_ll[s];
+			if (fabs(ll_diff) / fabs(ll[s]) < p->threshold && ll_diff < p->threshold) {
+				active[s] = 0;
+				--n_active;
+			}
+			last_ll[s] = ll[s];
+		}
+	}
+	SRB_CUDA(cudaStreamSynchronize(c.stream));
+	for (int s = 0; s < n_models; ++s) {
+		GMM *g = models[s];
+		g->host_stale = true;
+		g->master_valid = true;
+		if (gmm_pull_device_master(g)) return 1;
+		if (iters_out) iters_out[s] = iters[s];
+		if (ll_out) ll_out[s] = ll[s];
+	}
 	return 0;
 }
 
@@ -941,6 +1037,14 @@ int srb200_train_from_ubm_f64(GMM *gmm, GMM *ubm, const double *X, const Paramet
 	RowSrc src;
 	src.c64 = X;
 	return train_host(gmm, ubm, src, param, 0, iters_out, ll_out);
+}
+
+int srb200_train_many_from_ubm_f64(GMM *const *models, int n_models, GMM *ubm, const double *X, const int *frame_off, int dim, const Parameter *param,
+                                   int *iters_out, double *ll_out) {
+	API_ENTER();
+	RowSrc src;
+	src.c64 = X;
+	return train_many_from_ubm(models, n_models, ubm, src, frame_off, dim, param, iters_out, ll_out);
 }
 
 // ---- EM building blocks on device data ----

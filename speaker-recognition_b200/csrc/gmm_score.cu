@@ -19,6 +19,7 @@
 // The kernel is bound by the fp32 FMA pipe (2*D FFMA per frame-mixture pair); HBM traffic is the x tile once
 // and the parameters from L2 (DESIGN.md "roofline").
 #include "gmm_model.h"
+#include <algorithm>
 #include "kernels.h"
 
 namespace srb {
@@ -337,21 +338,26 @@ __global__ void score_reduce_kernel(const double *__restrict__ partial, const in
 // ------------------------------------------------------------------------------------------------
 // host side: frame-tile tables (cached per shape), chunking, launch
 // ------------------------------------------------------------------------------------------------
-struct TileTable {
-	std::vector<int> key;            // utt_off + S
+struct TileTable {                   // one cached shape; slots are REUSED on eviction and their buffers only grow
+	std::vector<int> key;            // utt_off + S + FT
 	int n_ftiles = 0;
+	unsigned char *d_meta = nullptr, *h_meta = nullptr;      // ftiles int4[n_ftiles] | utt_tile_start int[n_utt + 1]: device copy and pinned image
+	size_t meta_cap = 0, partial_cap = 0;
+	cudaEvent_t copied = nullptr;    // the upload of h_meta has executed (the image may be rewritten)
 	int4 *d_ftiles = nullptr;
 	int *d_utt_tile_start = nullptr;
 	double *d_partial = nullptr;
 	uint64_t stamp = 0;
 };
+constexpr size_t MAX_TABLES = 256;   // batched enrolment scores every speaker's own frame range: one shape per speaker
 static std::vector<TileTable> g_tables;
 static uint64_t g_stamp = 0;
 
 static void free_table(TileTable &t) {
-	if (t.d_ftiles) cudaFree(t.d_ftiles);
-	if (t.d_utt_tile_start) cudaFree(t.d_utt_tile_start);
+	if (t.d_meta) cudaFree(t.d_meta);
+	if (t.h_meta) cudaFreeHost(t.h_meta);
 	if (t.d_partial) cudaFree(t.d_partial);
+	if (t.copied) cudaEventDestroy(t.copied);
 	t = TileTable();
 }
 
@@ -360,6 +366,8 @@ void score_tables_release() {
 	g_tables.clear();
 }
 
+// Frame-tile table of a batch shape WITHOUT steady-state allocations: a miss rewrites the least recently used slot in place
+// (pinned image -> one async copy on the caller's stream, no synchronisation); buffers are reallocated only to grow.
 static int get_table(const int *utt_off, int n_utt, int S, int FT, cudaStream_t st, TileTable **out) {
 	std::vector<int> key(utt_off, utt_off + n_utt + 1);
 	key.push_back(S);
@@ -370,35 +378,61 @@ static int get_table(const int *utt_off, int n_utt, int S, int FT, cudaStream_t 
 			*out = &t;
 			return 0;
 		}
-	if (g_tables.size() >= 32) {   // evict least recently used
-		size_t lru = 0;
-		for (size_t i = 1; i < g_tables.size(); ++i)
-			if (g_tables[i].stamp < g_tables[lru].stamp) lru = i;
-		SRB_CUDA(cudaStreamSynchronize(st));
-		free_table(g_tables[lru]);
-		g_tables.erase(g_tables.begin() + lru);
+	TileTable *t = nullptr;
+	if (g_tables.size() < MAX_TABLES) {
+		g_tables.reserve(MAX_TABLES);            // pointers handed out earlier stay valid
+		g_tables.emplace_back();
+		t = &g_tables.back();
+		SRB_CUDA(cudaEventCreateWithFlags(&t->copied, cudaEventDisableTiming));
+	} else {
+		t = &g_tables[0];
+		for (auto &c : g_tables)
+			if (c.stamp < t->stamp) t = &c;
+		SRB_CUDA(cudaEventSynchronize(t->copied));
 	}
-	std::vector<int4> ft;
-	std::vector<int> uts(n_utt + 1);
+	long long nft = 0;
+	for (int u = 0; u < n_utt; ++u) nft += (utt_off[u + 1] - utt_off[u] + FT - 1) / FT;
+	const size_t off_uts = (size_t)std::max<long long>(nft, 1) * sizeof(int4), bytes = off_uts + (size_t)(n_utt + 1) * sizeof(int);
+	const size_t pbytes = (size_t)std::max<long long>(nft, 1) * (size_t)S * SC_MAX_WARPS * sizeof(double);
+	if (bytes > t->meta_cap) {
+		if (t->d_meta) {
+			SRB_CUDA(cudaStreamSynchronize(st));
+			cudaFree(t->d_meta);
+			cudaFreeHost(t->h_meta);
+			t->d_meta = t->h_meta = nullptr;
+		}
+		const size_t want = bytes + bytes / 2 + 1024;
+		SRB_CUDA(cudaMalloc(&t->d_meta, want));
+		SRB_CUDA(cudaMallocHost(&t->h_meta, want));
+		t->meta_cap = want;
+	}
+	if (pbytes > t->partial_cap) {
+		if (t->d_partial) {
+			SRB_CUDA(cudaStreamSynchronize(st));
+			cudaFree(t->d_partial);
+			t->d_partial = nullptr;
+		}
+		const size_t want = pbytes + pbytes / 2 + 1024;
+		SRB_CUDA(cudaMalloc(&t->d_partial, want));
+		t->partial_cap = want;
+	}
+	int4 *ft = reinterpret_cast<int4 *>(t->h_meta);
+	int *uts = reinterpret_cast<int *>(t->h_meta + off_uts);
+	int n = 0;
 	for (int u = 0; u < n_utt; ++u) {
-		uts[u] = (int)ft.size();
+		uts[u] = n;
 		const int b = utt_off[u], e = utt_off[u + 1];
-		for (int f = b; f < e; f += FT) ft.push_back(make_int4(f, (e - f < FT ? e - f : FT), u, 0));
+		for (int f = b; f < e; f += FT) ft[n++] = make_int4(f, (e - f < FT ? e - f : FT), u, 0);
 	}
-	uts[n_utt] = (int)ft.size();
-	TileTable t;
-	t.key = key;
-	t.n_ftiles = (int)ft.size();
-	t.stamp = ++g_stamp;
-	const size_t nft = ft.size() ? ft.size() : 1;
-	SRB_CUDA(cudaMalloc(&t.d_ftiles, nft * sizeof(int4)));
-	SRB_CUDA(cudaMalloc(&t.d_utt_tile_start, (size_t)(n_utt + 1) * sizeof(int)));
-	SRB_CUDA(cudaMalloc(&t.d_partial, nft * (size_t)S * SC_MAX_WARPS * sizeof(double)));
-	if (!ft.empty()) SRB_CUDA(cudaMemcpyAsync(t.d_ftiles, ft.data(), ft.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-	SRB_CUDA(cudaMemcpyAsync(t.d_utt_tile_start, uts.data(), uts.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-	SRB_CUDA(cudaStreamSynchronize(st));   // the source vectors die with this scope
-	g_tables.push_back(t);
-	*out = &g_tables.back();
+	uts[n_utt] = n;
+	t->key = key;
+	t->n_ftiles = n;
+	t->stamp = ++g_stamp;
+	t->d_ftiles = reinterpret_cast<int4 *>(t->d_meta);
+	t->d_utt_tile_start = reinterpret_cast<int *>(t->d_meta + off_uts);
+	SRB_CUDA(cudaMemcpyAsync(t->d_meta, t->h_meta, bytes, cudaMemcpyHostToDevice, st));
+	SRB_CUDA(cudaEventRecord(t->copied, st));
+	*out = t;
 	return 0;
 }
 

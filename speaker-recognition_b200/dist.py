@@ -6,6 +6,9 @@ tests) -- and nothing else crosses the fabric.  The path shards three ways (SURV
   * frame-sharded UBM EM (BASELINE config 3): every rank keeps N/world frames resident, runs the E-step kernels on
     its shard, ONE all-reduce(sum) of the float64 statistics vector per iteration, identical float64 M-step on every
     rank (deterministic, so no broadcast)                                 -> em_train
+  * speaker-sharded MAP enrolment: names are dealt to the ranks (shard_range), every rank adapts the UBM to ITS speakers in one
+    batched launch sequence, the resulting models are exchanged as text at the end -- no collective on the data path
+                                                                           -> enroll_sharded
   * speaker-sharded predict (BASELINE config 4): every rank scores the same features against its S/world speakers,
     all-gather of the per-rank [B, S_local] sums, global argmax           -> speaker_sharded_argmax
 
@@ -78,6 +81,27 @@ def speaker_sharded_argmax(local_sums, group=None):
     d.all_gather(parts, padded, group=group)
     full = torch.cat([p_[:, :n] for p_, n in zip(parts, sizes)], dim=1)
     return torch.argmax(full, dim=1), full      # torch.argmax returns the first maximum, like Python's max()
+
+
+def enroll_sharded(names, feats, fit_many, group=None):
+    """MAP enrolment of many speakers over the ranks (SURVEY.md s8e "MAP enrolment of many speakers: speakers over GPUs, no
+    collective").  names: list (same on every rank, same order); feats: dict name -> frame matrix -- a rank only needs the entries
+    of its own shard; fit_many(names_local, [feats...]) -> list of picklable models (e.g. GMM text dumps) for those names.
+    Returns {name: model} for ALL names on every rank (one all_gather_object of the small model blobs at the end)."""
+    d = _dist()
+    rank, ws = world()
+    lo, hi = shard_range(len(names), rank, ws)
+    mine = list(names[lo:hi])
+    models = fit_many(mine, [feats[n] for n in mine]) if mine else []
+    assert len(models) == len(mine)
+    if ws == 1:
+        return dict(zip(mine, models))
+    out = [None] * ws
+    d.all_gather_object(out, list(zip(mine, models)), group=group)
+    full = {}
+    for part in out:
+        full.update(dict(part))
+    return full
 
 
 class DeviceEM(object):

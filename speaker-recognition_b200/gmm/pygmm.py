@@ -167,6 +167,31 @@ class GMM(object):
         self._version += 1
         return self
 
+    @staticmethod
+    def fit_many_from_ubm(gmms, Xs, ubm):
+        """MAP-adapt `ubm` to every X in Xs at once (gmms[i] receives the model of Xs[i]): one host->device copy of all frames, the
+        speakers' EM kernels back to back, one synchronisation per log-likelihood check for all speakers (C ABI:
+        srb200_train_many_from_ubm_f64).  Same result as [g.fit(X, ubm) for g, X in zip(gmms, Xs)]; the training parameters
+        (nr_iteration, threshold, min_covar, ...) are taken from gmms[0]."""
+        assert len(gmms) == len(Xs) and len(gmms) >= 1
+        mats = [GMM._matrix(X) for X in Xs]
+        D = mats[0].shape[1]
+        off = np.zeros(len(mats) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(m) for m in mats])
+        X = np.ascontiguousarray(np.concatenate(mats, axis=0))
+        param = gmms[0]._gen_param(X)
+        arr = (C.c_void_p * len(gmms))(*[g.gmm for g in gmms])
+        its = (C.c_int * len(gmms))()
+        lls = (C.c_double * len(gmms))()
+        L = _lib.lib()
+        _lib.check(L.srb200_train_many_from_ubm_f64(arr, len(gmms), ubm.gmm, _lib.dptr(X), off.ctypes.data_as(C.POINTER(C.c_int)), D,
+                                                    C.byref(param), its, lls), "GMM.fit_many_from_ubm")
+        for i, g in enumerate(gmms):
+            g.nr_mixture = L.get_nr_mixtures(g.gmm)
+            g.last_iterations, g.last_log_likelihood = its[i], lls[i]
+            g._version += 1
+        return gmms
+
     _seed_counter = [0]
 
     @staticmethod

@@ -80,6 +80,18 @@ class GMMSet(object):
         gmm.fit(x, self.ubm)
         self.gmms.append(gmm)
 
+    def fit_many(self, xs, labels):
+        """enrol several speakers at once.  With a UBM this is ONE batched MAP adaptation (GMM.fit_many_from_ubm); without one it is
+        the reference's loop of independent EM trainings (gmmset.py:30-34)."""
+        if self.ubm is None or not len(labels):
+            for x, label in zip(xs, labels):
+                self.fit_new(x, label)
+            return
+        gmms = [GMM(self.gmm_order, **self.kwargs) for _ in labels]
+        GMM.fit_many_from_ubm(gmms, xs, self.ubm)
+        self.y.extend(labels)
+        self.gmms.extend(gmms)
+
     def cluster_by_label(self, X, y):
         Xtmp = defaultdict(list)
         for ind, x in enumerate(X):
@@ -95,8 +107,7 @@ class GMMSet(object):
 
     def fit(self, X, y):
         X, y = self.cluster_by_label(X, y)
-        for ind, x in enumerate(X):
-            self.fit_new(x, y[ind])
+        self.fit_many(X, y)
         self.auto_tune_parameter(X, y)
 
     # ---- scoring ----

@@ -47,8 +47,10 @@ class ModelInterface(object):
         start = time.time()
         if not quiet:
             print("Start training...")
-        for name, feats in self.features.items():
-            self.gmmset.fit_new(np.asarray(feats), name)
+        # the reference fits one name after the other (interface.py:81-82); with a UBM all names are MAP-adapted in ONE batched
+        # launch sequence (GMMSet.fit_many), without one it is the same loop of independent EM trainings
+        names = list(self.features.keys())
+        self.gmmset.fit_many([np.asarray(self.features[n]) for n in names], names)
         if not quiet:
             print(time.time() - start, " seconds")
 

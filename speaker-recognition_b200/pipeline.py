@@ -62,11 +62,25 @@ class BatchScorer(object):
             raise ValueError("an utterance is too short for MFCC extraction")
         self.rows = int(rows)
         self.feat_off = (C.c_int * (B + 1))()
-        self.d_pcm = torch.empty(self.n_samples, dtype=torch.int16, device=self.device)
-        self.d_feat = torch.empty((self.rows, self.ld), dtype=torch.float32, device=self.device)
-        self.d_sums = torch.empty((B, self.S), dtype=torch.float64, device=self.device)
-        self.d_best = torch.empty(B, dtype=torch.int32, device=self.device)
-        self.h_best = torch.empty(B, dtype=torch.int32).pin_memory()
+        # device / pinned buffers only ever GROW (with headroom): a stream of ragged batches stops allocating once it has seen its
+        # largest batch; the tensors used below are views of the capacity buffers
+        cap = getattr(self, "_cap", None)
+        if cap is None or self.n_samples > cap["samples"] or self.rows > cap["rows"] or B > cap["B"] or self.S != cap["S"]:
+            grow = lambda need, have: max(need + need // 4 + 64, have)
+            cap = dict(samples=grow(self.n_samples, cap["samples"] if cap else 0), rows=grow(self.rows, cap["rows"] if cap else 0),
+                       B=grow(B, cap["B"] if cap else 0), S=self.S)
+            torch.cuda.current_stream().synchronize()
+            self._pcm_buf = torch.empty(cap["samples"], dtype=torch.int16, device=self.device)
+            self._feat_buf = torch.empty((cap["rows"], self.ld), dtype=torch.float32, device=self.device)
+            self._sums_buf = torch.empty((cap["B"], self.S), dtype=torch.float64, device=self.device)
+            self._best_buf = torch.empty(cap["B"], dtype=torch.int32, device=self.device)
+            self._hbest_buf = torch.empty(cap["B"], dtype=torch.int32).pin_memory()
+            self._cap = cap
+        self.d_pcm = self._pcm_buf[:self.n_samples]
+        self.d_feat = self._feat_buf[:self.rows]
+        self.d_sums = self._sums_buf[:B]
+        self.d_best = self._best_buf[:B]
+        self.h_best = self._hbest_buf[:B]
         self.B = B
         self._shape = key
         # sub-batches for the end-to-end path: H2D of chunk c+1 overlaps the kernels of chunk c
@@ -88,8 +102,11 @@ class BatchScorer(object):
             self.chunks.append(dict(u0=u0, u1=u1, s0=int(off[u0]), s1=int(off[u1]), smp=smp, row0=row0, rows=rows_c,
                                     feat_off=(C.c_int * (u1 - u0 + 1))()))
             row0 += rows_c
-        self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.copy_events = [torch.cuda.Event() for _ in self.chunks]
+        if getattr(self, "copy_stream", None) is None:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+            self.copy_events = []
+        while len(self.copy_events) < len(self.chunks):
+            self.copy_events.append(torch.cuda.Event())
 
     # ---- stages (each enqueues on the current torch stream) ----
     def upload(self, pcm_host):

@@ -172,6 +172,26 @@ def gen_realparams():
     for i, f in frames.items():
         flat["realset/frames_%d" % i] = f
     assert int(np.argmax(sums)) == src
+    # (c) batched MAP enrolment: six speakers with different amounts of data, each adapted from the shipped 32-mixture UBM by TWO
+    # iterations of the reference's own GMMUBMTrainerBaseline (ref_harness: ref_map_iteration)
+    wu, mu, su = z["ubm32/w"], z["ubm32/mean"], z["ubm32/sigma"]
+    rng = np.random.default_rng(77)
+    lens = [150, 333, 900, 64, 512, 257]
+    Xs = [synth.draw(wu, mu + 0.4 * su * rng.standard_normal(mu.shape), su, n, seed=200 + i) for i, n in enumerate(lens)]
+    ubm = ref_so.RefGMM(wu, mu, su)
+    means = []
+    for X in Xs:
+        spk = ref_so.RefGMM(wu, mu, su)
+        spk.map_iteration(ubm, X, 2)
+        spk.map_iteration(ubm, X, 2)
+        w2, m2, s2 = spk.params()
+        assert np.array_equal(w2, wu) and np.array_equal(s2, su)       # MAP moves the means only (gmmubm.cc:40-81)
+        means.append(m2)
+        spk.free()
+    ubm.free()
+    flat["mapset/X"] = np.concatenate(Xs)
+    flat["mapset/frame_off"] = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    flat["mapset/mean2"] = np.stack(means)
     np.savez_compressed(os.path.join(HERE, "realparams_ref.npz"), **flat)
     print("realparams_ref.npz keys:", len(flat))
 

@@ -94,8 +94,20 @@ def _worker(rank, world, port, out_dir):
         slo, shi = sdist.shard_range(S, rank, world)
         full = torch.from_numpy(np.random.default_rng(9).standard_normal((4, S)))
         best, gathered = sdist.speaker_sharded_argmax(full[:, slo:shi].clone())
+        # ---- speaker-sharded MAP enrolment: every rank adapts its share of the names, models are exchanged at the end ----
+        names = ["n%d" % i for i in range(5)]
+        feats = {nm: X[300 * i:300 * i + 200 + 37 * i] + 0.1 * i for i, nm in enumerate(names)}
+        calls = []
+
+        def fit_many(local_names, local_feats):
+            calls.append(list(local_names))
+            return [gmm_ref.map_iteration(wt, mt, st_, mt, f, exact_exp=True)[1].tobytes() for f in local_feats]
+        enrolled = sdist.enroll_sharded(names, feats, fit_many)
+        elo, ehi = sdist.shard_range(len(names), rank, world)
+        assert calls == [names[elo:ehi]]                                   # one batched call per rank, over its own names only
         np.savez(os.path.join(out_dir, "misc_rank%d.npz" % rank), it2=it2, map_m=be3.m, labels=np.array(labels), best=best.numpy(),
-                 gathered=gathered.numpy(), full=full.numpy())
+                 gathered=gathered.numpy(), full=full.numpy(),
+                 **{"enr_" + nm: np.frombuffer(enrolled[nm], dtype=np.float64) for nm in names})
     finally:
         dist.destroy_process_group()
 
@@ -129,6 +141,10 @@ def test_world2_gloo_em_and_sharding(tmp_path):
     assert list(q[0]["labels"]) == ["u%d" % u for u in range(7)] == list(q[1]["labels"])
     assert np.array_equal(q[0]["gathered"], q[0]["full"]) and np.array_equal(q[1]["gathered"], q[0]["full"])
     assert np.array_equal(q[0]["best"], np.argmax(q[0]["full"], axis=1)) and np.array_equal(q[0]["best"], q[1]["best"])
+    for i in range(5):                                                     # every rank holds every speaker's model, equal to the oracle's
+        f = X[300 * i:300 * i + 200 + 37 * i] + 0.1 * i
+        want = gmm_ref.map_iteration(wt, mt, st_, mt, f, exact_exp=True)[1].ravel()
+        assert np.array_equal(q[0]["enr_n%d" % i], want) and np.array_equal(q[1]["enr_n%d" % i], want)
 
 
 def test_shard_range_covers_everything():

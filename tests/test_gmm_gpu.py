@@ -303,3 +303,54 @@ def test_dist_em_train_with_device_backend_single_rank():
     gw, gm, gsg = g.get_params()
     assert np.max(rel_err(gm, m)) < 5e-4 and np.max(np.abs(gsg - s) / s) < 5e-4 and np.max(np.abs(gw - w) / w) < 5e-4
     assert abs(ll - gmm_ref.score_all(w, m, s, X)) < 1e-4 * abs(ll)
+
+
+def test_batched_map_enrolment_matches_the_reference_per_speaker(golden_gmm, golden_real):
+    """srb200_train_many_from_ubm_f64 (what ModelInterface.train runs with a UBM): six speakers with different amounts of data in
+    ONE call equal, speaker by speaker, two iterations of the reference's GMMUBMTrainerBaseline (fixture from ref_map_iteration),
+    and equal the one-speaker-at-a-time path of this library"""
+    c, m = golden_gmm.case("ubm32"), golden_real.case("mapset")
+    ubm = GMM(32).set_params(c["w"], c["mean"], c["sigma"])
+    off = m["frame_off"]
+    Xs = [m["X"][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    gmms = [GMM(32, nr_iteration=2, threshold=0.0) for _ in Xs]
+    GMM.fit_many_from_ubm(gmms, Xs, ubm)
+    for i, g in enumerate(gmms):
+        w, mean, sg = g.get_params()
+        assert g.last_iterations == 2
+        assert np.max(np.abs(mean - m["mean2"][i]) / np.maximum(1.0, np.abs(m["mean2"][i]))) < 1e-4
+        assert np.array_equal(w, c["w"]) and np.array_equal(sg, c["sigma"])        # weights and sigmas stay the UBM's (gmmubm.cc:40-81)
+        one = GMM(32, nr_iteration=2, threshold=0.0).fit(Xs[i], ubm)
+        assert np.max(np.abs(one.get_params()[1] - mean)) < 1e-9                   # same kernels, same order: batching changes nothing
+        ex = gmm_ref.score_all(w, mean, sg, Xs[i], gmm_ref.MODE_LOGDOMAIN)
+        assert abs(g.last_log_likelihood - ex) < 1e-5 * abs(ex)
+    # the convergence rule is applied per speaker (gmm.cc:643-648): a huge threshold stops everyone at the second check
+    gm2 = [GMM(32, nr_iteration=20, threshold=1e9) for _ in Xs]
+    GMM.fit_many_from_ubm(gm2, Xs, ubm)
+    assert [g.last_iterations for g in gm2] == [4] * len(Xs)
+
+
+def test_model_interface_train_with_ubm_enrols_everyone_in_one_batch(tmp_path, golden_gmm):
+    """ModelInterface.train with a UBM file (src/gui/interface.py:63-83): 100 speakers enrolled by ONE batched MAP adaptation; the
+    result equals the per-speaker path and the enrolled set predicts its own speakers"""
+    from speaker_recognition_b200.interface import ModelInterface
+    c = golden_gmm.case("ubm32")
+    ubm = GMM(32).set_params(c["w"], c["mean"], c["sigma"])
+    ubm_file = str(tmp_path / "ubm.model")
+    ubm.dump(ubm_file, precision=17)
+    rng = np.random.default_rng(5)
+    mi = ModelInterface()
+    mi.UBM_MODEL_FILE = ubm_file
+    data = {}
+    for i in range(100):
+        shift = 0.6 * c["sigma"] * rng.standard_normal(c["mean"].shape)
+        data["p%03d" % i] = synth.draw(c["w"], c["mean"] + shift, c["sigma"], 120 + 7 * (i % 13), seed=900 + i)
+        mi.features["p%03d" % i].extend(data["p%03d" % i])
+    L = _lib.lib()
+    mi.train(quiet=True)
+    assert len(mi.gmmset.gmms) == 100 and mi.gmmset.ubm is not None
+    for k in (0, 37, 99):
+        nm = mi.gmmset.y[k]
+        one = GMM(32).fit(data[nm], mi.gmmset.ubm)
+        assert np.max(np.abs(one.get_params()[1] - mi.gmmset.gmms[k].get_params()[1])) < 1e-9
+        assert mi.gmmset.predict_one(data[nm]) == nm

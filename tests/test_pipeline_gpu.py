@@ -162,3 +162,51 @@ def test_cli_enroll_and_predict(tmp_path, capsys):
     for f, label in out:
         assert os.path.basename(f).split("_")[0] == label
     assert "->" in capsys.readouterr().out
+
+
+def test_ragged_batches_do_not_allocate_after_warm_up():
+    """200 batches of random utterance counts and lengths through the public batched API: once the largest batch has been seen, the
+    device-side free memory does not move (no cudaMalloc in libsrb200's shape / tile-table caches -- their slots are rewritten in
+    place -- nor in the pipeline's buffers) and the per-call latency stays flat"""
+    import time
+    import torch
+    from speaker_recognition_b200.gmm.pygmm import GMM
+    from speaker_recognition_b200.gmmset import GMMSet
+    from speaker_recognition_b200.pipeline import BatchScorer
+    S, K, D = 8, 32, 39
+    W, M, Sg = synth.models(S, K, D, seed0=3100)
+    gs = GMMSet(gmm_order=K)
+    for i in range(S):
+        gs.gmms.append(GMM(K).set_params(W[i], M[i], Sg[i]))
+        gs.y.append(i)
+    bs = BatchScorer(gs, fs=16000, nd=2)
+    rng = np.random.default_rng(11)
+    Bmax, Lmax = 6, 40000
+    pool = torch.from_numpy(synth.audio(Bmax * Lmax, seed=5)).pin_memory()
+
+    def run(lengths):
+        n = int(sum(lengths))
+        t0 = time.perf_counter()
+        lab = bs.predict_pcm(pool[:n], lengths)
+        return time.perf_counter() - t0, lab.numpy().copy()
+    for _ in range(3):
+        run([Lmax] * Bmax)                                       # warm-up with the largest batch
+    shapes = [[int(rng.integers(4000, Lmax)) for _ in range(int(rng.integers(1, Bmax + 1)))] for _ in range(40)]
+    for sh in shapes[:20]:
+        run(sh)                                                   # fills the 16 / 256 cache slots once
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    lat = []
+    for i in range(200):
+        sh = shapes[i % len(shapes)] if i % 3 else [int(rng.integers(4000, Lmax)) for _ in range(int(rng.integers(1, Bmax + 1)))]
+        dt, lab = run(sh)
+        lat.append(dt)
+        assert lab.shape == (len(sh),)
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] == free0                  # nothing was allocated (or freed) on the device
+    lat = np.sort(np.array(lat))
+    assert lat[int(0.95 * len(lat))] < 4.0 * lat[len(lat) // 2]  # no allocation / synchronisation spikes
+    # and the answers do not depend on what was cached: a fresh scorer gives the same labels for the last shape
+    bs2 = BatchScorer(gs, fs=16000, nd=2)
+    n = int(sum(sh))
+    assert np.array_equal(bs2.predict_pcm(pool[:n], sh).numpy(), lab)
