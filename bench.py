@@ -380,7 +380,8 @@ def sub_c3_em(L, rank, world, iters=10, N=1000000, K=512, D=39):
             "allreduce_bytes": int(stats.numel() * 8), "scaling": "strong", "final_ll": ll,
             "algorithmic_tflops": 7.0 * D * N * K * done / (ms * 1e-3) / 1e12,
             "limit": ("the all-reduce is %.1f %% of an iteration: compute-bound" % (100.0 * ar_us * 1e-3 / per_it)) if world > 1 else "single GPU: no exchange",
-            "e_step_passes": n_estep}
+            "e_step_passes": n_estep, "em_route_last": int(L.srb200_last_em_route()),
+            "em_route_note": "1 = tcgen05 E-step (gmm_em_tc.cu), 0 = fp32 FMA kernels (gmm_em.cu)"}
 
 
 def sub_c4(L, rank, world, S=1000, K=256, B=8, steps=5):

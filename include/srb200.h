@@ -83,6 +83,10 @@ int srb200_get_compat_clamp(void);
 int srb200_set_score_path(int path);
 int srb200_get_score_path(void);
 int srb200_last_score_route(void);
+/* route of the most recent EM E-step: 1 = tensor cores (gmm_em_tc.cu), 0 = fp32 FMA kernels (gmm_em.cu), -1 = none yet */
+int srb200_last_em_route(void);
+/* -1 (default): tensor cores for large jobs (K > 64, n K >= 2^24, 2 D + 1 <= 128), 0: FMA kernels only, 1: tensor cores wherever the shape allows */
+int srb200_set_em_path(int path);
 long long srb200_score_launch_count(void);          /* scoring launches issued by this process so far */
 int srb200_tc_pack_stats(GMM *const *models, int n_models, int *blocks_out, int *hard_entries_out, int *max_hard_per_block_out);
 /* the packed operands of route 1 (host only): info_out[8] = {Kp, blocks, columns per speaker, halfs per block, ints per block

@@ -54,6 +54,8 @@ PROTOTYPES = {
     "srb200_set_score_path": (_ci, [_ci]),
     "srb200_get_score_path": (_ci, []),
     "srb200_last_score_route": (_ci, []),
+    "srb200_last_em_route": (_ci, []),
+    "srb200_set_em_path": (_ci, [_ci]),
     "srb200_score_launch_count": (_cll, []),
     "srb200_tc_pack_stats": (_ci, [C.POINTER(_vp), _ci, _ip, _ip, _ip]),
     "srb200_tc_pack_export": (_ci, [C.POINTER(_vp), _ci, _ip, C.POINTER(C.c_uint16), _ip, _fp]),

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libsrb200.so")
-SOURCES = ["api.cu", "gmm_score.cu", "gmm_score_tc2.cu", "gmm_em.cu", "mfcc.cu", "lpc.cu", "silence.cu", "kmeans.cu"]
+SOURCES = ["api.cu", "gmm_score.cu", "gmm_score_tc2.cu", "gmm_em.cu", "gmm_em_tc.cu", "mfcc.cu", "lpc.cu", "silence.cu", "kmeans.cu"]
 HEADERS = ["common.cuh", "gmm_model.h", "kernels.h", "fft_core.h", "gmm_score_tc2.cuh", "gmm_score_tc_layout.h", os.path.join("..", "..", "include", "srb200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

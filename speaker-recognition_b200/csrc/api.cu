@@ -104,6 +104,8 @@ void PackedModels::release() {
 	if (d_tiles) cudaFree(d_tiles);
 	d_tiles = nullptr;
 	release_tc();
+	emtc_release(emtc);
+	emtc = nullptr;
 	bytes = 0;
 	S = 0;
 }
@@ -586,6 +588,20 @@ static int em_estep(GMM *g, const float *dX, int n, int ld, int D, double *d_sta
 	Context &c = ctx();
 	if (c.d_frame.ensure((size_t)n * sizeof(float)) || c.d_sums.ensure(sizeof(double))) return 1;      // no-ops once the workspaces are large enough
 	const int utt_off[2] = {0, n};
+	// large models: both passes on the tensor cores, operand images built on the device from the float64 master (gmm_em_tc.cu);
+	// parameters the uncorrected expanded form is not accurate for (and small jobs) take the FMA kernels below
+	c.last_em_route = 0;
+	if (em_tc_eligible(g->nr_mixtures, D, n)) {
+		int used = 0;
+		if (gmm_ensure_device_master(g)) return 1;
+		if (launch_estep_tc(g->packed, g->d_params, dX, n, ld, D, g->nr_mixtures, c.d_frame.as<float>(), c.d_sums.as<double>(), d_stats, c.compat_clamp, st,
+		                    &used))
+			return 1;
+		if (used) {
+			c.last_em_route = 1;
+			return 0;
+		}
+	}
 	// pass A: per-frame log2 p(x) (unclamped) + total log-likelihood (clamped like the reference's monitor, gmm.cc:635)
 	if (launch_score(g->packed, dX, ld, D, utt_off, 1, c.d_sums.as<double>(), c.d_frame.as<float>(), n, nullptr, c.compat_clamp, 1, st)) return 1;
 	// pass B: responsibilities + sufficient statistics
@@ -855,6 +871,13 @@ int srb200_set_score_path(int path) {
 }
 int srb200_get_score_path(void) { return ctx().score_path; }
 int srb200_last_score_route(void) { return ctx().last_score_route; }
+int srb200_last_em_route(void) { return ctx().last_em_route; }
+int srb200_set_em_path(int path) {
+	API_ENTER();
+	SRB_REQUIRE(path >= -1 && path <= 1, "em path must be -1 (default), 0 (fp32 FMA kernels) or 1 (tcgen05 wherever the shape allows)");
+	ctx().em_path = path;
+	return 0;
+}
 long long srb200_score_launch_count(void) { return ctx().score_launches; }
 
 GMM *new_gmm(int nr_mixture, int covariance_type) {

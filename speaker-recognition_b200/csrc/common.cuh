@@ -57,6 +57,8 @@ struct Context {
 	int compat_clamp = 1;
 	int score_path = -1;        // 0: fp32 FMA kernel, 1: tcgen05 3xTF32 kernel; -1: default (tensor-core route unless SRB200_SCORE_TC=0)
 	int last_score_route = -1;  // route the most recent scoring launch took (0 / 1)
+	int em_path = -1;           // -1 auto, 0 FMA kernels only, 1 tensor cores wherever the shape allows (tests)
+	int last_em_route = -1;     // route the most recent E-step took (0 = FMA kernels, 1 = tensor cores)
 	long long score_launches = 0;   // scoring launches so far (tests: "one launch for all speakers and the UBM")
 	// workspaces for host entry points (guarded by mu)
 	DevBuf d_x, d_out, d_tiles, d_partial, d_sums, d_misc, d_pcm, d_ceps, d_feat, d_stats, d_frame;

@@ -166,7 +166,7 @@ SRB_HD void dft16(const cpx *v, cpx *o) {
 //   P        power spectrum, bins 0..1024, bin k at k + 4 (k >> 4): every run of 16 bins is skewed by 16 bytes, so that the
 //            128-bit reads of the mel stage (lanes on segments that start 16 bins apart) spread over the banks
 constexpr int WF_TILE = 256;
-constexpr int WF_PLEN = 1284;           // floats: 1024 + 4 * 64 + 1, rounded up to a multiple of 4
+constexpr int WF_PLEN = 1296;           // floats: skewed bins 0..1024 (1024 + 4 * 64 + 1) plus the 16-bin reach of a mel segment that starts on the last 4-bin group
 SRB_HD int wf_t_index(int row, int col) { return row * 16 + (col ^ row); }
 SRB_HD int wf_z_index(int r, int q) { return r * WF_TILE + (q ^ (4 * r)); }
 SRB_HD int wf_p_index(int k) { return k + 4 * (k >> 4); }

@@ -318,13 +318,13 @@ __global__ void em_reduce_kernel(const double *__restrict__ partials, int n_slot
 
 __global__ void em_tail_kernel(const double *__restrict__ ll_sum, const float *__restrict__ lse2, int n, int clamp,
                                double *__restrict__ stats, int K, int D) {
-	// stats tail: [sum log p] [frames used]; one block, deterministic tree
-	__shared__ double sh[256];
-	double cnt = 0.0;
-	for (int i = threadIdx.x; i < n; i += blockDim.x) {
+	// stats tail: [sum log p] [frames used].  The count is a sum of small integers: exact (and so order-independent) in float64.
+	__shared__ int sh[256];
+	int cnt = 0;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const float l2 = lse2[i];
 		const bool dead = clamp && !(l2 * LN2F_EM >= DENORM_LOG_MIN_EM);
-		cnt += dead ? 0.0 : 1.0;
+		cnt += dead ? 0 : 1;
 	}
 	sh[threadIdx.x] = cnt;
 	__syncthreads();
@@ -333,9 +333,18 @@ __global__ void em_tail_kernel(const double *__restrict__ ll_sum, const float *_
 		__syncthreads();
 	}
 	if (threadIdx.x == 0) {
-		stats[K + 2 * (size_t)K * D] = ll_sum[0];
-		stats[K + 2 * (size_t)K * D + 1] = sh[0];
+		if (gridDim.x == 1) stats[K + 2 * (size_t)K * D + 1] = (double)sh[0];
+		else atomicAdd(&stats[K + 2 * (size_t)K * D + 1], (double)sh[0]);      // zeroed by the launcher
+		if (blockIdx.x == 0) stats[K + 2 * (size_t)K * D] = ll_sum[0];
 	}
+}
+
+int launch_em_tail(const double *d_ll_sum, const float *d_lse2, int n, int clamp, double *d_stats, int K, int D, cudaStream_t st) {
+	const int blocks = n <= 32768 ? 1 : std::min(ctx().sm_count * 4, ceil_div(n, 2048));      // short utterances (batched enrolment): one block, no memset
+	if (blocks > 1) SRB_CUDA(cudaMemsetAsync(d_stats + K + 2 * (size_t)K * D + 1, 0, sizeof(double), st));
+	em_tail_kernel<<<blocks, 256, 0, st>>>(d_ll_sum, d_lse2, n, clamp, d_stats, K, D);
+	SRB_CUDA(cudaGetLastError());
+	return 0;
 }
 
 // ---- M-step (float64), one thread per (k, d); params = w[K] | mean[K*D] | sigma[K*D] ----
@@ -493,9 +502,7 @@ int launch_estep_accumulate(const PackedModels &pm, const float *dX, int n, int 
 		em_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(g_em_partials.as<double>(), n_slots, n_ktiles, K, D, dp, d_stats);
 		SRB_CUDA(cudaGetLastError());
 	}
-	em_tail_kernel<<<1, 256, 0, st>>>(d_ll_sum, d_lse2, n, clamp, d_stats, K, D);
-	SRB_CUDA(cudaGetLastError());
-	return 0;
+	return launch_em_tail(d_ll_sum, d_lse2, n, clamp, d_stats, K, D, st);
 }
 
 int launch_mstep(double *d_params, const double *d_ubm_params, int K, int D, const double *d_stats, long long n_total,

@@ -307,14 +307,33 @@ __global__ void score_reduce_kernel(const double *__restrict__ partial, const in
 	__shared__ int si[256];
 	double bestv = -1.0e300;
 	int besti = 0x7fffffff;
-	for (int s = threadIdx.x; s < S; s += blockDim.x) {
+	// tps threads per speaker (a power of two) split the utterance's tiles and are tree-summed: a long utterance scored against
+	// few models (the E-step's pass A: one model, thousands of tiles) is not one thread's serial sum
+	int tps = 1;
+	while (tps * 2 * S <= (int)blockDim.x) tps *= 2;
+	const int spk_per_pass = blockDim.x / tps, j = threadIdx.x % tps, sl = threadIdx.x / tps;
+	for (int s0 = 0; s0 < S; s0 += spk_per_pass) {
+		const int s = s0 + sl;
 		double acc = 0.0;
-		for (int t = t0; t < t1; ++t)
-			for (int w = 0; w < parts; ++w) acc += partial[((size_t)t * S + s) * parts + w];
-		sums[(size_t)u * S + s] = acc;
-		if (s < S_arg && acc > bestv) {   // strict: keeps the first maximum within a thread's ascending s sequence
-			bestv = acc;
-			besti = s;
+		if (s < S)
+			for (int t = t0 + j; t < t1; t += tps)
+				for (int w = 0; w < parts; ++w) acc += partial[((size_t)t * S + s) * parts + w];
+		if (tps > 1) {
+			sv[threadIdx.x] = acc;
+			__syncthreads();
+			for (int w = tps / 2; w > 0; w >>= 1) {
+				if (j < w) sv[threadIdx.x] += sv[threadIdx.x + w];
+				__syncthreads();
+			}
+			acc = sv[threadIdx.x];
+			__syncthreads();
+		}
+		if (j == 0 && s < S) {
+			sums[(size_t)u * S + s] = acc;
+			if (s < S_arg && acc > bestv) {   // strict: keeps the first maximum within a thread's ascending s sequence
+				bestv = acc;
+				besti = s;
+			}
 		}
 	}
 	if (best == nullptr) return;
@@ -465,6 +484,19 @@ static bool g_score_attr_set = false;
 static bool g_score_scalar = false;
 static int g_score_warps = 4;
 static bool g_score_stagger = false;   // measured: no effect (fair-share scheduling pulls co-resident warps back into lockstep)
+
+int launch_score_tc_images(const Tc2Images &im, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums, float *d_frame_ll,
+                           int ldf, int *d_best, int clamp, int frame_log2, cudaStream_t st) {
+	Context &c = ctx();
+	c.last_score_route = 1;
+	++c.score_launches;
+	TileTable *tt = nullptr;
+	if (get_table(utt_off, n_utt, im.S, 128, st, &tt)) return 1;
+	if (launch_score_tc2_images(im, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;
+	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, im.S, im.S, 4, d_sums, d_best);
+	SRB_CUDA(cudaGetLastError());
+	return 0;
+}
 
 int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums,
                  float *d_frame_ll, int ldf, int *d_best, int clamp, int frame_log2, cudaStream_t st) {

@@ -40,6 +40,21 @@ int launch_score_tc2(PackedModels &pm, const float *dX, int ld, int D, const int
 		}
 		SRB_CUDA(cudaStreamSynchronize(st));
 	}
+	Tc2Images im;
+	im.B = pm.d_tc2;
+	im.hard = reinterpret_cast<const int4 *>(pm.d_tc_hard);
+	im.cs = pm.d_tc_cs;
+	im.Kp = Kp;
+	im.S = pm.S;
+	im.cols_per_spk = pm.tc_cols_per_spk;
+	im.blocks_total = pm.tc_blocks_total;
+	return launch_score_tc2_images(im, dX, ld, D, d_ftiles, n_ftiles, d_partial, d_frame_ll, ldf, clamp, frame_log2, st);
+}
+
+int launch_score_tc2_images(const Tc2Images &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, double *d_partial,
+                            float *d_frame_ll, int ldf, int clamp, int frame_log2, cudaStream_t st) {
+	Context &c = ctx();
+	const int Kp = pm.Kp;
 	if (!g_tc2_attr) {
 		SRB_CUDA(cudaFuncSetAttribute(gmm_score_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		SRB_CUDA(cudaFuncSetAttribute(gmm_score_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -51,22 +66,22 @@ int launch_score_tc2(PackedModels &pm, const float *dX, int ld, int D, const int
 	Tc2Args a;
 	a.X = dX;
 	a.ld = ld;
-	a.cs = pm.d_tc_cs;
-	a.B = reinterpret_cast<const __half *>(pm.d_tc2);
+	a.cs = pm.cs;
+	a.B = reinterpret_cast<const __half *>(pm.B);
 	a.ftiles = d_ftiles;
 	a.n_ftiles = n_ftiles;
 	a.Kp = Kp;
 	a.S = pm.S;
-	a.seg = pm.tc_cols_per_spk;
-	a.blocks_per_spk = pm.tc_cols_per_spk >= TC_NB ? pm.tc_cols_per_spk / TC_NB : 1;
-	a.n_blocks_total = pm.tc_blocks_total;
+	a.seg = pm.cols_per_spk;
+	a.blocks_per_spk = pm.cols_per_spk >= TC_NB ? pm.cols_per_spk / TC_NB : 1;
+	a.n_blocks_total = pm.blocks_total;
 	// a work unit is a PAIR of frame tiles x a chunk of speakers; one chunk when the pairs alone fill the CTA pairs of the chip
 	const int n_pairs = (n_ftiles + 1) / 2, n_clusters_max = std::max(1, c.sm_count / 2);
 	int n_chunks = 1;
 	if (n_pairs < n_clusters_max) n_chunks = std::min(pm.S, ceil_div(n_clusters_max, n_pairs));
 	int spc = ceil_div(pm.S, n_chunks);
-	if (pm.tc_cols_per_spk < TC_NB) {                        // small speakers: chunks start on block boundaries
-		const int per_block = TC_NB / pm.tc_cols_per_spk;
+	if (pm.cols_per_spk < TC_NB) {                        // small speakers: chunks start on block boundaries
+		const int per_block = TC_NB / pm.cols_per_spk;
 		spc = ceil_div(spc, per_block) * per_block;
 	}
 	n_chunks = ceil_div(pm.S, spc);
@@ -79,7 +94,7 @@ int launch_score_tc2(PackedModels &pm, const float *dX, int ld, int D, const int
 	a.frame_log2 = frame_log2;
 	a.D = D;
 	a.bstages = tc2_stages(Kp, D);
-	a.hard = reinterpret_cast<const int4 *>(pm.d_tc_hard);
+	a.hard = pm.hard;
 	const long long units = (long long)n_pairs * n_chunks;
 	const int grid = 2 * (int)std::min<long long>(units, n_clusters_max);      // cluster dims (2,1,1) are compiled into the kernel
 	const size_t smem = tc2_smem_bytes_n(Kp, D, a.bstages);

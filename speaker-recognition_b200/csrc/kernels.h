@@ -15,6 +15,18 @@ void score_tables_release();
 bool tc2_supported(const PackedModels &pm, int D);
 int launch_score_tc2(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, double *d_partial, float *d_frame_ll,
                      int ldf, int clamp, int frame_log2, cudaStream_t st);
+// the same kernel on operand images that already live on the device (built there by gmm_em_tc.cu from a float64 master)
+struct Tc2Images {
+	const void *B;             // [blocks_total][2 ranks][head | tail][64 * Kp] fp16
+	const int4 *hard;          // [blocks_total][TC_HSTRIDE]
+	const float *cs;           // [2][D]
+	int Kp, S, cols_per_spk, blocks_total;
+};
+int launch_score_tc2_images(const Tc2Images &im, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, double *d_partial,
+                            float *d_frame_ll, int ldf, int clamp, int frame_log2, cudaStream_t st);
+// frame tiles + launch + per-utterance reduction (gmm_score.cu)
+int launch_score_tc_images(const Tc2Images &im, const float *dX, int ld, int D, const int *utt_off, int n_utt, double *d_sums, float *d_frame_ll,
+                           int ldf, int *d_best, int clamp, int frame_log2, cudaStream_t st);
 
 // ---- gmm_em.cu ----
 // stats (float64): [K] N_k | [K*D] sum g x | [K*D] sum g x^2 | [1] sum log p | [1] frames used
@@ -26,6 +38,15 @@ int launch_estep_accumulate(const PackedModels &pm, const float *dX, int n, int 
 int launch_mstep(double *d_params, const double *d_ubm_params, int K, int D, const double *d_stats, long long n_total,
                  double min_covar, int mode, cudaStream_t st);
 int launch_pack_from_master(const double *d_params, int K, int D, PackedModels &pm, cudaStream_t st);
+int launch_em_tail(const double *d_ll_sum, const float *d_lse2, int n, int clamp, double *d_stats, int K, int D, cudaStream_t st);
+
+// ---- gmm_em_tc.cu: the E-step of large models on the tensor cores ----
+bool em_tc_eligible(int K, int D, int n);
+// *used = 1: d_stats holds the E-step's statistics; 0: these parameters are not safe for the uncorrected expanded form, nothing written
+int launch_estep_tc(PackedModels &pm, const double *d_params, const float *dX, int n, int ld, int D, int K, float *d_lse2, double *d_ll_sum,
+                    double *d_stats, int clamp, cudaStream_t st, int *used);
+struct EmTc;
+void emtc_release(EmTc *e);
 void em_release();
 
 // ---- mfcc.cu ----
