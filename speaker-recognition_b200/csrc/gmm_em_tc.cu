@@ -224,7 +224,7 @@ __device__ __forceinline__ void split_pack(float v0, float v1, uint32_t &hi, uin
 // shared memory: W image (head | tail) + nY Y tiles (head | tail, MN-major) + gamma tile (head | tail, MN-major) + raw frame tile
 // [128][ld] (+32 bytes: the last chunk of the last row may read up to two 16-byte units past it) + lse2[2][128] + barriers / TMEM slot
 static size_t et_smem_bytes(int Kp, int ld, int nY) {
-	return (size_t)2 * TC_NB * Kp * 2 + (size_t)nY * 2 * TC_M * Kp * 2 + (size_t)2 * TC_M * TC_NB * 2 + ((size_t)TC_M * ld * 4 + 32) + 2 * TC_M * 4 + 256;
+	return (size_t)2 * TC_NB * Kp * 2 + (size_t)nY * 2 * TC_M * Kp * 2 + (size_t)2 * TC_M * TC_NB * 2 + ((size_t)TC_M * ld * 4 + 32) + 2 * TC_M * 4 + (size_t)Kp * 4 + 256;
 }
 // Y double-buffered where it fits: the next tile's PHI / Y are then built while GEMM 2 of the current tile runs
 static int et_ybufs(int Kp, int ld) {
@@ -235,21 +235,28 @@ static int et_ybufs(int Kp, int ld) {
 
 // Column order of PHI / W / Y inside this file (any order works as long as the operands agree): k = 2 d -> x''_d^2, k = 2 d + 1 -> x''_d,
 // k = 2 D -> 1, rest 0 -- so that four dimensions (one 16-byte read of the frame row) make one 16-byte piece of the operand row.
+template <int NCH>      // Kp / 16
 __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const EtArgs A) {
 	extern __shared__ __align__(1024) unsigned char et_smem[];
-	const int Kp = A.Kp, D = A.D, ld = A.ld, nY = A.nY;
+	constexpr int Kp = NCH * 16;
+	const int D = A.D, ld = A.ld, nY = A.nY;
 	const uint32_t w_part = (uint32_t)TC_NB * Kp * 2, y_part = (uint32_t)TC_M * Kp * 2, g_part = (uint32_t)TC_M * TC_NB * 2;      // bytes of one image part
 	unsigned char *sW = et_smem;                         // [head | tail] 128 rows x Kp, K-major canonical (as stored in HBM)
 	unsigned char *sY = sW + 2 * w_part;                 // nY x [head | tail] Y[frame][col], MN-major canonical: (f >> 3) * (Kp / 8) * 128 + (c >> 3) * 128 + (f & 7) * 16 + (c & 7) * 2
 	unsigned char *sG = sY + (size_t)nY * 2 * y_part;    // [head | tail] gamma[frame][mixture], MN-major canonical: (f >> 3) * 2048 + (m >> 3) * 128 + (f & 7) * 16 + (m & 7) * 2
 	float *sX = reinterpret_cast<float *>(sG + 2 * g_part);        // [128][ld] the tile's frames as they lie in HBM (one bulk copy)
 	float *sL = sX + (size_t)TC_M * ld + 8;              // [2][128] lse2 of the tile's frames (+inf: the frame contributes nothing), by tile parity
-	uint64_t *bars = reinterpret_cast<uint64_t *>(sL + 2 * TC_M);
+	float *sC = sL + 2 * TC_M;                           // [2][Kp / 2] centre, scale per dimension (zero-padded)
+	uint64_t *bars = reinterpret_cast<uint64_t *>(sC + Kp);
 	uint64_t *bar_w = bars, *bar_a = bars + 1, *bar_g1 = bars + 2, *bar_g = bars + 3, *bar_g2 = bars + 4, *bar_x = bars + 5;
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int mb = blockIdx.x, split = blockIdx.y;
+	for (int i = tid; i < Kp; i += ET_THREADS) {
+		const int d = i % (Kp / 2);
+		sC[i] = d < D ? A.cs[(i / (Kp / 2)) * D + d] : 0.f;
+	}
 	if (tid == 0) {
 		mbar_init(bar_w, 1);
 		mbar_init(bar_a, 8);
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const E
 		const uint32_t dG_hi = (uint32_t)(128 >> 4) | (1u << 14), dY_hi = dG_hi;
 		const uint32_t dG0 = ((smem_u32(sG) >> 4) & 0x3FFF) | ((kg_G >> 4) << 16);
 		const uint32_t stepG = (2 * kg_G) >> 4, stepY = (2 * kg_Y) >> 4;
-		const int ks1 = Kp / 16;
+		constexpr int ks1 = NCH;
 		const uint32_t a_hi = tmem_base + ET_A_COL, a_lo = a_hi + (uint32_t)(Kp >> 1);
 		et::wait(bar_w, 0);
 		uint32_t it = 0;
@@ -312,6 +319,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const E
 			{
 				const uint32_t d1 = tmem_base + ET_L_COL;
 				et::mma_ts<0>(d1, a_hi, dW0, dW_hi, idesc1);
+#pragma unroll
 				for (int k = 1; k < ks1; ++k) et::mma_ts<1>(d1, a_hi + 8 * k, dW0 + stepW * k, dW_hi, idesc1);
 				for (int k = 0; k < ks1; ++k) et::mma_ts<1>(d1, a_lo + 8 * k, dW0 + stepW * k, dW_hi, idesc1);
 				for (int k = 0; k < ks1; ++k) et::mma_ts<1>(d1, a_hi + 8 * k, dW0 + (w_part >> 4) + stepW * k, dW_hi, idesc1);
@@ -337,21 +345,22 @@ __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const E
 		const int q = warp & 3, half = (warp - 1) >> 2;
 		const int row = q * 32 + lane;
 		const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-		const float *cen = A.cs, *alp = A.cs + D;
-		const int nch = Kp >> 4;
-		bool first_flush = true;
-		auto flush = [&]() {
-			// ACC lanes are MIXTURES: this thread owns mixture `row` of the block and its half of the Kp columns
-			const int c0 = half * (Kp >> 1), c1 = c0 + (Kp >> 1);
-			for (int c = c0; c < c1; c += 8) {
-				uint32_t r[8];
-				et::ld8(lane_base + ET_ACC_COL + c, r);
-				et::ld_wait();
-				double *p = my_part + (size_t)row * Kp + c;
+		const float4 *cen4 = reinterpret_cast<const float4 *>(sC), *alp4 = reinterpret_cast<const float4 *>(sC + Kp / 2);
+		constexpr int nch = NCH;
+		// float64 running sums of this thread's part of the statistics: mixture `row` of the block, its half of the Kp columns.  The
+		// tensor-memory accumulator is fp32 and is folded in here every ET_FLUSH_TILES tiles (1024 frames)
+		double acc64[Kp / 2];
 #pragma unroll
-				for (int j = 0; j < 8; ++j) p[j] = first_flush ? (double)__uint_as_float(r[j]) : p[j] + (double)__uint_as_float(r[j]);
+		for (int j = 0; j < Kp / 2; ++j) acc64[j] = 0.0;
+		auto flush = [&]() {
+#pragma unroll
+			for (int c = 0; c < Kp / 2; c += 8) {
+				uint32_t r[8];
+				et::ld8(lane_base + ET_ACC_COL + half * (Kp / 2) + c, r);
+				et::ld_wait();
+#pragma unroll
+				for (int j = 0; j < 8; ++j) acc64[c + j] += (double)__uint_as_float(r[j]);
 			}
-			first_flush = false;
 		};
 		// PHI (tensor memory) and Y (shared memory) of this thread's frame; the two warps of a lane quarter split the 16-value chunks
 		auto build = [&](int t, uint32_t itb) {
@@ -360,18 +369,20 @@ __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const E
 			const bool valid = fr < A.n;
 			const float4 *xr = reinterpret_cast<const float4 *>(sX + (size_t)row * ld);
 			unsigned char *ybuf = sY + (size_t)(itb % nY) * 2 * y_part;
+#pragma unroll
 			for (int c = half; c < nch; c += 2) {
 				uint32_t hi[8], lo[8];
 #pragma unroll
 				for (int u = 0; u < 2; ++u) {
 					const float4 xv = valid ? xr[2 * c + u] : make_float4(0.f, 0.f, 0.f, 0.f);
-					const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+					const float4 cv = cen4[2 * c + u], av = alp4[2 * c + u];
+					const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, cs4[4] = {cv.x, cv.y, cv.z, cv.w}, as4[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
 					for (int j = 0; j < 4; ++j) {
 						const int d = 8 * c + 4 * u + j;
 						float v0 = 0.f, v1 = 0.f;                  // (x''^2, x'') | (1, 0) at d == D | (0, 0) beyond
 						if (d < D) {
-							v1 = fminf(fmaxf((xs[j] - cen[d]) * alp[d], -T2_X_CLAMP), T2_X_CLAMP);
+							v1 = fminf(fmaxf((xs[j] - cs4[j]) * as4[j], -T2_X_CLAMP), T2_X_CLAMP);
 							v0 = v1 * v1;
 						} else if (d == D) {
 							v0 = 1.f;
@@ -448,11 +459,10 @@ __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const E
 			et::wait(bar_g2, (it - 1) & 1);
 			et::fence_after();
 			flush();
-		} else {
-			// no tiles in this split: its partial slot is all zeros
-			const int c0 = half * (Kp >> 1);
-			for (int c = c0; c < c0 + (Kp >> 1); ++c) my_part[(size_t)row * Kp + c] = 0.0;
 		}
+		double *p = my_part + (size_t)row * Kp + half * (Kp / 2);
+#pragma unroll
+		for (int j = 0; j < Kp / 2; ++j) p[j] = acc64[j];
 	}
 	et::fence_before();
 	__syncthreads();
@@ -553,7 +563,13 @@ int launch_estep_tc(PackedModels &pm, const double *d_params, const float *dX, i
 	if (launch_score_tc_images(im, dX, ld, D, utt_off, 1, d_ll_sum, d_lse2, n, nullptr, clamp, 1, st)) return 1;
 	// ---- pass B ----
 	if (!g_et_attr) {
-		SRB_CUDA(cudaFuncSetAttribute(em_accumulate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(em_accumulate_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(em_accumulate_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(em_accumulate_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(em_accumulate_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(em_accumulate_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(em_accumulate_tc_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		SRB_CUDA(cudaFuncSetAttribute(em_accumulate_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		g_et_attr = true;
 	}
 	EtArgs a;
@@ -570,7 +586,18 @@ int launch_estep_tc(PackedModels &pm, const double *d_params, const float *dX, i
 	a.n_split = n_split;
 	a.clamp = clamp;
 	a.nY = nY;
-	em_accumulate_tc_kernel<<<dim3(blocks, n_split), ET_THREADS, et_smem_bytes(Kp, ld, nY), st>>>(a);
+	const dim3 grid(blocks, n_split);
+	const size_t smem = et_smem_bytes(Kp, ld, nY);
+	switch (Kp / 16) {
+		case 2: em_accumulate_tc_kernel<2><<<grid, ET_THREADS, smem, st>>>(a); break;
+		case 3: em_accumulate_tc_kernel<3><<<grid, ET_THREADS, smem, st>>>(a); break;
+		case 4: em_accumulate_tc_kernel<4><<<grid, ET_THREADS, smem, st>>>(a); break;
+		case 5: em_accumulate_tc_kernel<5><<<grid, ET_THREADS, smem, st>>>(a); break;
+		case 6: em_accumulate_tc_kernel<6><<<grid, ET_THREADS, smem, st>>>(a); break;
+		case 7: em_accumulate_tc_kernel<7><<<grid, ET_THREADS, smem, st>>>(a); break;
+		case 8: em_accumulate_tc_kernel<8><<<grid, ET_THREADS, smem, st>>>(a); break;
+		default: return 0;      // Kp = 16 (D <= 7): FMA kernels
+	}
 	SRB_CUDA(cudaGetLastError());
 	em_tc_reduce_kernel<<<ceil_div(K * (D + 1), 256), 256, 0, st>>>(e->d_partials, n_split, blocks, Kp, K, D, e->d_cs, d_stats);
 	SRB_CUDA(cudaGetLastError());
