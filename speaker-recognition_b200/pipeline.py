@@ -86,8 +86,10 @@ class BatchScorer(object):
         # sub-batches for the end-to-end path: H2D of chunk c+1 overlaps the kernels of chunk c
         self.chunks = []
         # a small first sub-batch starts the kernels early (its copy is the only one nothing overlaps), later ones grow so the
-        # persistent scorer's waves stay full (measured at C2 x 64: equal quarters 13.66 ms, this schedule 12.69 ms per step); SRB200_E2E_CHUNKS="f1,f2,..." (cumulative fractions) overrides
-        fr = [1 / 32, 1 / 8, 5 / 16, 5 / 8, 1.0] if B >= 32 else ([0.25, 0.5, 0.75, 1.0] if B >= 8 else [1.0])
+        # persistent scorer's waves stay full, and the LAST one is small again: its kernels are the only ones no copy overlaps.  Measured
+        # at C2 x 64 (profiles/r2_e2e_sweep.txt): five growing chunks 8.38 ms, this schedule 7.61 ms, ten chunks 7.9-8.1 ms per step (the
+        # copy alone takes 6 ms).  SRB200_E2E_CHUNKS="f1,f2,..." (cumulative fractions) overrides
+        fr = [1 / 32, 1 / 8, 0.25, 0.4, 0.55, 0.7, 0.85, 1.0] if B >= 32 else ([0.25, 0.5, 0.75, 1.0] if B >= 8 else [1.0])
         env = os.environ.get("SRB200_E2E_CHUNKS")
         if env:
             fr = [float(x) for x in env.split(",")]
