@@ -104,8 +104,6 @@ void PackedModels::release() {
 	if (d_tiles) cudaFree(d_tiles);
 	d_tiles = nullptr;
 	release_tc();
-	emtc_release(emtc);
-	emtc = nullptr;
 	bytes = 0;
 	S = 0;
 }

@@ -433,7 +433,10 @@ static DevBuf g_em_partials;
 static bool g_em_attr_set = false;
 static int g_em_variant = 2;   // default: FFMA2 in phase 1, scalar FFMA in phase 2 (measured fastest: 7.86 vs 8.07 / 8.64 / 8.66 ms at C3)
 
-void em_release() { g_em_partials.release(); }
+void em_release() {
+	g_em_partials.release();
+	em_tc_release();
+}
 
 static size_t em_smem_bytes(int D) {
 	const int xrows = ((D + EM_DP - 1) / EM_DP) * EM_DP;

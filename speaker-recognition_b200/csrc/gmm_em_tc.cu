@@ -26,26 +26,28 @@ constexpr int ET_THREADS = 288;             // warp 0: loads + MMA issue; warps 
 constexpr int ET_FLUSH_TILES = 8;           // tiles (of 128 frames) between float64 flushes of the accumulator
 constexpr int ET_L_COL = 0, ET_ACC_COL = 128, ET_A_COL = 256;      // TMEM columns: GEMM-1 accumulator | GEMM-2 accumulator (Kp) | PHI head, tail (Kp)
 
-struct EmTc {                               // device-side operand images of ONE model, rebuilt from the float64 master every iteration
-	int K = 0, D = 0, Kp = 0, blocks = 0;
-	float *d_cs = nullptr;                  // [2][D] centre, scale
-	__half *d_img2 = nullptr;               // scorer layout: [blocks][2 ranks][head | tail][64 * Kp]
-	__half *d_img128 = nullptr;             // this file's GEMM 1: [blocks][head | tail][128 * Kp], 128-row K-major canonical layout
-	int4 *d_hard = nullptr;                 // [blocks][TC_HSTRIDE]: headers only (valid-column masks), no entries
-	int *d_flag = nullptr;                  // != 0: do not use the tensor route for these parameters
-	double *d_partials = nullptr;           // [n_split][blocks][128][Kp]
-	size_t partials_cap = 0;
+// Workspace of the route: operand images of the model being trained (rebuilt from its float64 master every iteration) and the
+// float64 partials.  One per process, grow-only (DevBuf), shared by every model that trains: an E-step call builds, uses and is
+// done with it before it returns to its caller's stream order, and the C ABI is synchronous per context.
+struct EmTcWorkspace {
+	DevBuf cs;                              // [2][D] centre, scale
+	DevBuf img2;                            // scorer layout: [blocks][2 ranks][head | tail][64 * Kp]
+	DevBuf img128;                          // this file's GEMM 1: [blocks][head | tail][128 * Kp], 128-row K-major canonical layout
+	DevBuf hard;                            // [blocks][TC_HSTRIDE]: headers only (valid-column masks), no entries
+	DevBuf flag;                            // != 0: do not use the tensor route for these parameters
+	DevBuf partials;                        // [n_split][blocks][128][Kp] float64
+	PinBuf h_flag;
 };
+static EmTcWorkspace g_ws;
 
-void emtc_release(EmTc *e) {
-	if (!e) return;
-	cudaFree(e->d_cs);
-	cudaFree(e->d_img2);
-	cudaFree(e->d_img128);
-	cudaFree(e->d_hard);
-	cudaFree(e->d_flag);
-	cudaFree(e->d_partials);
-	delete e;
+void em_tc_release() {
+	g_ws.cs.release();
+	g_ws.img2.release();
+	g_ws.img128.release();
+	g_ws.hard.release();
+	g_ws.flag.release();
+	g_ws.partials.release();
+	g_ws.h_flag.release();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -519,42 +521,33 @@ int launch_estep_tc(PackedModels &pm, const double *d_params, const float *dX, i
 	const int Kp = t2_kp(D), blocks = ceil_div(K, TC_NB);
 	const int nY = et_ybufs(Kp, ld);
 	if (nY == 0 || (ld & 3) != 0 || (reinterpret_cast<uintptr_t>(dX) & 15) != 0) return 0;      // the frame tile is one 16-byte-granular bulk copy
-	if (pm.emtc == nullptr) pm.emtc = new EmTc();
-	EmTc *e = pm.emtc;
-	if (e->K != K || e->D != D) {
-		SRB_CUDA(cudaStreamSynchronize(st));
-		cudaFree(e->d_cs), cudaFree(e->d_img2), cudaFree(e->d_img128), cudaFree(e->d_hard), cudaFree(e->d_flag);
-		e->d_cs = nullptr, e->d_img2 = nullptr, e->d_img128 = nullptr, e->d_hard = nullptr, e->d_flag = nullptr;
-		SRB_CUDA(cudaMalloc(&e->d_cs, (size_t)2 * D * sizeof(float)));
-		SRB_CUDA(cudaMalloc(&e->d_img2, (size_t)blocks * t2_block_halfs(Kp) * sizeof(__half)));
-		SRB_CUDA(cudaMalloc(&e->d_img128, (size_t)blocks * 2 * TC_NB * Kp * sizeof(__half)));
-		SRB_CUDA(cudaMalloc(&e->d_hard, (size_t)blocks * TC_HSTRIDE * sizeof(int4)));
-		SRB_CUDA(cudaMalloc(&e->d_flag, sizeof(int)));
-		e->K = K, e->D = D, e->Kp = Kp, e->blocks = blocks;
-	}
+	(void)pm;
 	const int n_split = std::max(1, c.sm_count / blocks);
-	const size_t pbytes = (size_t)n_split * blocks * TC_NB * Kp * sizeof(double);
-	if (pbytes > e->partials_cap) {
-		SRB_CUDA(cudaStreamSynchronize(st));
-		cudaFree(e->d_partials);
-		e->d_partials = nullptr;
-		SRB_CUDA(cudaMalloc(&e->d_partials, pbytes));
-		e->partials_cap = pbytes;
-	}
+	EmTcWorkspace &w = g_ws;                                   // ensure() is a no-op once the buffers are large enough
+	if (w.cs.ensure((size_t)2 * D * sizeof(float)) || w.img2.ensure((size_t)blocks * t2_block_halfs(Kp) * sizeof(__half)) ||
+	    w.img128.ensure((size_t)blocks * 2 * TC_NB * Kp * sizeof(__half)) || w.hard.ensure((size_t)blocks * TC_HSTRIDE * sizeof(int4)) ||
+	    w.flag.ensure(sizeof(int)) || w.partials.ensure((size_t)n_split * blocks * TC_NB * Kp * sizeof(double)) || w.h_flag.ensure(sizeof(int)))
+		return 1;
+	float *d_cs = w.cs.as<float>();
+	__half *d_img2 = w.img2.as<__half>(), *d_img128 = w.img128.as<__half>();
+	int4 *d_hard = w.hard.as<int4>();
+	int *d_flag = w.flag.as<int>();
+	double *d_partials = w.partials.as<double>();
 	// ---- operand images from the master ----
-	SRB_CUDA(cudaMemsetAsync(e->d_hard, 0, (size_t)blocks * TC_HSTRIDE * sizeof(int4), st));
-	em_tc_cs_kernel<<<D, 128, 0, st>>>(d_params, K, D, e->d_cs, e->d_flag);
-	em_tc_pack_kernel<<<ceil_div(blocks * TC_NB * 32, 256), 256, 0, st>>>(d_params, K, D, Kp, blocks, e->d_cs, e->d_img2, e->d_img128, e->d_hard, e->d_flag);
+	SRB_CUDA(cudaMemsetAsync(d_hard, 0, (size_t)blocks * TC_HSTRIDE * sizeof(int4), st));
+	em_tc_cs_kernel<<<D, 128, 0, st>>>(d_params, K, D, d_cs, d_flag);
+	em_tc_pack_kernel<<<ceil_div(blocks * TC_NB * 32, 256), 256, 0, st>>>(d_params, K, D, Kp, blocks, d_cs, d_img2, d_img128, d_hard, d_flag);
 	SRB_CUDA(cudaGetLastError());
-	int flag = 1;
-	SRB_CUDA(cudaMemcpyAsync(&flag, e->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+	int *h_flag = w.h_flag.as<int>();
+	*h_flag = 1;
+	SRB_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
 	SRB_CUDA(cudaStreamSynchronize(st));
-	if (flag != 0) return 0;
+	if (*h_flag != 0) return 0;
 	// ---- pass A: the tcgen05 scorer on the device-built images: per-frame log2 p(x) (unclamped) + the total log-likelihood ----
 	Tc2Images im;
-	im.B = e->d_img2;
-	im.hard = e->d_hard;
-	im.cs = e->d_cs;
+	im.B = d_img2;
+	im.hard = d_hard;
+	im.cs = d_cs;
 	im.Kp = Kp;
 	im.S = 1;
 	im.cols_per_spk = blocks * TC_NB;
@@ -578,10 +571,10 @@ int launch_estep_tc(PackedModels &pm, const double *d_params, const float *dX, i
 	a.D = D;
 	a.n = n;
 	a.Kp = Kp;
-	a.cs = e->d_cs;
-	a.img128 = e->d_img128;
+	a.cs = d_cs;
+	a.img128 = d_img128;
 	a.lse2 = d_lse2;
-	a.partials = e->d_partials;
+	a.partials = d_partials;
 	a.blocks = blocks;
 	a.n_split = n_split;
 	a.clamp = clamp;
@@ -599,7 +592,7 @@ int launch_estep_tc(PackedModels &pm, const double *d_params, const float *dX, i
 		default: return 0;      // Kp = 16 (D <= 7): FMA kernels
 	}
 	SRB_CUDA(cudaGetLastError());
-	em_tc_reduce_kernel<<<ceil_div(K * (D + 1), 256), 256, 0, st>>>(e->d_partials, n_split, blocks, Kp, K, D, e->d_cs, d_stats);
+	em_tc_reduce_kernel<<<ceil_div(K * (D + 1), 256), 256, 0, st>>>(d_partials, n_split, blocks, Kp, K, D, d_cs, d_stats);
 	SRB_CUDA(cudaGetLastError());
 	if (launch_em_tail(d_ll_sum, d_lse2, n, clamp, d_stats, K, D, st)) return 1;
 	*used = 1;

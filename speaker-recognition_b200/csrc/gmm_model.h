@@ -24,8 +24,6 @@ constexpr float PAD_C2 = -1.0e30f;
 
 static inline size_t tile_floats(int D) { return (size_t)64 * D + 32; }
 
-struct EmTc;                      // gmm_em_tc.cu: device-built operand images of the model being trained
-
 struct PackedModels {             // device-resident packed parameters of S models sharing D and Kpad
 	int S = 0, K = 0, Kpad = 0, D = 0, tiles_per_model = 0;
 	int S_arg = 0;                // models that take part in the per-utterance argmax (0 = all): a set may carry its UBM as an extra model
@@ -41,7 +39,6 @@ struct PackedModels {             // device-resident packed parameters of S mode
 	float *d_tc_cs = nullptr;
 	int tc_cols_per_spk = 0, tc_blocks_total = 0;
 	bool tc_built = false;        // the tensor-core images describe the CURRENT parameters (possibly empty: set not supported)
-	EmTc *emtc = nullptr;         // training only: operand images rebuilt on the device every EM iteration
 	void release();
 	void release_tc();            // drop the tensor-core images (host and device); the FMA tiles stay
 };

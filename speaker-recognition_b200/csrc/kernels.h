@@ -45,8 +45,7 @@ bool em_tc_eligible(int K, int D, int n);
 // *used = 1: d_stats holds the E-step's statistics; 0: these parameters are not safe for the uncorrected expanded form, nothing written
 int launch_estep_tc(PackedModels &pm, const double *d_params, const float *dX, int n, int ld, int D, int K, float *d_lse2, double *d_ll_sum,
                     double *d_stats, int clamp, cudaStream_t st, int *used);
-struct EmTc;
-void emtc_release(EmTc *e);
+void em_tc_release();
 void em_release();
 
 // ---- mfcc.cu ----
