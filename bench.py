@@ -523,15 +523,31 @@ def main():
     feat_ms = float(np.mean([a.elapsed_time(b) for a, b in f_ev]))
     labels_dev = bs.d_best.cpu().numpy().copy()
 
-    # ---- end-to-end through the public batched API: pinned host PCM -> labels on host, every step ----
+    # ---- end-to-end through the public batched API: pinned host PCM -> labels on host, every step.  (1) one step at a time
+    # (predict_pcm = submit + result); (2) the same API used as a serving loop uses it: step i+1 is submitted before step i's labels
+    # are collected, so its first H2D copies overlap step i's last kernels (two buffer slots) -- every step still copies its own
+    # input from pinned host memory and reads its own labels back inside the timed region.  (2) is the e2e headline.
     for _ in range(2):
         bs.predict_pcm(host, lengths)
     barrier()
-    w2 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         lab = bs.predict_pcm(host, lengths)
+    e1.record()
+    barrier()
+    e2e_sync_ms = e0.elapsed_time(e1)
+    assert np.array_equal(lab.numpy(), labels_dev)
+    barrier()
+    w2 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pending = bs.submit(host, lengths)
+    for _ in range(args.steps - 1):
+        nxt = bs.submit(host, lengths)
+        lab = bs.result(pending)
+        pending = nxt
+    lab = bs.result(pending)
     e1.record()
     barrier()
     w3 = time.perf_counter()
@@ -541,10 +557,10 @@ def main():
     clocks = sampler.summary([(w0, w1 + 0.06), (w2, w3 + 0.06)])
     assert np.array_equal(lab.numpy(), labels_dev)
 
-    t = torch.tensor([dev_ms, e2e_ms, score_ms, feat_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_ms, score_ms, feat_ms, e2e_sync_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, score_ms, feat_ms = [float(x) for x in t.cpu()]
+    dev_ms, e2e_ms, score_ms, feat_ms, e2e_sync_ms = [float(x) for x in t.cpu()]
     total_frames = frames_per_step * args.steps * world
     value = total_frames / (dev_ms * 1e-3)
     e2e_value = total_frames / (e2e_ms * 1e-3)
@@ -660,7 +676,9 @@ def main():
                 "batch": {"utts_per_step_per_gpu": B, "parallelism": "utterance-sharded x%d" % world},
                 "frame_model_pairs_per_sec": value * S_SPK,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(B * UTT_SAMPLES * 2), "d2h_bytes_per_step": int(B * 4),
-                        "ms_per_step": e2e_ms / args.steps, "api": "pipeline.BatchScorer.predict_pcm"},
+                        "ms_per_step": e2e_ms / args.steps, "api": "pipeline.BatchScorer.submit / result, two steps in flight",
+                        "one_step_at_a_time": {"value": total_frames / (e2e_sync_ms * 1e-3), "ms_per_step": e2e_sync_ms / args.steps,
+                                               "api": "pipeline.BatchScorer.predict_pcm"}},
                 "gpu_launches": BatchScorer.KERNELS_PER_STEP * args.steps,
                 "kernel_ms": {"mfcc_features": feat_ms, "gmm_score": score_ms},
                 "score_route": "tcgen05_3xfp16_cta_pairs" if route == 1 else "fp32_fma",

@@ -67,21 +67,12 @@ class BatchScorer(object):
         cap = getattr(self, "_cap", None)
         if cap is None or self.n_samples > cap["samples"] or self.rows > cap["rows"] or B > cap["B"] or self.S != cap["S"]:
             grow = lambda need, have: max(need + need // 4 + 64, have)
-            cap = dict(samples=grow(self.n_samples, cap["samples"] if cap else 0), rows=grow(self.rows, cap["rows"] if cap else 0),
-                       B=grow(B, cap["B"] if cap else 0), S=self.S)
-            torch.cuda.current_stream().synchronize()
-            self._pcm_buf = torch.empty(cap["samples"], dtype=torch.int16, device=self.device)
-            self._feat_buf = torch.empty((cap["rows"], self.ld), dtype=torch.float32, device=self.device)
-            self._sums_buf = torch.empty((cap["B"], self.S), dtype=torch.float64, device=self.device)
-            self._best_buf = torch.empty(cap["B"], dtype=torch.int32, device=self.device)
-            self._hbest_buf = torch.empty(cap["B"], dtype=torch.int32).pin_memory()
-            self._cap = cap
-        self.d_pcm = self._pcm_buf[:self.n_samples]
-        self.d_feat = self._feat_buf[:self.rows]
-        self.d_sums = self._sums_buf[:B]
-        self.d_best = self._best_buf[:B]
-        self.h_best = self._hbest_buf[:B]
+            self._cap = dict(samples=grow(self.n_samples, cap["samples"] if cap else 0), rows=grow(self.rows, cap["rows"] if cap else 0),
+                             B=grow(B, cap["B"] if cap else 0), S=self.S)
+            torch.cuda.synchronize(self.device)    # nothing in flight may still use the buffers that are about to go
+            self._slots = {}
         self.B = B
+        self._use_slot(0)
         self._shape = key
         # sub-batches for the end-to-end path: H2D of chunk c+1 overlaps the kernels of chunk c
         self.chunks = []
@@ -108,9 +99,32 @@ class BatchScorer(object):
             row0 += rows_c
         if getattr(self, "copy_stream", None) is None:
             self.copy_stream = torch.cuda.Stream(device=self.device)
-            self.copy_events = []
-        while len(self.copy_events) < len(self.chunks):
-            self.copy_events.append(torch.cuda.Event())
+        self._direct_use = True
+
+    def _slot(self, k):
+        """buffers of pipeline slot k at the current capacity (slot 0: the direct API; slots 0/1 alternate in submit())"""
+        torch = self.torch
+        sl = self._slots.get(k)
+        if sl is None:
+            cap = self._cap
+            sl = dict(pcm=torch.empty(cap["samples"], dtype=torch.int16, device=self.device),
+                      feat=torch.empty((cap["rows"], self.ld), dtype=torch.float32, device=self.device),
+                      sums=torch.empty((cap["B"], self.S), dtype=torch.float64, device=self.device),
+                      best=torch.empty(cap["B"], dtype=torch.int32, device=self.device),
+                      hbest=torch.empty(cap["B"], dtype=torch.int32).pin_memory(),
+                      done=torch.cuda.Event(), copied=[], used=False, B=0)
+            self._slots[k] = sl
+        return sl
+
+    def _use_slot(self, k):
+        """point the views the stages work on (d_pcm, d_feat, d_sums, d_best, h_best) at slot k"""
+        sl = self._slot(k)
+        self.d_pcm = sl["pcm"][:self.n_samples]
+        self.d_feat = sl["feat"][:self.rows]
+        self.d_sums = sl["sums"][:self.B]
+        self.d_best = sl["best"][:self.B]
+        self.h_best = sl["hbest"][:self.B]
+        return sl
 
     def _wave_align(self, bounds, lengths):
         """move the sub-batch boundaries by up to two utterances so that every sub-batch fills whole waves of the persistent scorer:
@@ -139,14 +153,17 @@ class BatchScorer(object):
     # ---- stages (each enqueues on the current torch stream) ----
     def upload(self, pcm_host):
         """pcm_host: pinned int16 torch tensor holding the utterances back to back"""
+        self._direct_use = True
         self.d_pcm.copy_(pcm_host, non_blocking=True)
 
     def features(self):
+        self._direct_use = True
         st = self.torch.cuda.current_stream().cuda_stream
         _lib.check(self.L.srb200_mfcc_extract_dev(self.ex._h, self.d_pcm.data_ptr(), self.smp_off, self.B, self.nd,
                                                   self.d_feat.data_ptr(), self.ld, self.feat_off, st), "mfcc_extract_dev")
 
     def score(self):
+        self._direct_use = True
         st = self.torch.cuda.current_stream().cuda_stream
         _lib.check(self.L.srb200_gmmset_score_dev(self._set(), self.d_feat.data_ptr(), self.ld, self.dim, self.feat_off, self.B,
                                                   self.d_sums.data_ptr(), None, 0, self.d_best.data_ptr(), st), "gmmset_score_dev")
@@ -156,20 +173,31 @@ class BatchScorer(object):
         self.features()
         self.score()
 
-    def predict_pcm(self, pcm_host, lengths):
-        """end to end: pinned host PCM in, speaker indices (host int32 tensor, pinned) out.  The batch is cut into
-        sub-batches of utterances; the H2D copy of sub-batch c+1 (copy stream) overlaps the kernels of sub-batch c."""
+    def submit(self, pcm_host, lengths):
+        """enqueue one end-to-end step -- pinned host PCM in, speaker indices out -- and return a ticket for result().  The batch
+        is cut into sub-batches of utterances: the H2D copy of sub-batch c+1 (copy stream) overlaps the kernels of sub-batch c.
+        Two buffer slots alternate, so a caller that submits step i+1 before collecting step i also overlaps the first copies of
+        step i+1 with the last kernels of step i (the copy engine and the SMs are then both busy all the time)."""
         torch = self.torch
         set_h = self._set()
         self._prepare(lengths)
+        k = getattr(self, "_next", 0)
+        self._next = k ^ 1
+        sl = self._use_slot(k)
         cur = torch.cuda.current_stream()
-        self.copy_stream.wait_stream(cur)              # previous users of d_pcm are done
+        if self._direct_use:
+            self.copy_stream.wait_stream(cur)          # direct users of the buffers (upload / features / score) are done
+            self._direct_use = False
+        elif sl["used"]:
+            self.copy_stream.wait_event(sl["done"])    # the step that used this slot before (two submits ago) has finished
+        while len(sl["copied"]) < len(self.chunks):
+            sl["copied"].append(torch.cuda.Event())
         with torch.cuda.stream(self.copy_stream):
-            for c, ev in zip(self.chunks, self.copy_events):
+            for c, ev in zip(self.chunks, sl["copied"]):
                 self.d_pcm[c["s0"]:c["s1"]].copy_(pcm_host[c["s0"]:c["s1"]], non_blocking=True)
                 ev.record(self.copy_stream)
         st = cur.cuda_stream
-        for c, ev in zip(self.chunks, self.copy_events):
+        for c, ev in zip(self.chunks, sl["copied"]):
             cur.wait_event(ev)
             nu = c["u1"] - c["u0"]
             _lib.check(self.L.srb200_mfcc_extract_dev(self.ex._h, self.d_pcm.data_ptr() + 2 * c["s0"], c["smp"], nu, self.nd,
@@ -179,8 +207,20 @@ class BatchScorer(object):
                                                       c["feat_off"], nu, self.d_sums.data_ptr() + 8 * self.S * c["u0"], None, 0,
                                                       self.d_best.data_ptr() + 4 * c["u0"], st), "gmmset_score_dev")
         self.h_best.copy_(self.d_best, non_blocking=True)
-        cur.synchronize()
-        return self.h_best
+        sl["done"].record(cur)
+        sl["used"] = True
+        sl["B"] = self.B
+        return sl
+
+    def result(self, ticket):
+        """wait for a submitted step; returns its speaker indices (pinned host int32 tensor, valid until the slot's next submit)"""
+        sl = ticket                                     # the slot itself: stays valid if a later, larger batch re-allocates the slots
+        sl["done"].synchronize()
+        return sl["hbest"][:sl["B"]]
+
+    def predict_pcm(self, pcm_host, lengths):
+        """end to end and synchronous: pinned host PCM in, speaker indices (host int32 tensor, pinned) out"""
+        return self.result(self.submit(pcm_host, lengths))
 
     def predict(self, signals):
         """convenience: list of int16 numpy signals -> list of labels"""

@@ -210,3 +210,37 @@ def test_ragged_batches_do_not_allocate_after_warm_up():
     bs2 = BatchScorer(gs, fs=16000, nd=2)
     n = int(sum(sh))
     assert np.array_equal(bs2.predict_pcm(pool[:n], sh).numpy(), lab)
+
+
+def test_two_steps_in_flight_give_the_synchronous_answers():
+    """submit() / result(): step i+1 is enqueued (its copies on the copy stream, into the other buffer slot) before step i's labels
+    are collected; every step's labels equal those of the synchronous predict_pcm on the same input"""
+    import torch
+    from speaker_recognition_b200.gmm.pygmm import GMM
+    from speaker_recognition_b200.gmmset import GMMSet
+    from speaker_recognition_b200.pipeline import BatchScorer
+    S, K, D = 6, 32, 39
+    W, M, Sg = synth.models(S, K, D, seed0=4200)
+    gs = GMMSet(gmm_order=K)
+    for i in range(S):
+        gs.gmms.append(GMM(K).set_params(W[i], M[i], Sg[i]))
+        gs.y.append(i)
+    bs = BatchScorer(gs, fs=16000, nd=2)
+    rng = np.random.default_rng(3)
+    steps = []
+    for i in range(7):
+        lengths = [int(rng.integers(6000, 30000)) for _ in range(int(rng.integers(1, 6)))]
+        if i in (2, 3):
+            lengths = [30000] * 40                                   # a chunked step (B >= 32) between unchunked ones
+        pcm = torch.from_numpy(synth.audio(int(sum(lengths)), seed=100 + i)).pin_memory()
+        steps.append((pcm, lengths))
+    want = [bs.predict_pcm(p, l).numpy().copy() for p, l in steps]
+    got = []
+    pending = bs.submit(*steps[0])
+    for p, l in steps[1:]:
+        nxt = bs.submit(p, l)
+        got.append(bs.result(pending).numpy().copy())
+        pending = nxt
+    got.append(bs.result(pending).numpy().copy())
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
