@@ -74,32 +74,40 @@ class BatchScorer(object):
         self.B = B
         self._use_slot(0)
         self._shape = key
-        # sub-batches for the end-to-end path: H2D of chunk c+1 overlaps the kernels of chunk c
-        self.chunks = []
-        # a small first sub-batch starts the kernels early (its copy is the only one nothing overlaps), later ones grow so the
-        # persistent scorer's waves stay full, and the LAST one is small again: its kernels are the only ones no copy overlaps.  Measured
-        # at C2 x 64 (profiles/r2_e2e_sweep.txt): five growing chunks 8.38 ms, this schedule 7.61 ms, ten chunks 7.9-8.1 ms per step (the
-        # copy alone takes 6 ms).  SRB200_E2E_CHUNKS="f1,f2,..." (cumulative fractions) overrides
-        fr = [1 / 32, 1 / 8, 0.25, 0.4, 0.55, 0.7, 0.85, 1.0] if B >= 32 else ([0.25, 0.5, 0.75, 1.0] if B >= 8 else [1.0])
+        # sub-batches for the end-to-end path: H2D of chunk c+1 overlaps the kernels of chunk c.
+        # One step at a time ("sync"): a small first sub-batch starts the kernels early (its copy is the only one nothing overlaps),
+        # later ones grow so the persistent kernels' waves stay full, and the LAST one is small again: its kernels are the only ones no
+        # copy overlaps.  Two steps in flight ("pipe"): the next step's copies fill those gaps anyway, so few, large sub-batches win
+        # (per-launch ramps and tails cost 0.1 ms per sub-batch).  Measured at C2 x 64 (profiles/r2_e2e_sweep.txt; the copy alone
+        # takes 6.0 ms, the kernels 6.16): sync 12.2 / 9.5 / 8.2 / 7.5 ms per step with 1 / 2 / 4 / 8 sub-batches, pipe 6.47 / 6.43 /
+        # 6.57 / 6.96.  SRB200_E2E_CHUNKS="f1,f2,..." (cumulative fractions) overrides both.
         env = os.environ.get("SRB200_E2E_CHUNKS")
+        fr_sync = [1 / 32, 1 / 8, 0.25, 0.4, 0.55, 0.7, 0.85, 1.0] if B >= 32 else ([0.25, 0.5, 0.75, 1.0] if B >= 8 else [1.0])
+        fr_pipe = [0.5, 1.0] if B >= 8 else [1.0]
         if env:
-            fr = [float(x) for x in env.split(",")]
+            fr_sync = fr_pipe = [float(x) for x in env.split(",")]
+        self.chunk_sets = {"sync": self._make_chunks(fr_sync, off, key), "pipe": self._make_chunks(fr_pipe, off, key)}
+        self.chunks = self.chunk_sets["sync"]
+        if getattr(self, "copy_stream", None) is None:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._direct_use = True
+
+    def _make_chunks(self, fr, off, key):
+        B = len(key)
         bounds = sorted(set([0] + [min(B, max(1, round(f * B))) for f in fr] + [B]))
-        if B >= 32 and os.environ.get("SRB200_E2E_ALIGN", "1") != "0":
+        if B >= 32 and len(bounds) > 3 and os.environ.get("SRB200_E2E_ALIGN", "1") != "0":
             bounds = self._wave_align(bounds, key)
-        n_chunks = len(bounds) - 1
+        chunks = []
         row0 = 0
-        for c in range(n_chunks):
+        for c in range(len(bounds) - 1):
             u0, u1 = bounds[c], bounds[c + 1]
             rel = (off[u0:u1 + 1] - off[u0]).tolist()
             smp = (C.c_longlong * (u1 - u0 + 1))(*rel)
             rows_c = int(self.L.srb200_mfcc_rows_total(self.ex._h, smp, u1 - u0, self.nd))
-            self.chunks.append(dict(u0=u0, u1=u1, s0=int(off[u0]), s1=int(off[u1]), smp=smp, row0=row0, rows=rows_c,
-                                    feat_off=(C.c_int * (u1 - u0 + 1))()))
+            chunks.append(dict(u0=u0, u1=u1, s0=int(off[u0]), s1=int(off[u1]), smp=smp, row0=row0, rows=rows_c,
+                               feat_off=(C.c_int * (u1 - u0 + 1))()))
             row0 += rows_c
-        if getattr(self, "copy_stream", None) is None:
-            self.copy_stream = torch.cuda.Stream(device=self.device)
-        self._direct_use = True
+        return chunks
 
     def _slot(self, k):
         """buffers of pipeline slot k at the current capacity (slot 0: the direct API; slots 0/1 alternate in submit())"""
@@ -183,6 +191,9 @@ class BatchScorer(object):
         self._prepare(lengths)
         k = getattr(self, "_next", 0)
         self._next = k ^ 1
+        other = self._slots.get(k ^ 1)
+        in_flight = other is not None and other["used"] and not other["done"].query()      # the caller keeps two steps in flight
+        self.chunks = self.chunk_sets["pipe" if in_flight else "sync"]
         sl = self._use_slot(k)
         cur = torch.cuda.current_stream()
         if self._direct_use:
