@@ -22,9 +22,15 @@
 namespace srb {
 
 constexpr double ET_SAFE_NB2 = TC_HARD_BUDGET;      // max over rows of sum nb''^2 the uncorrected form is trusted with: the scorer's own budget
-constexpr int ET_THREADS = 288;             // warp 0: loads + MMA issue; warps 1-8: epilogue (TMEM lane quarter = warp % 4, column half = (warp - 1) / 4)
-constexpr int ET_FLUSH_TILES = 8;           // tiles (of 128 frames) between float64 flushes of the accumulator
-constexpr int ET_L_COL = 0, ET_ACC_COL = 128, ET_A_COL = 256;      // TMEM columns: GEMM-1 accumulator | GEMM-2 accumulator (Kp) | PHI head, tail (Kp)
+constexpr int ET_FT = 64;                   // frames per tile of pass B
+constexpr int ET_NS = 4;                    // PHI stages in shared memory
+constexpr int ET_NX = 4;                    // raw frame-tile buffers (bulk-copy targets), loaded three tiles ahead
+constexpr int ET_THREADS = 352;             // warp 0: MMA issue; warps 1-10 build PHI; warps 1-8 also turn L^T into gamma (TMEM lane quarter = warp % 4, frame half = (warp - 1) / 4)
+constexpr int ET_WARP_PROD0 = 9;            // warps 9, 10: PHI only
+constexpr int ET_BUILDERS = 320;            // threads of warps 1-10: one (frame, 16-column chunk) task each at Kp = 80
+constexpr int ET_FLUSH_TILES = 16;          // tiles (of 64 frames) between float64 flushes of the accumulator: 1024 frames
+// tensor memory: W (A operand of GEMM 1: head Kp/2 | tail Kp/2 columns) | L^T accumulators [2][64] | gamma (A operand of GEMM 2) [2][head 32 | tail 32] | ACC [Kp]
+constexpr int ET_W_COL = 0, ET_L_COL = 128, ET_G_COL = 256, ET_ACC_COL = 384;
 
 // Workspace of the route: operand images of the model being trained (rebuilt from its float64 master every iteration) and the
 // float64 partials.  One per process, grow-only (DevBuf), shared by every model that trains: an E-step call builds, uses and is
@@ -102,10 +108,9 @@ __device__ __forceinline__ void et_put(__half *img2, __half *img128, int Kp, int
 	const size_t b2 = (size_t)blk * t2_block_halfs(Kp) + (size_t)(col >> 6) * 2 * T2_NH * Kp + t2_img_off(col & 63, k);
 	img2[b2] = h;
 	img2[b2 + (size_t)T2_NH * Kp] = l;
-	const size_t o128 = ((size_t)(k128 >> 3) * (TC_NB / 8) + (size_t)(col >> 3)) * 64 + (col & 7) * 8 + (k128 & 7);
-	const size_t b1 = (size_t)blk * 2 * TC_NB * Kp + o128;
+	const size_t b1 = ((size_t)blk * TC_NB + col) * 2 * Kp + k128;      // pass B: row-major [block][mixture][head Kp | tail Kp]
 	img128[b1] = h;
-	img128[b1 + (size_t)TC_NB * Kp] = l;
+	img128[b1 + Kp] = l;
 }
 
 // one warp per mixture row (incl. the padding rows of the last block): lanes stride over the dimensions
@@ -154,10 +159,10 @@ struct EtArgs {
 	const float *X;
 	int ld, D, n, Kp;
 	const float *cs;
-	const __half *img128;      // [blocks][head | tail][128 * Kp]
+	const __half *img128;      // [blocks][128 mixtures][head Kp | tail Kp], this file's column order
 	const float *lse2;         // [n] log2 p(x_t) from pass A
 	double *partials;          // [n_split][blocks][128][Kp]
-	int blocks, n_split, clamp, nY;
+	int blocks, n_split, clamp;
 };
 
 namespace et {
@@ -173,6 +178,13 @@ __device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&v)[8]) {
 	asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
 	             "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
 	             : "memory");
+}
+__device__ __forceinline__ void st16(uint32_t taddr, const uint32_t (&v)[16]) {
+	asm volatile(
+	    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+	    "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]),
+	    "r"(v[13]), "r"(v[14]), "r"(v[15])
+	    : "memory");
 }
 __device__ __forceinline__ void ld8(uint32_t taddr, uint32_t (&r)[8]) {
 	asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -200,6 +212,14 @@ __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_
 	    "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
 	    : "memory");
 }
+// the same with the accumulate flag as a run-time predicate
+__device__ __forceinline__ void mma_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+	asm volatile(
+	    "{\n\t.reg .b64 db;\n\t.reg .pred p, pe;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\telect.sync _|pe, 0xffffffff;\n\t"
+	    "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+	    "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+	    : "memory");
+}
 // D[tmem] (+)= A[smem] . B[smem], both operands through shared-memory descriptors; `acc` is a run-time predicate
 __device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
 	asm volatile(
@@ -223,49 +243,49 @@ __device__ __forceinline__ void split_pack(float v0, float v1, uint32_t &hi, uin
 }
 }  // namespace et
 
-// shared memory: W image (head | tail) + nY Y tiles (head | tail, MN-major) + gamma tile (head | tail, MN-major) + raw frame tile
-// [128][ld] (+32 bytes: the last chunk of the last row may read up to two 16-byte units past it) + lse2[2][128] + barriers / TMEM slot
-static size_t et_smem_bytes(int Kp, int ld, int nY) {
-	return (size_t)2 * TC_NB * Kp * 2 + (size_t)nY * 2 * TC_M * Kp * 2 + (size_t)2 * TC_M * TC_NB * 2 + ((size_t)TC_M * ld * 4 + 32) + 2 * TC_M * 4 + (size_t)Kp * 4 + 256;
-}
-// Y double-buffered where it fits: the next tile's PHI / Y are then built while GEMM 2 of the current tile runs
-static int et_ybufs(int Kp, int ld) {
-	for (int nY = 2; nY >= 1; --nY)
-		if (et_smem_bytes(Kp, ld, nY) <= 227 * 1024) return nY;
-	return 0;
+// shared memory: ET_NS PHI stages [head | tail][64 frames x Kp] + ET_NX raw frame tiles [64][ld] (+32 bytes: the last chunk of the last
+// row may read up to two 16-byte units past it) + lse2[ET_NS][64] + centre/scale [2][Kp/2] + barriers / TMEM slot
+static size_t et_smem_bytes(int Kp, int ld) {
+	return (size_t)ET_NS * 2 * ET_FT * Kp * 2 + (size_t)ET_NX * ((size_t)ET_FT * ld * 4 + 32) + (size_t)ET_NS * ET_FT * 4 + (size_t)Kp * 4 + 512;
 }
 
-// Column order of PHI / W / Y inside this file (any order works as long as the operands agree): k = 2 d -> x''_d^2, k = 2 d + 1 -> x''_d,
-// k = 2 D -> 1, rest 0 -- so that four dimensions (one 16-byte read of the frame row) make one 16-byte piece of the operand row.
+// Pass B, transposed so that two frame tiles are in flight and nothing but PHI goes through shared memory:
+//   GEMM 1   L^T[mixture][frame] = W . PHI^T     A = W in tensor memory (written once per CTA), B = the PHI tile [64 frames][Kp], K-major
+//   gamma    thread = mixture row: gamma = 2^(L^T - lse2[frame]) -> fp16 head + tail -> tensor memory (the A operand of GEMM 2)
+//   GEMM 2   ACC[mixture][col] += gamma . Y      B = the SAME shared-memory tile read MN-major (Y[frame][col] = PHI[frame][col]:
+//            the 8 x 16-byte core matrices of the K-major PHI tile are the core matrices of the MN-major Y tile; only the
+//            descriptor's strides differ: LBO = 128 (8 frames on), SBO = 1024 (8 columns on))
+// Column order of PHI / W (any order works as long as the operands agree): k = 2 d -> x''_d^2, k = 2 d + 1 -> x''_d, k = 2 D -> 1,
+// rest 0 -- four dimensions (one 16-byte read of the frame row) make one 16-byte piece of the operand row.
+// Roles: warp 0 issues the MMAs in the order G1(t+1), G2(t); warps 1-8 turn L^T into gamma (double-buffered in tensor memory on both
+// sides) and keep the float64 running sums; warps 9-10 build PHI (thread = frame) from raw frame tiles that arrive by bulk copy.
 template <int NCH>      // Kp / 16
 __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const EtArgs A) {
 	extern __shared__ __align__(1024) unsigned char et_smem[];
 	constexpr int Kp = NCH * 16;
-	const int D = A.D, ld = A.ld, nY = A.nY;
-	const uint32_t w_part = (uint32_t)TC_NB * Kp * 2, y_part = (uint32_t)TC_M * Kp * 2, g_part = (uint32_t)TC_M * TC_NB * 2;      // bytes of one image part
-	unsigned char *sW = et_smem;                         // [head | tail] 128 rows x Kp, K-major canonical (as stored in HBM)
-	unsigned char *sY = sW + 2 * w_part;                 // nY x [head | tail] Y[frame][col], MN-major canonical: (f >> 3) * (Kp / 8) * 128 + (c >> 3) * 128 + (f & 7) * 16 + (c & 7) * 2
-	unsigned char *sG = sY + (size_t)nY * 2 * y_part;    // [head | tail] gamma[frame][mixture], MN-major canonical: (f >> 3) * 2048 + (m >> 3) * 128 + (f & 7) * 16 + (m & 7) * 2
-	float *sX = reinterpret_cast<float *>(sG + 2 * g_part);        // [128][ld] the tile's frames as they lie in HBM (one bulk copy)
-	float *sL = sX + (size_t)TC_M * ld + 8;              // [2][128] lse2 of the tile's frames (+inf: the frame contributes nothing), by tile parity
-	float *sC = sL + 2 * TC_M;                           // [2][Kp / 2] centre, scale per dimension (zero-padded)
+	constexpr uint32_t p_part = (uint32_t)ET_FT * Kp * 2, p_stage = 2 * p_part;      // bytes: one PHI part (head or tail), one stage
+	const int D = A.D, ld = A.ld;
+	const uint32_t x_buf = (uint32_t)ET_FT * ld * 4 + 32;
+	unsigned char *sP = et_smem;                                 // [ET_NS][head | tail] (k >> 3) * 1024 + (f >> 3) * 128 + (f & 7) * 16 + (k & 7) * 2
+	unsigned char *sXb = sP + ET_NS * p_stage;                   // [ET_NX] raw frame tiles as they lie in HBM
+	float *sL = reinterpret_cast<float *>(sXb + ET_NX * x_buf);  // [ET_NS][64] lse2 of the tile's frames (+inf: the frame contributes nothing)
+	float *sC = sL + ET_NS * ET_FT;                              // [2][Kp / 2] alpha_d, -c_d alpha_d (zero-padded)
 	uint64_t *bars = reinterpret_cast<uint64_t *>(sC + Kp);
-	uint64_t *bar_w = bars, *bar_a = bars + 1, *bar_g1 = bars + 2, *bar_g = bars + 3, *bar_g2 = bars + 4, *bar_x = bars + 5;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+	uint64_t *x_full = bars, *x_empty = bars + 4, *phi_full = bars + 8, *phi_empty = bars + 12, *l_full = bars + 16, *l_empty = bars + 18,
+	         *g_full = bars + 20, *g_empty = bars + 22;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 26);
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int mb = blockIdx.x, split = blockIdx.y;
-	for (int i = tid; i < Kp; i += ET_THREADS) {
+	for (int i = tid; i < Kp; i += ET_THREADS) {             // x'' = x * alpha + (-c * alpha); both 0 beyond D
 		const int d = i % (Kp / 2);
-		sC[i] = d < D ? A.cs[(i / (Kp / 2)) * D + d] : 0.f;
+		const float al = d < D ? A.cs[D + d] : 0.f, ce = d < D ? A.cs[d] : 0.f;
+		sC[i] = i < Kp / 2 ? al : -ce * al;
 	}
 	if (tid == 0) {
-		mbar_init(bar_w, 1);
-		mbar_init(bar_a, 8);
-		mbar_init(bar_g1, 1);
-		mbar_init(bar_g, 8);
-		mbar_init(bar_g2, 1);
-		mbar_init(bar_x, 1);
+		for (int i = 0; i < ET_NX; ++i) mbar_init(&x_full[i], 1), mbar_init(&x_empty[i], 10);
+		for (int i = 0; i < ET_NS; ++i) mbar_init(&phi_full[i], 10), mbar_init(&phi_empty[i], 1);
+		for (int i = 0; i < 2; ++i) mbar_init(&l_full[i], 1), mbar_init(&l_empty[i], 8), mbar_init(&g_full[i], 8), mbar_init(&g_empty[i], 1);
 		fence_mbar_init();
 	}
 	if (warp == 0) {
@@ -277,78 +297,139 @@ __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const E
 	et::fence_after();
 	const uint32_t tmem_base = *tmem_slot;
 
-	const int n_tiles = (A.n + TC_M - 1) / TC_M;
+	const int n_tiles = (A.n + ET_FT - 1) / ET_FT;
 	const int per = (n_tiles + A.n_split - 1) / A.n_split;
-	const int t0 = split * per, t1 = min(n_tiles, t0 + per);
-	double *my_part = A.partials + ((size_t)split * A.blocks + mb) * TC_NB * Kp;
+	const int t0 = min(n_tiles, split * per), t1 = min(n_tiles, t0 + per);
+	const int nt = t1 - t0;
+
+	// ---- W of this block into tensor memory: lane = mixture row, the two warps of a lane quarter write head and tail ----
+	if (warp >= 1 && warp <= 8) {
+		const int q = warp & 3, h = (warp - 1) >> 2, row = q * 32 + lane;
+		const uint4 *src = reinterpret_cast<const uint4 *>(A.img128 + (((size_t)mb * TC_NB + row) * 2 + h) * Kp);
+#pragma unroll
+		for (int c = 0; c < NCH; ++c) {
+			const uint4 a = __ldg(src + 2 * c), b = __ldg(src + 2 * c + 1);
+			const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+			et::st8(tmem_base + ((uint32_t)(q * 32) << 16) + ET_W_COL + h * (Kp / 2) + 8 * c, r);
+		}
+		asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+	}
+	et::fence_before();
+	__syncthreads();
+	et::fence_after();
 
 	if (warp == 0) {
-		// ======================= loads + MMA issue =======================
-		auto load_x = [&](int t) {      // the tile's frames: rows are contiguous in HBM ([n][ld]), so the tile is ONE bulk copy
-			if (lane == 0) {
-				const uint32_t bytes = (uint32_t)min(TC_M, A.n - t * TC_M) * (uint32_t)ld * 4u;
-				mbar_expect_tx(bar_x, bytes);
-				bulk_g2s(sX, A.X + (size_t)t * TC_M * ld, bytes, bar_x);
-			}
-			__syncwarp();
-		};
-		if (lane == 0) {
-			mbar_expect_tx(bar_w, 2 * w_part);
-			bulk_g2s(sW, A.img128 + (size_t)mb * 2 * TC_NB * Kp, 2 * w_part, bar_w);
-		}
-		__syncwarp();
-		if (t0 < t1) load_x(t0);
-		const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TC_NB >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);                               // K-major A (TMEM) and B
-		const uint32_t idesc2 = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(Kp >> 3) << 17) | ((uint32_t)(TC_NB >> 4) << 24);      // MN-major A and B, N = Kp
-		constexpr uint32_t lbo_w = (TC_NB / 8) * 128;
-		const uint32_t dW_hi = (uint32_t)(128 >> 4) | (1u << 14);                                                                        // SBO 128 | version
-		const uint32_t dW0 = ((smem_u32(sW) >> 4) & 0x3FFF) | ((lbo_w >> 4) << 16);
-		constexpr uint32_t stepW = (2 * lbo_w) >> 4;
-		// MN-major tiles: K-groups (8 frames) are (MN / 8) * 128 bytes apart = the descriptor's LBO, MN-adjacent core matrices 128 bytes
-		// = its SBO (measured: experiments/tc_mn_major_test.cu, profiles/r2_mn_major_probe.txt)
-		const uint32_t kg_G = (TC_NB / 8) * 128, kg_Y = (uint32_t)(Kp / 8) * 128;
-		const uint32_t dG_hi = (uint32_t)(128 >> 4) | (1u << 14), dY_hi = dG_hi;
-		const uint32_t dG0 = ((smem_u32(sG) >> 4) & 0x3FFF) | ((kg_G >> 4) << 16);
-		const uint32_t stepG = (2 * kg_G) >> 4, stepY = (2 * kg_Y) >> 4;
-		constexpr int ks1 = NCH;
-		const uint32_t a_hi = tmem_base + ET_A_COL, a_lo = a_hi + (uint32_t)(Kp >> 1);
-		et::wait(bar_w, 0);
-		uint32_t it = 0;
-		for (int t = t0; t < t1; ++t, ++it) {
-			et::wait(bar_a, it & 1);                     // PHI in tensor memory, Y in shared memory; the raw frame tile has been consumed
-			et::fence_after();
-			if (t + 1 < t1) load_x(t + 1);
-			{
-				const uint32_t d1 = tmem_base + ET_L_COL;
-				et::mma_ts<0>(d1, a_hi, dW0, dW_hi, idesc1);
+		// ======================= MMA issue =======================
+		constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(ET_FT >> 3) << 17) | ((uint32_t)(TC_NB >> 4) << 24);                  // A (TMEM) and B K-major, N = 64
+		constexpr uint32_t idesc2 = (1u << 4) | (1u << 16) | ((uint32_t)(Kp >> 3) << 17) | ((uint32_t)(TC_NB >> 4) << 24);        // B MN-major, N = Kp
+		constexpr uint32_t d1_hi = (uint32_t)(128 >> 4) | (1u << 14), d1_lbo = (uint32_t)(1024 >> 4) << 16;                       // K-major: LBO = K-group stride, SBO = 8 frames on
+		constexpr uint32_t d2_hi = (uint32_t)(1024 >> 4) | (1u << 14), d2_lbo = (uint32_t)(128 >> 4) << 16;                       // MN-major: LBO = K-group (8 frames), SBO = 8 columns on
+		const uint32_t w_hi = tmem_base + ET_W_COL, w_lo = w_hi + Kp / 2;
+		for (int i = 0; i <= nt; ++i) {
+			if (i < nt) {
+				const int s = i % ET_NS, b = i & 1;
+				et::wait(&phi_full[s], (uint32_t)(i / ET_NS) & 1);
+				et::wait(&l_empty[b], ((uint32_t)(i >> 1) & 1) ^ 1);
+				et::fence_after();
+				const uint32_t d1 = tmem_base + ET_L_COL + 64 * b;
+				const uint32_t pb = ((smem_u32(sP + (size_t)s * p_stage) >> 4) & 0x3FFF) | d1_lbo;
+				et::mma_ts<0>(d1, w_hi, pb, d1_hi, idesc1);
 #pragma unroll
-				for (int k = 1; k < ks1; ++k) et::mma_ts<1>(d1, a_hi + 8 * k, dW0 + stepW * k, dW_hi, idesc1);
-				for (int k = 0; k < ks1; ++k) et::mma_ts<1>(d1, a_lo + 8 * k, dW0 + stepW * k, dW_hi, idesc1);
-				for (int k = 0; k < ks1; ++k) et::mma_ts<1>(d1, a_hi + 8 * k, dW0 + (w_part >> 4) + stepW * k, dW_hi, idesc1);
-				et::commit(bar_g1);
+				for (int k = 1; k < NCH; ++k) et::mma_ts<1>(d1, w_hi + 8 * k, pb + 128 * k, d1_hi, idesc1);
+#pragma unroll
+				for (int k = 0; k < NCH; ++k) et::mma_ts<1>(d1, w_lo + 8 * k, pb + 128 * k, d1_hi, idesc1);
+#pragma unroll
+				for (int k = 0; k < NCH; ++k) et::mma_ts<1>(d1, w_hi + 8 * k, pb + (p_part >> 4) + 128 * k, d1_hi, idesc1);
+				et::commit(&l_full[b]);
 			}
-			et::wait(bar_g, it & 1);                     // gamma tile in shared memory (and a due flush has read ACC)
-			et::fence_after();
-			{
-				const uint32_t d2 = tmem_base + ET_ACC_COL;
-				const uint32_t dY0 = ((smem_u32(sY + (size_t)(it % nY) * 2 * y_part) >> 4) & 0x3FFF) | ((kg_Y >> 4) << 16);
-				uint32_t acc = (it % ET_FLUSH_TILES) == 0 ? 0u : 1u;      // first GEMM 2 after a flush overwrites the accumulator
-				for (int k = 0; k < TC_M / 16; ++k) {        // gamma head x Y head, gamma tail x Y head, gamma head x Y tail
-					et::mma_ss(d2, dG0 + stepG * k, dG_hi, dY0 + stepY * k, dY_hi, idesc2, acc);
+			if (i > 0) {
+				const int j = i - 1, s = j % ET_NS, b = j & 1;
+				et::wait(&g_full[b], (uint32_t)(j >> 1) & 1);            // gamma of tile j is in tensor memory (and a due flush has read ACC)
+				et::fence_after();
+				const uint32_t d2 = tmem_base + ET_ACC_COL, gh = tmem_base + ET_G_COL + 64 * b, gt = gh + 32;
+				const uint32_t yb = ((smem_u32(sP + (size_t)s * p_stage) >> 4) & 0x3FFF) | d2_lbo;
+				uint32_t acc = (j % ET_FLUSH_TILES) == 0 ? 0u : 1u;      // first GEMM 2 after a flush overwrites the accumulator
+#pragma unroll
+				for (int k = 0; k < ET_FT / 16; ++k) {                   // gamma head x Y head, gamma tail x Y head, gamma head x Y tail
+					et::mma_ts_p(d2, gh + 8 * k, yb + 16 * k, d2_hi, idesc2, acc);
 					acc = 1u;
-					et::mma_ss(d2, dG0 + (g_part >> 4) + stepG * k, dG_hi, dY0 + stepY * k, dY_hi, idesc2, 1u);
-					et::mma_ss(d2, dG0 + stepG * k, dG_hi, dY0 + (y_part >> 4) + stepY * k, dY_hi, idesc2, 1u);
+					et::mma_ts<1>(d2, gt + 8 * k, yb + 16 * k, d2_hi, idesc2);
+					et::mma_ts<1>(d2, gh + 8 * k, yb + (p_part >> 4) + 16 * k, d2_hi, idesc2);
 				}
-				et::commit(bar_g2);
+				et::commit(&g_empty[b]);
+				et::commit(&phi_empty[s]);
 			}
 		}
 	} else {
-		// ======================= epilogue: thread = frame row (PHI / Y / gamma) or mixture row (flush) =======================
-		const int q = warp & 3, half = (warp - 1) >> 2;
-		const int row = q * 32 + lane;
+		// ======================= warps 1-10: PHI tiles (all), gamma (warps 1-8, thread = mixture row) =======================
+		const int q = warp & 3, h = (warp - 1) >> 2, row = q * 32 + lane;
 		const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-		const float4 *cen4 = reinterpret_cast<const float4 *>(sC), *alp4 = reinterpret_cast<const float4 *>(sC + Kp / 2);
-		constexpr int nch = NCH;
+		const int btid = tid - 32;                               // 0..319
+		const bool issuer = btid == 0;
+		const bool gamma_warp = warp < ET_WARP_PROD0;
+		auto load_x = [&](int t, int xb) {      // the tile's frames: rows are contiguous in HBM ([n][ld]), so the tile is ONE bulk copy
+			const uint32_t bytes = (uint32_t)min(ET_FT, A.n - t * ET_FT) * (uint32_t)ld * 4u;
+			mbar_expect_tx(&x_full[xb], bytes);
+			bulk_g2s(sXb + (size_t)xb * x_buf, A.X + (size_t)t * ET_FT * ld, bytes, &x_full[xb]);
+		};
+		if (issuer)
+			for (int j = 0; j < min(nt, ET_NX - 1); ++j) load_x(t0 + j, j);
+		__syncwarp();
+		const float4 *cen4 = reinterpret_cast<const float4 *>(sC), *nca4 = reinterpret_cast<const float4 *>(sC + Kp / 2);
+		// PHI of tile j: a task = one frame x one chunk of 16 operand columns (8 dimensions: two 16-byte reads of the frame row, two
+		// 16-byte pieces of the head row and two of the tail row); tasks are dealt to the 320 threads, frames fastest
+		auto build = [&](int j) {
+			const int t = t0 + j, s = j % ET_NS, xb = j % ET_NX;
+			et::wait(&x_full[xb], (uint32_t)(j / ET_NX) & 1);
+			et::wait(&phi_empty[s], ((uint32_t)(j / ET_NS) & 1) ^ 1);        // GEMM 2 of tile j - ET_NS has read this stage
+			for (int task = btid; task < ET_FT * NCH; task += ET_BUILDERS) {
+				const int f = task & (ET_FT - 1), c = task >> 6;
+				const int fr = t * ET_FT + f;
+				const bool valid = fr < A.n;
+				const float4 *xr = reinterpret_cast<const float4 *>(sXb + (size_t)xb * x_buf) + (size_t)f * (ld >> 2);
+				uint32_t hi[8], lo[8];
+#pragma unroll
+				for (int u = 0; u < 2; ++u) {
+					const float4 xv = valid ? xr[2 * c + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+					const float4 av = cen4[2 * c + u], bv = nca4[2 * c + u];      // x'' = x * alpha - c * alpha
+					const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, as4[4] = {av.x, av.y, av.z, av.w}, bs4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+					for (int jj = 0; jj < 4; ++jj) {
+						const int d = 8 * c + 4 * u + jj;
+						const float xin = d < D ? xs[jj] : 0.f;      // row padding / the next row's data: never enters the arithmetic (it may be NaN)
+						float v1 = fminf(fmaxf(fmaf(xin, as4[jj], bs4[jj]), -T2_X_CLAMP), T2_X_CLAMP);      // 0 beyond D (alpha = 0 there)
+						float v0 = v1 * v1;
+						if (d == D) v0 = 1.f;                      // the constant column; columns beyond stay (0, 0)
+						if (!valid) v0 = 0.f, v1 = 0.f;
+						et::split_pack(v0, v1, hi[4 * u + jj], lo[4 * u + jj]);
+					}
+				}
+				unsigned char *ph = sP + (size_t)s * p_stage + (size_t)(2 * c) * 1024 + (size_t)(f >> 3) * 128 + (f & 7) * 16;
+				*reinterpret_cast<uint4 *>(ph) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+				*reinterpret_cast<uint4 *>(ph + 1024) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+				*reinterpret_cast<uint4 *>(ph + p_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+				*reinterpret_cast<uint4 *>(ph + p_part + 1024) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+				if (c == 0) {
+					float l2 = __int_as_float(0x7f800000);           // +inf -> gamma = 2^(-inf) = 0
+					if (valid) {
+						l2 = __ldg(A.lse2 + fr);
+						if (A.clamp && !(l2 * TC_LN2 >= -744.4400719213812f)) l2 = __int_as_float(0x7f800000);      // gmm.cc:482-490: underflowed frame
+					}
+					sL[s * ET_FT + f] = l2;
+				}
+			}
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the PHI stores become visible to the tensor core
+			__syncwarp();
+			if (lane == 0) {
+				mbar_arrive(&phi_full[s]);
+				mbar_arrive(&x_empty[xb]);
+			}
+			if (issuer && j + ET_NX - 1 < nt) {              // tile j + 3 goes into the buffer tile j - 1 used
+				if (j >= 1) et::wait(&x_empty[(j - 1) % ET_NX], (uint32_t)((j - 1) / ET_NX) & 1);
+				load_x(t + ET_NX - 1, (j + ET_NX - 1) % ET_NX);
+			}
+			__syncwarp();
+		};
 		// float64 running sums of this thread's part of the statistics: mixture `row` of the block, its half of the Kp columns.  The
 		// tensor-memory accumulator is fp32 and is folded in here every ET_FLUSH_TILES tiles (1024 frames)
 		double acc64[Kp / 2];
@@ -358,113 +439,59 @@ __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const E
 #pragma unroll
 			for (int c = 0; c < Kp / 2; c += 8) {
 				uint32_t r[8];
-				et::ld8(lane_base + ET_ACC_COL + half * (Kp / 2) + c, r);
+				et::ld8(lane_base + ET_ACC_COL + h * (Kp / 2) + c, r);
 				et::ld_wait();
 #pragma unroll
 				for (int j = 0; j < 8; ++j) acc64[c + j] += (double)__uint_as_float(r[j]);
 			}
 		};
-		// PHI (tensor memory) and Y (shared memory) of this thread's frame; the two warps of a lane quarter split the 16-value chunks
-		auto build = [&](int t, uint32_t itb) {
-			et::wait(bar_x, itb & 1);
-			const int fr = t * TC_M + row;
-			const bool valid = fr < A.n;
-			const float4 *xr = reinterpret_cast<const float4 *>(sX + (size_t)row * ld);
-			unsigned char *ybuf = sY + (size_t)(itb % nY) * 2 * y_part;
+		for (int j = 0; j < min(nt, 2); ++j) build(j);
+		for (int i = 0; i < nt; ++i) {
+			if (i + 2 < nt) build(i + 2);                        // two tiles ahead of the gamma stage: GEMM 1 of tile i + 1 runs under gamma of tile i
+			if (!gamma_warp) continue;
+			const int s = i % ET_NS, b = i & 1;
+			et::wait(&l_full[b], (uint32_t)(i >> 1) & 1);
+			et::fence_after();
+			uint32_t v[32];
+			et::ld32(lane_base + ET_L_COL + 64 * b + 32 * h, v);
+			et::ld_wait();
+			et::fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&l_empty[b]);                  // GEMM 1 of tile i + 2 may overwrite this buffer
+			const float4 *l4 = reinterpret_cast<const float4 *>(sL + s * ET_FT + 32 * h);
+			uint32_t hi[16], lo[16];
 #pragma unroll
-			for (int c = half; c < nch; c += 2) {
-				uint32_t hi[8], lo[8];
-#pragma unroll
-				for (int u = 0; u < 2; ++u) {
-					const float4 xv = valid ? xr[2 * c + u] : make_float4(0.f, 0.f, 0.f, 0.f);
-					const float4 cv = cen4[2 * c + u], av = alp4[2 * c + u];
-					const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, cs4[4] = {cv.x, cv.y, cv.z, cv.w}, as4[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-					for (int j = 0; j < 4; ++j) {
-						const int d = 8 * c + 4 * u + j;
-						float v0 = 0.f, v1 = 0.f;                  // (x''^2, x'') | (1, 0) at d == D | (0, 0) beyond
-						if (d < D) {
-							v1 = fminf(fmaxf((xs[j] - cs4[j]) * as4[j], -T2_X_CLAMP), T2_X_CLAMP);
-							v0 = v1 * v1;
-						} else if (d == D) {
-							v0 = 1.f;
-						}
-						if (!valid) v0 = 0.f, v1 = 0.f;
-						et::split_pack(v0, v1, hi[4 * u + j], lo[4 * u + j]);
-					}
-				}
-				et::st8(lane_base + ET_A_COL + 8 * c, hi);
-				et::st8(lane_base + ET_A_COL + (Kp >> 1) + 8 * c, lo);
-				// the same 16 values as two 16-byte pieces of the Y row (columns 16 c .. 16 c + 15)
-				unsigned char *yh = ybuf + (size_t)(row >> 3) * (Kp / 8) * 128 + (size_t)(2 * c) * 128 + (row & 7) * 16;
-				*reinterpret_cast<uint4 *>(yh) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-				*reinterpret_cast<uint4 *>(yh + 128) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-				*reinterpret_cast<uint4 *>(yh + y_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-				*reinterpret_cast<uint4 *>(yh + y_part + 128) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+			for (int j4 = 0; j4 < 8; ++j4) {
+				const float4 ls = l4[j4];                             // the same address in every lane: a broadcast read
+				const float g0 = ex2_approx(__uint_as_float(v[4 * j4]) - ls.x), g1 = ex2_approx(__uint_as_float(v[4 * j4 + 1]) - ls.y);
+				const float g2 = ex2_approx(__uint_as_float(v[4 * j4 + 2]) - ls.z), g3 = ex2_approx(__uint_as_float(v[4 * j4 + 3]) - ls.w);
+				et::split_pack(g0, g1, hi[2 * j4], lo[2 * j4]);
+				et::split_pack(g2, g3, hi[2 * j4 + 1], lo[2 * j4 + 1]);
 			}
-			if (half == 0) {
-				float l2 = __int_as_float(0x7f800000);       // +inf -> gamma = 2^(-inf) = 0
-				if (valid) {
-					l2 = __ldg(A.lse2 + fr);
-					if (A.clamp && !(l2 * TC_LN2 >= -744.4400719213812f)) l2 = __int_as_float(0x7f800000);      // gmm.cc:482-490: underflowed frame
-				}
-				sL[(itb & 1) * TC_M + row] = l2;
+			if (i > 0 && (i % ET_FLUSH_TILES) == 0) {                 // GEMM 2 of tile i - 1 complete -> fold the accumulator before GEMM 2 of tile i overwrites it
+				et::wait(&g_empty[(i - 1) & 1], (uint32_t)((i - 1) >> 1) & 1);
+				et::fence_after();
+				flush();
 			}
+			et::wait(&g_empty[b], ((uint32_t)(i >> 1) & 1) ^ 1);      // GEMM 2 of tile i - 2 has read this gamma buffer
+			et::fence_after();
+			et::st16(lane_base + ET_G_COL + 64 * b + 16 * h, hi);
+			et::st16(lane_base + ET_G_COL + 64 * b + 32 + 16 * h, lo);
 			asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the Y stores become visible to the tensor core
 			et::fence_before();
 			__syncwarp();
-			if (lane == 0) mbar_arrive(bar_a);
-		};
-		uint32_t it = 0;
-		if (t0 < t1) build(t0, 0);
-		for (int t = t0; t < t1; ++t, ++it) {
-			// ---- gamma = 2^(L - lse2) for this thread's frame and its 64 mixtures, fp16 head + tail, MN-major.  GEMM 1 of this tile
-			// complete implies GEMM 2 of the previous one complete (the tensor pipe is in order): the gamma tile, the accumulator and
-			// the other Y buffer are free
-			et::wait(bar_g1, it & 1);
-			et::fence_after();
-			if (it > 0 && (it % ET_FLUSH_TILES) == 0) flush();
-			const float lse = sL[(it & 1) * TC_M + row];
-#pragma unroll 1
-			for (int cc = 0; cc < 2; ++cc) {
-				uint32_t v[32];
-				et::ld32(lane_base + ET_L_COL + 64 * half + 32 * cc, v);
-				et::ld_wait();
-				unsigned char *gh = sG + (size_t)(row >> 3) * 2048 + (size_t)(8 * half + 4 * cc) * 128 + (row & 7) * 16;
-#pragma unroll
-				for (int g8 = 0; g8 < 4; ++g8) {             // 8 mixtures = one 16-byte piece
-					uint32_t hi[4], lo[4];
-#pragma unroll
-					for (int j = 0; j < 4; ++j) {
-						const float g0 = ex2_approx(__uint_as_float(v[8 * g8 + 2 * j]) - lse), g1 = ex2_approx(__uint_as_float(v[8 * g8 + 2 * j + 1]) - lse);
-						et::split_pack(g0, g1, hi[j], lo[j]);
-					}
-					*reinterpret_cast<uint4 *>(gh + g8 * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-					*reinterpret_cast<uint4 *>(gh + g_part + g8 * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-				}
-			}
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			et::fence_before();
-			__syncwarp();
-			if (lane == 0) mbar_arrive(bar_g);
-			// ---- the next tile's operands, while GEMM 2 of this one runs (two Y buffers) or after it (one)
-			if (t + 1 < t1) {
-				if (nY == 1) {
-					et::wait(bar_g2, it & 1);
-					et::fence_after();
-				}
-				build(t + 1, it + 1);
-			}
+			if (lane == 0) mbar_arrive(&g_full[b]);
 		}
-		if (t1 > t0) {
-			et::wait(bar_g2, (it - 1) & 1);
-			et::fence_after();
-			flush();
-		}
-		double *p = my_part + (size_t)row * Kp + half * (Kp / 2);
+		if (gamma_warp) {
+			if (nt > 0) {
+				et::wait(&g_empty[(nt - 1) & 1], (uint32_t)((nt - 1) >> 1) & 1);
+				et::fence_after();
+				flush();
+			}
+			double *p = A.partials + (((size_t)split * A.blocks + mb) * TC_NB + row) * Kp + h * (Kp / 2);
 #pragma unroll
-		for (int j = 0; j < Kp / 2; ++j) p[j] = acc64[j];
+			for (int j = 0; j < Kp / 2; ++j) p[j] = acc64[j];
+		}
 	}
 	et::fence_before();
 	__syncthreads();
@@ -519,8 +546,7 @@ int launch_estep_tc(PackedModels &pm, const double *d_params, const float *dX, i
 	Context &c = ctx();
 	*used = 0;
 	const int Kp = t2_kp(D), blocks = ceil_div(K, TC_NB);
-	const int nY = et_ybufs(Kp, ld);
-	if (nY == 0 || (ld & 3) != 0 || (reinterpret_cast<uintptr_t>(dX) & 15) != 0) return 0;      // the frame tile is one 16-byte-granular bulk copy
+	if (et_smem_bytes(Kp, ld) > 227 * 1024 || (ld & 3) != 0 || (reinterpret_cast<uintptr_t>(dX) & 15) != 0) return 0;      // the frame tile is one 16-byte-granular bulk copy
 	(void)pm;
 	const int n_split = std::max(1, c.sm_count / blocks);
 	EmTcWorkspace &w = g_ws;                                   // ensure() is a no-op once the buffers are large enough
@@ -578,9 +604,8 @@ int launch_estep_tc(PackedModels &pm, const double *d_params, const float *dX, i
 	a.blocks = blocks;
 	a.n_split = n_split;
 	a.clamp = clamp;
-	a.nY = nY;
 	const dim3 grid(blocks, n_split);
-	const size_t smem = et_smem_bytes(Kp, ld, nY);
+	const size_t smem = et_smem_bytes(Kp, ld);
 	switch (Kp / 16) {
 		case 2: em_accumulate_tc_kernel<2><<<grid, ET_THREADS, smem, st>>>(a); break;
 		case 3: em_accumulate_tc_kernel<3><<<grid, ET_THREADS, smem, st>>>(a); break;
