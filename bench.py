@@ -345,9 +345,18 @@ def sub_c3_em(L, rank, world, iters=10, N=1000000, K=512, D=39):
     w0 = np.ones(K) / K
     del X, comp
 
+    passes = [0]
+
     def run(n_it):
         gm = GMM(K).set_params(w0, m0, s0)
         be = sdist.DeviceEM(gm, Xd, hi - lo, ld, D)
+        passes[0] = 0
+        inner = be.estep
+
+        def counted():
+            passes[0] += 1
+            return inner()
+        be.estep = counted
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -373,7 +382,7 @@ def sub_c3_em(L, rank, world, iters=10, N=1000000, K=512, D=39):
         e1.record()
         torch.cuda.synchronize()
         ar_us = _maxed(e0.elapsed_time(e1) / 50 * 1e3, world)
-    n_estep = done + done // 2                      # every second iteration's monitor costs one more E-step pass
+    n_estep = passes[0]                             # the monitor of iteration i is the E-step of iteration i + 1: one extra pass at the end at most
     per_it = ms / max(done, 1)
     return {"workload": "C3", "mixtures": K, "dim": D, "frames": N, "nranks": world, "frames_per_rank": hi - lo, "iterations": done,
             "ms_total": ms, "ms_per_iteration": per_it, "frames_per_sec_per_iteration": N / (per_it * 1e-3), "allreduce_us": ar_us,
