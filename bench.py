@@ -347,9 +347,10 @@ def sub_c3_em(L, rank, world, iters=10, N=1000000, K=512, D=39):
 
     passes = [0]
 
-    def run(n_it):
+    def run(n_it, n_local=None):
+        n_local = hi - lo if n_local is None else n_local
         gm = GMM(K).set_params(w0, m0, s0)
-        be = sdist.DeviceEM(gm, Xd, hi - lo, ld, D)
+        be = sdist.DeviceEM(gm, Xd, n_local, ld, D)
         passes[0] = 0
         inner = be.estep
 
@@ -362,7 +363,7 @@ def sub_c3_em(L, rank, world, iters=10, N=1000000, K=512, D=39):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        done, ll = sdist.em_train(be, N, n_it, threshold=0.0)
+        done, ll = sdist.em_train(be, N if n_local == hi - lo else n_local * world, n_it, threshold=0.0)
         e1.record()
         torch.cuda.synchronize()
         return done, ll, e0.elapsed_time(e1)
@@ -384,11 +385,27 @@ def sub_c3_em(L, rank, world, iters=10, N=1000000, K=512, D=39):
         ar_us = _maxed(e0.elapsed_time(e1) / 50 * 1e3, world)
     n_estep = passes[0]                             # the monitor of iteration i is the E-step of iteration i + 1: one extra pass at the end at most
     per_it = ms / max(done, 1)
+    # the part of an iteration that does not shrink with the shard (operand packing, the route flag read, M-step, launches, the
+    # all-reduce): the same loop on the smallest shard the tensor route takes (n K = 2^24)
+    n_small = min(hi - lo, (1 << 24) // K)
+    run(2, n_small)
+    d_s, _, ms_s = run(iters, n_small)
+    fixed_ms = _maxed(ms_s, world) / max(d_s, 1)
+    ar_share = ar_us * 1e-3 / per_it
+    if world == 1:
+        limit = "single GPU: no exchange; %.2f of %.2f ms per iteration is the fixed part (measured on a %d-frame shard)" % (fixed_ms, per_it, n_small)
+    elif ar_share >= 0.2:
+        limit = "exchange-bound: the all-reduce is %.0f %% of an iteration" % (100.0 * ar_share)
+    elif fixed_ms >= 0.5 * per_it:
+        limit = ("latency-bound: %.2f of %.2f ms per iteration is the fixed part that does not shrink with the shard (measured on a %d-frame shard: operand "
+                 "packing, route flag read, M-step, launches, all-reduce %.0f us = %.0f %%)" % (fixed_ms, per_it, n_small, ar_us, 100.0 * ar_share))
+    else:
+        limit = "compute-bound: the all-reduce is %.1f %% of an iteration, the fixed part %.2f of %.2f ms" % (100.0 * ar_share, fixed_ms, per_it)
     return {"workload": "C3", "mixtures": K, "dim": D, "frames": N, "nranks": world, "frames_per_rank": hi - lo, "iterations": done,
             "ms_total": ms, "ms_per_iteration": per_it, "frames_per_sec_per_iteration": N / (per_it * 1e-3), "allreduce_us": ar_us,
             "allreduce_bytes": int(stats.numel() * 8), "scaling": "strong", "final_ll": ll,
             "algorithmic_tflops": 7.0 * D * N * K * done / (ms * 1e-3) / 1e12,
-            "limit": ("the all-reduce is %.1f %% of an iteration: compute-bound" % (100.0 * ar_us * 1e-3 / per_it)) if world > 1 else "single GPU: no exchange",
+            "limit": limit, "fixed_ms_per_iteration": fixed_ms,
             "e_step_passes": n_estep, "em_route_last": int(L.srb200_last_em_route()),
             "em_route_note": "1 = tcgen05 E-step (gmm_em_tc.cu), 0 = fp32 FMA kernels (gmm_em.cu)"}
 
