@@ -384,6 +384,7 @@ def sub_c3_em(L, rank, world, iters=10, N=1000000, K=512, D=39):
         torch.cuda.synchronize()
         ar_us = _maxed(e0.elapsed_time(e1) / 50 * 1e3, world)
     n_estep = passes[0]                             # the monitor of iteration i is the E-step of iteration i + 1: one extra pass at the end at most
+    route_main = int(L.srb200_last_em_route())
     per_it = ms / max(done, 1)
     # the part of an iteration that does not shrink with the shard (operand packing, the route flag read, M-step, launches, the
     # all-reduce): the same loop on the smallest shard the tensor route takes (n K = 2^24)
@@ -406,7 +407,7 @@ def sub_c3_em(L, rank, world, iters=10, N=1000000, K=512, D=39):
             "allreduce_bytes": int(stats.numel() * 8), "scaling": "strong", "final_ll": ll,
             "algorithmic_tflops": 7.0 * D * N * K * done / (ms * 1e-3) / 1e12,
             "limit": limit, "fixed_ms_per_iteration": fixed_ms,
-            "e_step_passes": n_estep, "em_route_last": int(L.srb200_last_em_route()),
+            "e_step_passes": n_estep, "em_route_last": route_main,
             "em_route_note": "1 = tcgen05 E-step (gmm_em_tc.cu), 0 = fp32 FMA kernels (gmm_em.cu)"}
 
 
