@@ -6,11 +6,11 @@
 //   pass B   gamma[t][k] = 2^(l2[t][k] - lse2[t]);   S[k][:] = sum_t gamma[t][k] * [x''_t^2, x''_t, 1]      (GEMM over the FRAMES)
 // Here the fp16 head/tail operand images of the CURRENT parameters are built on the device from the float64 master
 // (em_tc_pack_kernel: no host round trip inside an EM iteration), pass A is the tcgen05 scorer reading those images, and pass B is
-// em_accumulate_tc_kernel: per (128-mixture block, frame range) a CTA alternates
-//     GEMM 1  L[128 frames x 128 mixtures] = PHI (tensor memory) . W^T (shared memory, resident for the CTA's lifetime)
-//     epilogue  gamma = 2^(L - lse2), split into fp16 head + tail, written MN-major into shared memory (a thread owns a frame row)
-//     GEMM 2  ACC[128 mixtures x Kp] += gamma^T . Y,  Y = [x''^2, x'', 1] (fp16 head + tail, MN-major)   -- 3 passes each
-// with ACC in tensor memory, flushed into float64 partials every 1024 frames; em_tc_reduce_kernel sums the partials and maps
+// em_accumulate_tc_kernel: per (128-mixture block, frame range) a CTA pipelines, per tile of 64 frames,
+//     GEMM 1  L^T[128 mixtures x 64 frames] = W (tensor memory, written once per CTA) . PHI^T (shared-memory ring, K-major)
+//     gamma   thread = mixture row: gamma = 2^(L^T - lse2), fp16 head + tail, written back to tensor memory
+//     GEMM 2  ACC[128 mixtures x Kp] += gamma (tensor memory) . Y,  Y = the same shared-memory tile read MN-major   -- 3 passes each
+// with ACC in tensor memory, folded into float64 running sums (registers) every 1024 frames; em_tc_reduce_kernel sums the splits and maps
 // the centred / scaled moments back to sum gamma x, sum gamma x^2.  Exactly corrected entries (gmm_score_tc2's add-back) are NOT
 // used here: the packer computes max_k sum_d nb''^2 and raises a flag when the expanded form would not be accurate enough
 // (collapsed mixtures far from the centre) -- the caller then runs the FMA kernels of gmm_em.cu for that iteration.
@@ -218,14 +218,6 @@ __device__ __forceinline__ void mma_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint3
 	    "{\n\t.reg .b64 db;\n\t.reg .pred p, pe;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\telect.sync _|pe, 0xffffffff;\n\t"
 	    "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
 	    "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
-	    : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem], both operands through shared-memory descriptors; `acc` is a run-time predicate
-__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
-	asm volatile(
-	    "{\n\t.reg .b64 da, db;\n\t.reg .pred p, pe;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\telect.sync _|pe, 0xffffffff;\n\t"
-	    "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
-	    "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
 	    : "memory");
 }
 __device__ __forceinline__ void commit(uint64_t *bar) {
