@@ -203,28 +203,32 @@ __device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&r)[32]) {
 	    : "r"(taddr));
 }
 __device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem] . B[smem]^T, single CTA, whole converged warp, one lane elected
+// D[tmem] (+)= A[tmem] . B[smem]^T, single CTA.  These three run inside a region that ONE elected lane executes (one election per
+// GEMM of a tile, not per instruction): the operands then stay in uniform registers and the MMAs issue back to back -- the
+// per-instruction form (elect + 2 VOTEU + 4 R2UR + 2 UMOV + UTCHMMA) cost ten instructions and a dependent chain per MMA.
 template <int ACC>
 __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
 	asm volatile(
-	    "{\n\t.reg .b64 db;\n\t.reg .pred p, pe;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\telect.sync _|pe, 0xffffffff;\n\t"
-	    "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+	    "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
 	    "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
 	    : "memory");
 }
 // the same with the accumulate flag as a run-time predicate
 __device__ __forceinline__ void mma_ts_p(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
 	asm volatile(
-	    "{\n\t.reg .b64 db;\n\t.reg .pred p, pe;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\telect.sync _|pe, 0xffffffff;\n\t"
-	    "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+	    "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
 	    "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
 	    : "memory");
 }
 __device__ __forceinline__ void commit(uint64_t *bar) {
-	asm volatile(
-	    "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
-	    "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
-	    : "memory");
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(ok));
+	return ok != 0;
 }
 __device__ __forceinline__ void split_pack(float v0, float v1, uint32_t &hi, uint32_t &lo) {      // v0 in the low half
 	const __half2 h = __floats2half2_rn(v0, v1);
@@ -325,14 +329,17 @@ __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const E
 				et::fence_after();
 				const uint32_t d1 = tmem_base + ET_L_COL + 64 * b;
 				const uint32_t pb = ((smem_u32(sP + (size_t)s * p_stage) >> 4) & 0x3FFF) | d1_lbo;
-				et::mma_ts<0>(d1, w_hi, pb, d1_hi, idesc1);
+				if (et::elect_one()) {
+					et::mma_ts<0>(d1, w_hi, pb, d1_hi, idesc1);
 #pragma unroll
-				for (int k = 1; k < NCH; ++k) et::mma_ts<1>(d1, w_hi + 8 * k, pb + 128 * k, d1_hi, idesc1);
+					for (int k = 1; k < NCH; ++k) et::mma_ts<1>(d1, w_hi + 8 * k, pb + 128 * k, d1_hi, idesc1);
 #pragma unroll
-				for (int k = 0; k < NCH; ++k) et::mma_ts<1>(d1, w_lo + 8 * k, pb + 128 * k, d1_hi, idesc1);
+					for (int k = 0; k < NCH; ++k) et::mma_ts<1>(d1, w_lo + 8 * k, pb + 128 * k, d1_hi, idesc1);
 #pragma unroll
-				for (int k = 0; k < NCH; ++k) et::mma_ts<1>(d1, w_hi + 8 * k, pb + (p_part >> 4) + 128 * k, d1_hi, idesc1);
-				et::commit(&l_full[b]);
+					for (int k = 0; k < NCH; ++k) et::mma_ts<1>(d1, w_hi + 8 * k, pb + (p_part >> 4) + 128 * k, d1_hi, idesc1);
+					et::commit(&l_full[b]);
+				}
+				__syncwarp();
 			}
 			if (i > 0) {
 				const int j = i - 1, s = j % ET_NS, b = j & 1;
@@ -341,15 +348,18 @@ __global__ void __launch_bounds__(ET_THREADS, 1) em_accumulate_tc_kernel(const E
 				const uint32_t d2 = tmem_base + ET_ACC_COL, gh = tmem_base + ET_G_COL + 64 * b, gt = gh + 32;
 				const uint32_t yb = ((smem_u32(sP + (size_t)s * p_stage) >> 4) & 0x3FFF) | d2_lbo;
 				uint32_t acc = (j % ET_FLUSH_TILES) == 0 ? 0u : 1u;      // first GEMM 2 after a flush overwrites the accumulator
+				if (et::elect_one()) {
 #pragma unroll
-				for (int k = 0; k < ET_FT / 16; ++k) {                   // gamma head x Y head, gamma tail x Y head, gamma head x Y tail
-					et::mma_ts_p(d2, gh + 8 * k, yb + 16 * k, d2_hi, idesc2, acc);
-					acc = 1u;
-					et::mma_ts<1>(d2, gt + 8 * k, yb + 16 * k, d2_hi, idesc2);
-					et::mma_ts<1>(d2, gh + 8 * k, yb + (p_part >> 4) + 16 * k, d2_hi, idesc2);
+					for (int k = 0; k < ET_FT / 16; ++k) {               // gamma head x Y head, gamma tail x Y head, gamma head x Y tail
+						et::mma_ts_p(d2, gh + 8 * k, yb + 16 * k, d2_hi, idesc2, acc);
+						acc = 1u;
+						et::mma_ts<1>(d2, gt + 8 * k, yb + 16 * k, d2_hi, idesc2);
+						et::mma_ts<1>(d2, gh + 8 * k, yb + (p_part >> 4) + 16 * k, d2_hi, idesc2);
+					}
+					et::commit(&g_empty[b]);
+					et::commit(&phi_empty[s]);
 				}
-				et::commit(&g_empty[b]);
-				et::commit(&phi_empty[s]);
+				__syncwarp();
 			}
 		}
 	} else {

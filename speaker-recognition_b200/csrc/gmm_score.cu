@@ -21,6 +21,7 @@
 #include "gmm_model.h"
 #include <algorithm>
 #include "kernels.h"
+#include "gmm_score_tc_layout.h"
 
 namespace srb {
 
@@ -493,7 +494,7 @@ int launch_score_tc_images(const Tc2Images &im, const float *dX, int ld, int D, 
 	TileTable *tt = nullptr;
 	if (get_table(utt_off, n_utt, im.S, 128, st, &tt)) return 1;
 	if (launch_score_tc2_images(im, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;
-	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, im.S, im.S, 4, d_sums, d_best);
+	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, im.S, im.S, T2_PARTS, d_sums, d_best);
 	SRB_CUDA(cudaGetLastError());
 	return 0;
 }
@@ -534,7 +535,7 @@ int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *ut
 		TileTable *tt = nullptr;
 		if (get_table(utt_off, n_utt, pm.S, 128, st, &tt)) return 1;
 		if (launch_score_tc2(pm, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;
-		score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, pm.S_arg > 0 ? pm.S_arg : pm.S, 4, d_sums, d_best);
+		score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, pm.S_arg > 0 ? pm.S_arg : pm.S, T2_PARTS, d_sums, d_best);
 		SRB_CUDA(cudaGetLastError());
 		return 0;
 	}

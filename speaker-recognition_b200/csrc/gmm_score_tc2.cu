@@ -10,7 +10,8 @@ static size_t tc2_smem_bytes_n(int Kp, int D, int nst) {
 	// half-block stages (head | tail: 256 Kp bytes) + hard-entry ring + add-back scratch [16][32][T2_SCR_STRIDE] + finisher ring
 	// [T2_FSLOTS][4][128] float2 + mbarriers / TMEM slot word (512 B) + x'' tile [128][D|1]
 	return (size_t)nst * 4 * T2_NH * Kp + (size_t)T2_HSTAGES * TC_HSTRIDE * 16 + 16 * 32 * T2_SCR_STRIDE * sizeof(float) +
-	       (size_t)T2_FSLOTS * 4 * TC_M * 8 + 512 + (size_t)TC_M * tc_x_stride(D) * sizeof(float);
+	       (size_t)T2_FSLOTS * 4 * TC_M * 8 + 512 + (size_t)TC_M * tc_x_stride(D) * sizeof(float) +
+	       (size_t)2 * T2_RED_SPK * T2_RED_STRIDE * sizeof(float);      // + the finishers' row-sum buffers
 }
 
 // deepest B ring that fits (a stage is 960 tensor cycles of work at Kp = 80; the ring has to cover the L2 latency); 0 = unsupported
@@ -109,3 +110,12 @@ int launch_score_tc2_images(const Tc2Images &pm, const float *dX, int ld, int D,
 }
 
 }  // namespace srb
+
+#if SRB_T2_PROF
+extern "C" int srb200_debug_tc2_prof(unsigned long long *out) {      // experiments only: read and clear the cycle counters
+	if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+	if (cudaMemcpyFromSymbol(out, srb::g_tc2_prof, sizeof(srb::g_tc2_prof)) != cudaSuccess) return 1;
+	static unsigned long long zero[2 * 20 * 8];
+	return cudaMemcpyToSymbol(srb::g_tc2_prof, zero, sizeof(zero)) != cudaSuccess;
+}
+#endif

@@ -64,6 +64,32 @@ struct Tc2Args {
 	const int4 *hard;          // [n_blocks_total][TC_HSTRIDE], layout in gmm_score_tc_layout.h
 };
 
+#if SRB_T2_PROF          /* experiments only: where do the warps of CTA pair 0 spend their cycles? [20 warps][8 counters] per CTA rank */
+__device__ unsigned long long g_tc2_prof[2][20][8];
+#define T2P_DECL unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt = clock64(); const long long pt00 = pt
+#define T2P(k)                              \
+	do {                                    \
+		const long long now_ = clock64();   \
+		pf[k] += (unsigned long long)(now_ - pt); \
+		pt = now_;                          \
+	} while (0)
+#define T2P_FLUSH                                                                                      \
+	do {                                                                                               \
+		pf[6] = (unsigned long long)(clock64() - pt00);                                                \
+		if (lane == 0 && blockIdx.x < 2)                                                               \
+			for (int k_ = 0; k_ < 8; ++k_) atomicAdd(&g_tc2_prof[blockIdx.x][warp][k_], pf[k_]);       \
+	} while (0)
+#else
+#define T2P_DECL
+#define T2P(k)
+#define T2P_FLUSH
+#endif
+#if SRB_T2_PROF == 2      /* finer split of the epilogue's block loop */
+#define T2E(coarse, fine) T2P(fine)
+#else
+#define T2E(coarse, fine) T2P(coarse)
+#endif
+
 namespace tc2 {
 
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -90,11 +116,55 @@ __device__ __forceinline__ void arrive_cluster(uint32_t addr) {
 }
 // bounded waits: a broken pipeline traps instead of hanging the GPU
 __device__ __forceinline__ void wait(uint64_t *bar, uint32_t parity) {
-	long long spins = 0;
+	if (mbar_try_wait(bar, parity)) return;
+	int spins = 0;
 	while (!mbar_try_wait(bar, parity)) {
-		if (++spins > 400000000LL) __trap();
+		if (++spins > 400000000) __trap();
 	}
 }
+// The same on 32-bit shared-window addresses computed ONCE per thread: the per-block loops of the epilogue add ring offsets to them
+// (a generic pointer costs a generic -> shared conversion -- S2UR CgaCtaId, LEA, subtract -- at every use inside a cluster kernel).
+__device__ __forceinline__ bool try_wait_a(uint32_t bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(ok)
+	    : "r"(bar), "r"(parity)
+	    : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void wait_a(uint32_t bar, uint32_t parity) {
+	if (try_wait_a(bar, parity)) return;
+	int spins = 0;
+	while (!try_wait_a(bar, parity)) {
+		if (++spins > 400000000) __trap();
+	}
+}
+__device__ __forceinline__ void arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ int4 lds128(uint32_t a) {
+	int4 v;
+	asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ uint32_t keep(uint32_t x) {      // a value ptxas must hold in a register (it cannot re-execute a volatile statement)
+	uint32_t y;
+	asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+	return y;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t a) {
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+	return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
 // 32 accumulator columns of this thread's lane; the registers are valid after ld_wait()
 __device__ __forceinline__ void ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
 	asm volatile(
@@ -114,25 +184,28 @@ __device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&v)[8]) {
 	             : "memory");
 }
 // D[tmem] (+)= A[tmem] . B[smem]^T over the CTA pair: A (this CTA's 128 rows) is read from tensor memory, B (64 rows from each
-// CTA) from shared memory.  Issued by the whole converged warp of the LEADER CTA, one lane elected inside the statement.
+// CTA) from shared memory.  For a region that ONE elected lane of the leader's MMA warp executes: with one election per BLOCK
+// (not per instruction) every operand stays in uniform registers -- SASS: 15 UTCHMMA back to back with one UIADD3 between them,
+// where the per-instruction form cost ELECT + 2 VOTEU + 4 R2UR + 2 UMOV each (ten instructions per MMA).
 template <int ACC>
-__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+__device__ __forceinline__ void mma_f16_ts_1t(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
 	asm volatile(
-	    "{\n\t.reg .b64 db;\n\t.reg .pred p, pe;\n\t"
+	    "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
 	    "mov.b64 db, {%2, %3};\n\t"
 	    "setp.ne.b32 p, %5, 0;\n\t"
-	    "elect.sync _|pe, 0xffffffff;\n\t"
-	    "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+	    "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
 	    "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC)
 	    : "memory");
 }
-// completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void commit_pair(uint64_t *bar) {
-	asm volatile(
-	    "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
-	    "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
-	    "h"((uint16_t)3)
-	    : "memory");
+__device__ __forceinline__ void commit_pair_1t(uint64_t *bar) {
+	asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+	             "h"((uint16_t)3)
+	             : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\tselp.u32 %0, 1, 0, pe;\n\t}" : "=r"(ok));
+	return ok != 0;
 }
 // fp32 -> fp16 head + fp16 tail, both round-to-nearest; two values per call, packed (first value in the low half)
 __device__ __forceinline__ void split_pack(float v0, float v1, uint32_t &hi, uint32_t &lo) {
@@ -183,17 +256,16 @@ __device__ __forceinline__ unsigned long long tc2_exp2_poly2(unsigned long long 
 
 // online log2-sum-exp2 update with 32 new values (one chunk of accumulator columns) for one frame; the first NP of the 32
 // exponentials are evaluated on the FMA pipe, the others by MUFU.EX2
-template <int NP>
+// FRESH: the running pair is known to be empty (m_run = -3e38, s_run = 0: the first chunk of a speaker) -- no rescale of the old sum
+template <int NP, bool FRESH>
 __device__ __forceinline__ void tc2_lse_update(const float *v, float &m_run, float &s_run) {
-	float t[16];                                   // tree reduction (ptxas fuses the pairs into three-input FMNMX3)
+	// three-input maxima throughout (SASS FMNMX3): 10 + 4 + 2 instructions for the 32 values and the running maximum
+	auto max3 = [](float a, float b, float c) { return fmaxf(fmaxf(a, b), c); };
+	float t[10];
 #pragma unroll
-	for (int i = 0; i < 16; ++i) t[i] = fmaxf(v[2 * i], v[2 * i + 1]);
-#pragma unroll
-	for (int w = 8; w >= 1; w >>= 1)
-#pragma unroll
-		for (int i = 0; i < w; ++i) t[i] = fmaxf(t[i], t[i + w]);
-	const float mx = t[0];
-	const float m_new = fmaxf(m_run, mx);
+	for (int i = 0; i < 10; ++i) t[i] = max3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+	const float u0 = max3(t[0], t[1], t[2]), u1 = max3(t[3], t[4], t[5]), u2 = max3(t[6], t[7], t[8]), u3 = max3(t[9], v[30], v[31]);
+	const float m_new = max3(max3(u0, u1, u2), u3, m_run);
 	// packed fp32x2 adds (SASS FADD2): the 32 subtractions and the 32 sum updates cost 16 instructions each
 	const float nm = -m_new;
 	unsigned long long nm2, acc01 = 0ull, acc23 = 0ull;
@@ -212,8 +284,13 @@ __device__ __forceinline__ void tc2_lse_update(const float *v, float &m_run, flo
 			float a, b, c, d;
 			asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(d01));
 			asm("mov.b64 {%0, %1}, %2;" : "=f"(c), "=f"(d) : "l"(d23));
+#if (SRB_T2_FAKE & 1)
+			asm("mov.b64 %0, {%1, %2};" : "=l"(e01) : "f"(a), "f"(b));
+			asm("mov.b64 %0, {%1, %2};" : "=l"(e23) : "f"(c), "f"(d));
+#else
 			asm("mov.b64 %0, {%1, %2};" : "=l"(e01) : "f"(ex2_approx(a)), "f"(ex2_approx(b)));
 			asm("mov.b64 %0, {%1, %2};" : "=l"(e23) : "f"(ex2_approx(c)), "f"(ex2_approx(d)));
+#endif
 		}
 		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc01) : "l"(acc01), "l"(e01));
 		asm("add.rn.f32x2 %0, %1, %2;" : "=l"(acc23) : "l"(acc23), "l"(e23));
@@ -221,7 +298,8 @@ __device__ __forceinline__ void tc2_lse_update(const float *v, float &m_run, flo
 	float s0, s1, s2, s3;
 	asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(acc01));
 	asm("mov.b64 {%0, %1}, %2;" : "=f"(s2), "=f"(s3) : "l"(acc23));
-	s_run = fmaf(s_run, ex2_approx(m_run - m_new), (s0 + s1) + (s2 + s3));
+	if (FRESH) s_run = (s0 + s1) + (s2 + s3);
+	else s_run = fmaf(s_run, ex2_approx(m_run - m_new), (s0 + s1) + (s2 + s3));
 	m_run = m_new;
 }
 
@@ -245,6 +323,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 	uint64_t *fin_full = a_ready + 1, *fin_empty = fin_full + T2_FSLOTS;
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fin_empty + T2_FSLOTS);
 	float *sX = reinterpret_cast<float *>(bars + 64);                                           // [128][XS] x'' of the unit's tile
+	float *red = sX + (size_t)TC_M * XS;                                                        // [2 finishers][T2_RED_SPK][T2_RED_STRIDE] per-row log-likelihoods awaiting their row sums
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const uint32_t rank = tc2::cluster_rank();
@@ -287,6 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 		if (lane == 0) {
 			uint32_t it_h = 0, ph_b = 0;
 			int st_b = 0;
+			T2P_DECL;
 			for (int u = cluster_id; u < n_units; u += n_clusters) {
 				const int chunk = u % A.n_chunks;
 				const int blk0 = chunk * blocks_per_chunk_full;
@@ -296,18 +376,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 					// on ONE barrier: an epilogue warp that sees the block's accumulator (tm_full) knows the list has landed too -- the MMA
 					// warp waited for this barrier before it issued -- so the epilogue needs no wait of its own for the list
 					const int hst = it_h % T2_HSTAGES;
+					T2P(2);
 					tc2::wait(&empty_h[hst], ((it_h / T2_HSTAGES) & 1) ^ 1);
+					T2P(0);
 					tc2::wait(&empty_b[st_b], ph_b ^ 1);
-					mbar_expect_tx(&full_b[st_b], stage_bytes + TC_HSTRIDE * 16);
+					T2P(1);
+					const uint32_t copy_bytes = (SRB_T2_FAKE & 32) ? 1024u : stage_bytes;      /* timing experiment: a token copy */
+					mbar_expect_tx(&full_b[st_b], copy_bytes + TC_HSTRIDE * 16);
 					bulk_g2s(hring + (size_t)hst * TC_HSTRIDE, A.hard + (size_t)b * TC_HSTRIDE, TC_HSTRIDE * 16, &full_b[st_b]);
 					const unsigned char *src = reinterpret_cast<const unsigned char *>(A.B) + ((size_t)b * 2 + rank) * stage_bytes;
-					bulk_g2s(sB + (size_t)st_b * stage_bytes, src, stage_bytes, &full_b[st_b]);
+					bulk_g2s(sB + (size_t)st_b * stage_bytes, src, copy_bytes, &full_b[st_b]);
 					if (++st_b == NST) {
 						st_b = 0;
 						ph_b ^= 1;
 					}
 				}
 			}
+			T2P_FLUSH;
 		}
 	} else if (warp == T2_WARP_MMA && rank != 0) {
 		// ======================= peer CTA: relay "my half of the stage has landed" to the leader =======================
@@ -340,42 +425,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 		const uint32_t tail_off = part_bytes >> 4;
 		uint32_t ph_b = 0, it_a = 0, it_s = 0;
 		int st_b = 0;
+		T2P_DECL;
 		for (int u = cluster_id; u < n_units; u += n_clusters, ++it_a) {
 			const int chunk = u % A.n_chunks;
 			const int blk0 = chunk * blocks_per_chunk_full;
 			const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
+			T2P(4);
 			tc2::wait(a_ready, it_a & 1);            // PHI of both CTAs' tiles is in tensor memory
 			tc2::fence_after();
+			T2P(0);
 			for (int b = blk0; b < blk1; ++b, ++it_s) {
 				const int slot = it_s % T2_SLOTS;
 				tc2::wait(&tm_empty[slot], ((it_s / T2_SLOTS) & 1) ^ 1);
+				T2P(1);
 				const int st = st_b;
 				tc2::wait(&full_b[st], ph_b);
+				T2P(2);
 				tc2::wait(&peer_full[st], ph_b);
 				tc2::fence_after();
+				T2P(5);
 				const uint32_t d_tmem = tmem_base + (uint32_t)(slot * TC_NB);
 				const uint32_t dB0 = ((smem_u32(sB + (size_t)st * stage_bytes) >> 4) & 0x3FFF) | ((lbo_b >> 4) << 16);
 				// 3xFP16: (A_hi + A_lo) * B_hi, then A_hi * B_lo
-				tc2::mma_f16_ts<0>(d_tmem, a_hi, dB0, d_hi, idesc);     // first MMA of the block overwrites the slot
+				if (tc2::elect_one()) {                 // ONE election per block: the lane issues the block's MMAs and both commits
+					tc2::mma_f16_ts_1t<0>(d_tmem, a_hi, dB0, d_hi, idesc);
 #pragma unroll
-				for (int k = 1; k < ksteps; ++k) tc2::mma_f16_ts<1>(d_tmem, a_hi + 8 * k, dB0 + stepB * k, d_hi, idesc);
+					for (int k = 1; k < ((SRB_T2_FAKE & 16) ? 1 : ksteps); ++k) tc2::mma_f16_ts_1t<1>(d_tmem, a_hi + 8 * k, dB0 + stepB * k, d_hi, idesc);
 #pragma unroll
-				for (int k = 0; k < ksteps; ++k) tc2::mma_f16_ts<1>(d_tmem, a_lo + 8 * k, dB0 + stepB * k, d_hi, idesc);
+					for (int k = 0; k < ((SRB_T2_FAKE & 16) ? 2 : ksteps); ++k) tc2::mma_f16_ts_1t<1>(d_tmem, a_lo + 8 * k, dB0 + stepB * k, d_hi, idesc);
 #pragma unroll
-				for (int k = 0; k < ksteps; ++k) tc2::mma_f16_ts<1>(d_tmem, a_hi + 8 * k, dB0 + tail_off + stepB * k, d_hi, idesc);
-				tc2::commit_pair(&empty_b[st]);         // both CTAs' stage may be refilled once these MMAs have read it
-				tc2::commit_pair(&tm_full[slot]);       // the accumulator slot is complete (in both CTAs)
+					for (int k = 0; k < ((SRB_T2_FAKE & 16) ? 2 : ksteps); ++k) tc2::mma_f16_ts_1t<1>(d_tmem, a_hi + 8 * k, dB0 + tail_off + stepB * k, d_hi, idesc);
+					tc2::commit_pair_1t(&empty_b[st]);
+					tc2::commit_pair_1t(&tm_full[slot]);
+				}
+				__syncwarp();
+				T2P(3);
 				if (++st_b == NST) {
 					st_b = 0;
 					ph_b ^= 1;
 				}
 			}
 		}
+		T2P_FLUSH;
 	} else if (warp >= T2_WARP_FIN0) {
 		// ======================= finishers: warp 16 rows 0-63, warp 17 rows 64-127 =======================
+		// Per speaker: merge the four column groups' (max, sum), log2, clamp, optional per-frame output.  The per-(tile, speaker) ROW
+		// SUMS are not taken speaker by speaker (a 5-step shuffle tree per speaker and batch is a ~300-cycle dependent chain: measured, it
+		// paced the whole kernel at 1 900 cycles per block against 1 370 without it): the per-row values of up to T2_RED_SPK speakers
+		// are parked in shared memory, [speaker][row], and summed with lane = speaker -- 64 independent loads and adds per 32 speakers,
+		// in a fixed order (deterministic), one store of partial[tile][speaker][finisher] per lane.
 		const int f = warp - T2_WARP_FIN0;
 		const int seg = A.seg;
+		float *tb = red + (size_t)f * (T2_RED_SPK * T2_RED_STRIDE);
 		uint32_t it_f = 0;
+		T2P_DECL;
 		for (int u = cluster_id; u < n_units; u += n_clusters) {
 			const int pair = u / A.n_chunks, chunk = u - pair * A.n_chunks;
 			const int tile = 2 * pair + (int)rank;
@@ -384,29 +487,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 			const int blk1 = min(A.n_blocks_total, blk0 + blocks_per_chunk_full);
 			const int4 ft = tile_ok ? A.ftiles[tile] : make_int4(0, 0, 0, 0);
 			int spk = chunk * A.spk_per_chunk;
+			int base = spk, cnt = 0;                  // speakers [base, base + cnt) are parked
 			const int n_entries = seg >= TC_NB ? (blk1 - blk0) / A.blocks_per_spk : (blk1 - blk0);
+			auto flush = [&]() {
+				__syncwarp();
+				if (tile_ok && lane < cnt && base + lane < A.S) {
+					const float *r = tb + lane * T2_RED_STRIDE;
+					float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+					for (int i = 0; i < 64; i += 4) {
+						a0 += r[i];
+						a1 += r[i + 1];
+						a2 += r[i + 2];
+						a3 += r[i + 3];
+					}
+					A.partial[((size_t)tile * A.S + base + lane) * T2_PARTS + f] = (double)((a0 + a1) + (a2 + a3));
+				}
+				__syncwarp();
+				base += cnt;
+				cnt = 0;
+			};
 			for (int e = 0; e < n_entries; ++e, ++it_f) {
 				const int slot = it_f % T2_FSLOTS;
+				T2P(2);
 				tc2::wait(&fin_full[slot], (it_f / T2_FSLOTS) & 1);
+				T2P(0);
 				const float2 *fs = fin + (size_t)slot * 4 * TC_M;
 #pragma unroll
-				for (int batch = 0; batch < 2; ++batch) {
+				for (int batch = 0; batch < ((SRB_T2_FAKE & 8) ? 0 : 2); ++batch) {
 					const int q = 2 * f + batch, row = q * 32 + lane;
 					const bool valid = row < ft.y;
 					float2 g[4];
 #pragma unroll
 					for (int c = 0; c < 4; ++c) g[c] = fs[c * TC_M + row];
-					// close one speaker from its (m, s): clamp, per-frame output, per-(tile, speaker, lane quarter) partial sum
+					// close one speaker from its (m, s): clamp, per-frame output, park the row's value for the row sum
 					auto out = [&](int my_spk, float m, float sacc) {
 						if (my_spk < A.S && tile_ok) {
 							const float l2 = m + lg2_approx(sacc);
 							float ll = l2 * TC_LN2;
 							if (A.clamp && !(ll >= -744.4400719213812f)) ll = -34.538776394910684f;
 							if (valid && A.frame_ll != nullptr) A.frame_ll[(size_t)my_spk * A.ldf + ft.x + row] = A.frame_log2 ? l2 : ll;
-							float local = valid ? ll : 0.f;
-#pragma unroll
-							for (int off = 16; off >= 1; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
-							if (lane == 0) A.partial[((size_t)tile * A.S + my_spk) * 4 + q] = (double)local;
+							tb[(my_spk - base) * T2_RED_STRIDE + batch * 32 + lane] = valid ? ll : 0.f;
 						}
 					};
 					auto merge2 = [](float2 a, float2 b) {
@@ -414,8 +535,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 						return make_float2(M, a.y * ex2_approx(a.x - M) + b.y * ex2_approx(b.x - M));
 					};
 					if (seg >= TC_NB) {
-						const float2 r = merge2(merge2(g[0], g[1]), merge2(g[2], g[3]));
-						out(spk, r.x, r.y);
+						// four groups against their common maximum: 4 exponentials (a pairwise tree costs 6)
+						const float M = fmaxf(fmaxf(g[0].x, g[1].x), fmaxf(g[2].x, g[3].x));
+						const float sacc = (g[0].y * ex2_approx(g[0].x - M) + g[1].y * ex2_approx(g[1].x - M)) +
+						                   (g[2].y * ex2_approx(g[2].x - M) + g[3].y * ex2_approx(g[3].x - M));
+						out(spk, M, sacc);
 					} else if (seg == 64) {
 						const float2 r0 = merge2(g[0], g[1]), r1 = merge2(g[2], g[3]);
 						out(spk, r0.x, r0.y);
@@ -427,9 +551,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				}
 				__syncwarp();
 				if (lane == 0) mbar_arrive(&fin_empty[slot]);
-				spk += seg >= TC_NB ? 1 : (seg == 64 ? 2 : 4);
+				T2P(1);
+				const int step = seg >= TC_NB ? 1 : (seg == 64 ? 2 : 4);
+				spk += step;
+				cnt += step;
+				if (cnt == T2_RED_SPK) flush();
 			}
+			flush();
 		}
+		T2P_FLUSH;
 	} else {
 		// ======================= epilogue (16 warps; thread = frame row; the 4 warps of a lane quarter take the 4 column groups) ====
 		const int ew = warp;                          // 0..15
@@ -439,16 +569,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 		const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 		float *my_scr = scr + ((size_t)ew * 32 + lane) * T2_SCR_STRIDE;      // this thread's flagged-column sums (slot p = p-th flagged column of the group)
 		float *xrow = sX + (size_t)row * XS;
-		const unsigned char *xrow_b = reinterpret_cast<const unsigned char *>(xrow);
-		unsigned char *scr_b = reinterpret_cast<unsigned char *>(my_scr) - 1;      // entry.w = 1 + byte offset of the scratch column
+		// entry.w = 1 + byte offset of the scratch column; shared-window addresses for the scratch and the x'' row (a generic pointer
+		// store costs an S2R CgaCtaId + LEA + IADD3 conversion per access inside the add-back loop)
+		// (through an opaque move: at the register cap ptxas otherwise REMATERIALISES the conversion inside the loop)
+		const uint32_t a_scr = tc2::keep(smem_u32(my_scr)), a_scr_m1 = a_scr - 1u, a_xrow = tc2::keep(smem_u32(xrow));
 		const int seg = A.seg;
 		const int cols_per_spk = (seg >= TC_NB) ? A.blocks_per_spk * TC_NB : seg;
 		const int nch = Kp >> 4;                      // chunks of 16 k-values = 8 packed columns
 		const uint32_t a_ready_leader = tc2::mapa(smem_u32(a_ready), 0);
 		const uint32_t tm_empty_leader = tc2::mapa(smem_u32(tm_empty), 0);
-		uint32_t it_f = 0, ph_s = 0;
-		int slot = 0, hst = 0;                        // accumulator slot / hard-list ring position of the next block (rings never reset)
+		// shared-window addresses of everything the block loop touches, computed once (ring offsets are added per block)
+		const uint32_t a_tm_full = smem_u32(tm_full), a_empty_h = smem_u32(empty_h), a_hdr = smem_u32(hring) + 16u * (uint32_t)cg;
+		const uint32_t a_fin = smem_u32(fin) + 8u * (uint32_t)(cg * TC_M + row), a_fin_full = smem_u32(fin_full), a_fin_empty = smem_u32(fin_empty);
+		const uint32_t t_ld = lane_base + (uint32_t)(cg * 32);
+		const bool single = seg < TC_NB || A.blocks_per_spk == 1;      // every block closes a speaker: no running pair to rescale
+		uint32_t ph_s = 0, ph_f = 0;                  // phase of the accumulator ring / of the finisher ring
+		uint32_t slot8 = 0;                           // 8 x accumulator slot of the next block (barrier offset; x 16 = TMEM column offset)
+		uint32_t hoff = 0;                            // byte offset of the next block's list in the hard-entry ring (its barrier: hoff >> 8)
+		uint32_t fslot8 = 0;                          // 8 x finisher-ring slot of the next hand-over (rings never reset)
+		static_assert(TC_NB == 128 && TC_HSTRIDE * 16 == 2048 && (T2_HSTAGES & (T2_HSTAGES - 1)) == 0 && T2_FSLOTS == 8, "ring offsets below");
 #define SRB_TC2_QBAR() asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory")      /* the 4 warps of this lane quarter */
+		T2P_DECL;
 		for (int u = cluster_id; u < n_units; u += n_clusters) {
 			const int pair = u / A.n_chunks, chunk = u - pair * A.n_chunks;
 			const int tile = 2 * pair + (int)rank;
@@ -508,34 +649,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				}
 			}
 
+			T2E(5, 6);
 			float m_run = -3.0e38f, s_run = 0.f;
 			int col_in_spk = 0;                       // columns of the current speaker consumed so far (by the quarter's warps together)
 
 			// end of a speaker segment: this warp's running (max, sum) of its 32-column group goes to the finishers.  The ring is
 			// checked once per FOUR hand-overs (the finishers release in order: the last slot of the next four being free means all are)
 			auto handoff = [&]() {
-				const int slot = it_f % T2_FSLOTS;
-				if ((it_f & 3) == 0) tc2::wait(&fin_empty[slot + 3], ((it_f / T2_FSLOTS) & 1) ^ 1);
-				fin[((size_t)slot * 4 + cg) * TC_M + row] = make_float2(m_run, s_run);
+				if ((fslot8 & 24u) == 0) tc2::wait_a(a_fin_empty + fslot8 + 24u, ph_f ^ 1);
+				T2E(4, 5);
+				tc2::sts64(a_fin + fslot8 * (4 * TC_M), m_run, s_run);
 				__syncwarp();
-				if (lane == 0) mbar_arrive(&fin_full[slot]);
-				++it_f;
+				if (lane == 0) tc2::arrive_a(a_fin_full + fslot8);
+				fslot8 = (fslot8 + 8u) & (8u * T2_FSLOTS - 1);
+				if (fslot8 == 0) ph_f ^= 1;
 				m_run = -3.0e38f;
 				s_run = 0.f;
 			};
 
 			for (int b = blk0; b < blk1; ++b) {
 				// ---- accumulator -> registers.  The only wait of the block: tm_full also covers the block's hard-entry list (producer).
-				tc2::wait(&tm_full[slot], ph_s);
+				T2E(4, 7);
+				tc2::wait_a(a_tm_full + slot8, ph_s);
 				tc2::fence_after();
+				T2E(0, 0);
 				uint32_t vr[32];
-				tc2::ld32_issue(lane_base + (uint32_t)(slot * TC_NB + cg * 32), vr);
-				const int4 *hl = hring + (size_t)hst * TC_HSTRIDE;
-				const int4 hd = hl[cg];                  // this warp's group: {first entry, end entry, flagged columns, valid-column mask}
+#if (SRB_T2_FAKE & 4)         /* timing experiment: the accumulator is never read */
+#pragma unroll
+				for (int i = 0; i < 32; ++i) vr[i] = 0x3f800000u + (uint32_t)b;
+				const int4 hd = make_int4(0, 0, 0, -1);
+#else
+				tc2::ld32_issue(t_ld + 16u * slot8, vr);
+				const int4 hd = tc2::lds128(a_hdr + hoff);   // this warp's group: {first entry, end entry, flagged columns, valid-column mask}
 				tc2::ld_wait();
+#endif
+				T2E(1, 0);
 				tc2::fence_before();
 				__syncwarp();
-				if (lane == 0) tc2::arrive_cluster(tm_empty_leader + 8u * (uint32_t)slot);      // the leader's MMA warp overwrites both CTAs' slots
+				if (lane == 0) tc2::arrive_cluster(tm_empty_leader + slot8);      // the leader's MMA warp overwrites both CTAs' slots
+				T2E(2, 1);
 				float v[32];
 #pragma unroll
 				for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vr[i]);
@@ -544,41 +696,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				// column's final entry -- park each column's sum in this thread's scratch slots (a dynamic column index cannot address
 				// registers), then subtract: the flagged columns are the group's FIRST hd.z columns, a multiple of four
 				if (hd.y > hd.x) {
-					const int4 *e = hl + TC_HHEAD + hd.x;
+					const uint32_t a_e = a_hdr - 16u * (uint32_t)cg + hoff + 16u * (uint32_t)(TC_HHEAD + hd.x);      // the group's first entry
 					const int n = hd.y - hd.x;
 					float csum = 0.f;
 #pragma unroll 1
 					for (int i = 0; i < n; i += 4) {      // four entries per step, all loads of a step ahead of its first scratch store
-						const int4 a0 = e[i], a1 = e[i + 1], a2 = e[i + 2], a3 = e[i + 3];
-						const float x0 = *reinterpret_cast<const float *>(xrow_b + a0.x), x1 = *reinterpret_cast<const float *>(xrow_b + a1.x);
-						const float x2 = *reinterpret_cast<const float *>(xrow_b + a2.x), x3 = *reinterpret_cast<const float *>(xrow_b + a3.x);
+						const int4 a0 = tc2::lds128(a_e + 16u * i), a1 = tc2::lds128(a_e + 16u * i + 16u), a2 = tc2::lds128(a_e + 16u * i + 32u), a3 = tc2::lds128(a_e + 16u * i + 48u);
+						const float x0 = tc2::lds32f(a_xrow + (uint32_t)a0.x), x1 = tc2::lds32f(a_xrow + (uint32_t)a1.x);
+						const float x2 = tc2::lds32f(a_xrow + (uint32_t)a2.x), x3 = tc2::lds32f(a_xrow + (uint32_t)a3.x);
 						const float t0 = fmaf(x0, __int_as_float(a0.y), __int_as_float(a0.z)), t1 = fmaf(x1, __int_as_float(a1.y), __int_as_float(a1.z));
 						const float t2 = fmaf(x2, __int_as_float(a2.y), __int_as_float(a2.z)), t3 = fmaf(x3, __int_as_float(a3.y), __int_as_float(a3.z));
 						csum = fmaf(t0, t0, csum);
 						if (a0.w) {
-							*reinterpret_cast<float *>(scr_b + a0.w) = csum;
+							tc2::sts32(a_scr_m1 + (uint32_t)a0.w, csum);
 							csum = 0.f;
 						}
 						csum = fmaf(t1, t1, csum);
 						if (a1.w) {
-							*reinterpret_cast<float *>(scr_b + a1.w) = csum;
+							tc2::sts32(a_scr_m1 + (uint32_t)a1.w, csum);
 							csum = 0.f;
 						}
 						csum = fmaf(t2, t2, csum);
 						if (a2.w) {
-							*reinterpret_cast<float *>(scr_b + a2.w) = csum;
+							tc2::sts32(a_scr_m1 + (uint32_t)a2.w, csum);
 							csum = 0.f;
 						}
 						csum = fmaf(t3, t3, csum);
 						if (a3.w) {
-							*reinterpret_cast<float *>(scr_b + a3.w) = csum;
+							tc2::sts32(a_scr_m1 + (uint32_t)a3.w, csum);
 							csum = 0.f;
 						}
 					}
 #pragma unroll
 					for (int c = 0; c < T2_MAX_FLAGGED / 4; ++c) {
 						if (4 * c < hd.z) {
-							const float4 t = *reinterpret_cast<const float4 *>(my_scr + 4 * c);
+							const float4 t = tc2::lds128f(a_scr + 16u * c);
 							v[4 * c] -= t.x;
 							v[4 * c + 1] -= t.y;
 							v[4 * c + 2] -= t.z;
@@ -587,13 +739,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 					}
 				}
 				const uint32_t vmask = (uint32_t)hd.w;
+				T2E(2, 2);
 				__syncwarp();
-				if (lane == 0) mbar_arrive(&empty_h[hst]);
-				if (++slot == T2_SLOTS) {
-					slot = 0;
+				if (lane == 0) tc2::arrive_a(a_empty_h + (hoff >> 8));
+				slot8 += 8u;
+				if (slot8 == 8u * T2_SLOTS) {
+					slot8 = 0;
 					ph_s ^= 1;
 				}
-				hst = (hst + 1) & (T2_HSTAGES - 1);
+				hoff = (hoff + TC_HSTRIDE * 16) & (T2_HSTAGES * TC_HSTRIDE * 16 - 1);
 				// ---- columns beyond a speaker's mixtures (row padding) take no part in the sum
 				if (vmask != 0xffffffffu) {
 #pragma unroll
@@ -602,7 +756,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				}
 				// column segmentation: seg >= 128 -> the block belongs to one speaker (quarter-wide merge at its end); seg == 64 ->
 				// two speakers per block, two warps each; seg == 32 -> every warp's group is its own speaker
-				tc2_lse_update<T2_POLY_EXP>(v, m_run, s_run);
+				T2E(2, 3);
+#if (SRB_T2_FAKE & 6)         /* timing experiments only: results are wrong */
+				m_run = v[0] + v[31];
+				s_run = 1.f;
+#else
+				if (single) tc2_lse_update<T2_POLY_EXP, true>(v, m_run, s_run);
+				else tc2_lse_update<T2_POLY_EXP, false>(v, m_run, s_run);
+#endif
+				T2E(3, 4);
+#if SRB_T2_PROF == 1
+				pf[7] += 1;
+#endif
 				if (seg < TC_NB) {
 					handoff();
 				} else {
@@ -614,6 +779,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 				}
 			}
 		}
+		T2P_FLUSH;
 #undef SRB_TC2_QBAR
 	}
 	tc2::fence_before();

@@ -32,6 +32,9 @@ constexpr int T2_HSTAGES = 8;        // ring of per-block hard-entry lists: the 
 constexpr int T2_THREADS = 640;      // 16 epilogue warps (0-15: TMEM lane quarter = warp % 4), 2 finisher warps, producer warp, MMA / relay warp
 constexpr int T2_WARP_FIN0 = 16, T2_WARP_PRODUCER = 18, T2_WARP_MMA = 19;
 constexpr int T2_FSLOTS = 8;         // ring of (max, sum) hand-overs from the epilogue warps to the finishers: [slot][4 groups][128 rows] float2
+constexpr int T2_PARTS = 2;          // row-sum partials per (frame tile, speaker): one per finisher warp (64 rows each)
+constexpr int T2_RED_SPK = 32;       // speakers whose per-row values a finisher parks before it takes their row sums (lane = speaker)
+constexpr int T2_RED_STRIDE = 65;    // floats per parked speaker: 64 rows + 1 (the 32 lanes of the row sum hit 32 different banks)
 constexpr int T2_MAX_FLAGGED = 16;   // flagged (exactly corrected) columns per 32-column group; the packer orders them first
 constexpr int T2_SCR_STRIDE = 20;    // floats per thread of add-back scratch: 16 slots, stride 20 keeps the 128-bit loads conflict-free
 #ifndef SRB_T2_POLY_EXP
@@ -40,6 +43,12 @@ constexpr int T2_SCR_STRIDE = 20;    // floats per thread of add-back scratch: 1
 constexpr int T2_POLY_EXP = SRB_T2_POLY_EXP;   // of every 32 exponentials of the epilogue, this many run as a polynomial on the FMA pipe instead of MUFU.EX2.
                                                // Measured on B200 (C2 x 64 utterances): 0 -> 3.28 ms, 8 -> 3.34 ms, 16 -> 3.65 ms: the epilogue is bound by
                                                // issue slots (0.58 IPC, 63 % MUFU), not by the MUFU unit, so the extra FMA instructions lose; kept switchable.
+#ifndef SRB_T2_PROF
+#define SRB_T2_PROF 0
+#endif
+#ifndef SRB_T2_FAKE
+#define SRB_T2_FAKE 0
+#endif
 constexpr float T2_X_CLAMP = 240.f;  // |x''| bound before squaring (fp16 max 65504)
 constexpr double T2_W_MAX = 60000.0; // |W| bound of an fp16 image entry; larger terms are added back exactly instead
 __host__ __device__ static inline int t2_kp(int D) { return ((2 * D + 1 + 15) / 16) * 16; }
