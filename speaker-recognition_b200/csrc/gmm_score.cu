@@ -300,12 +300,13 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 3 : 2) gmm_score_kern
 
 // sums[u][s] = sum over the frame tiles of utterance u (deterministic order); best[u] = first argmax_s
 // (over the first S_arg models: a speaker set may carry its UBM as an extra, unranked model at the end)
-__global__ void score_reduce_kernel(const double *__restrict__ partial, const int *__restrict__ utt_tile_start, int S, int S_arg, int parts,
+constexpr int SCORE_REDUCE_THREADS = 1024;      // one block per utterance: the more threads share a speaker's tiles, the shorter the serial sums
+__global__ void __launch_bounds__(SCORE_REDUCE_THREADS) score_reduce_kernel(const double *__restrict__ partial, const int *__restrict__ utt_tile_start, int S, int S_arg, int parts,
                                     double *__restrict__ sums, int *__restrict__ best) {
 	const int u = blockIdx.x;
 	const int t0 = utt_tile_start[u], t1 = utt_tile_start[u + 1];
-	__shared__ double sv[256];
-	__shared__ int si[256];
+	__shared__ double sv[SCORE_REDUCE_THREADS];
+	__shared__ int si[SCORE_REDUCE_THREADS];
 	double bestv = -1.0e300;
 	int besti = 0x7fffffff;
 	// tps threads per speaker (a power of two) split the utterance's tiles and are tree-summed: a long utterance scored against
@@ -494,7 +495,7 @@ int launch_score_tc_images(const Tc2Images &im, const float *dX, int ld, int D, 
 	TileTable *tt = nullptr;
 	if (get_table(utt_off, n_utt, im.S, 128, st, &tt)) return 1;
 	if (launch_score_tc2_images(im, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;
-	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, im.S, im.S, T2_PARTS, d_sums, d_best);
+	score_reduce_kernel<<<n_utt, SCORE_REDUCE_THREADS, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, im.S, im.S, T2_PARTS, d_sums, d_best);
 	SRB_CUDA(cudaGetLastError());
 	return 0;
 }
@@ -535,7 +536,7 @@ int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *ut
 		TileTable *tt = nullptr;
 		if (get_table(utt_off, n_utt, pm.S, 128, st, &tt)) return 1;
 		if (launch_score_tc2(pm, dX, ld, D, tt->d_ftiles, tt->n_ftiles, tt->d_partial, d_frame_ll, ldf, clamp, frame_log2, st)) return 1;
-		score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, pm.S_arg > 0 ? pm.S_arg : pm.S, T2_PARTS, d_sums, d_best);
+		score_reduce_kernel<<<n_utt, SCORE_REDUCE_THREADS, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, pm.S_arg > 0 ? pm.S_arg : pm.S, T2_PARTS, d_sums, d_best);
 		SRB_CUDA(cudaGetLastError());
 		return 0;
 	}
@@ -575,7 +576,7 @@ int launch_score(PackedModels &pm, const float *dX, int ld, int D, const int *ut
 		else gmm_score_kernel<true, 4><<<grid, 128, smem, st>>>(a);
 		SRB_CUDA(cudaGetLastError());
 	}
-	score_reduce_kernel<<<n_utt, 256, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, pm.S_arg > 0 ? pm.S_arg : pm.S, warps, d_sums, d_best);
+	score_reduce_kernel<<<n_utt, SCORE_REDUCE_THREADS, 0, st>>>(tt->d_partial, tt->d_utt_tile_start, pm.S, pm.S_arg > 0 ? pm.S_arg : pm.S, warps, d_sums, d_best);
 	SRB_CUDA(cudaGetLastError());
 	return 0;
 }

@@ -491,17 +491,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 			const int n_entries = seg >= TC_NB ? (blk1 - blk0) / A.blocks_per_spk : (blk1 - blk0);
 			auto flush = [&]() {
 				__syncwarp();
-				if (tile_ok && lane < cnt && base + lane < A.S) {
-					const float *r = tb + lane * T2_RED_STRIDE;
+				if (cnt > 0) {
+					// g = 32 / (cnt rounded up to a power of two) lanes share a speaker: each sums every g-th row, then a shuffle tree
+					// over the g lanes (a full buffer: g = 1, lane = speaker, no shuffles; one speaker -- the E-step's pass A -- g = 32)
+					int cp = 1;
+					while (cp < cnt) cp <<= 1;
+					const int g = 32 / cp, sl = lane / g, j = lane - sl * g;
 					float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-					for (int i = 0; i < 64; i += 4) {
-						a0 += r[i];
-						a1 += r[i + 1];
-						a2 += r[i + 2];
-						a3 += r[i + 3];
+					if (sl < cnt) {
+						const float *r = tb + sl * T2_RED_STRIDE;
+						for (int i = j; i < 64; i += 4 * g) {
+							a0 += r[i];
+							if (i + g < 64) a1 += r[i + g];
+							if (i + 2 * g < 64) a2 += r[i + 2 * g];
+							if (i + 3 * g < 64) a3 += r[i + 3 * g];
+						}
 					}
-					A.partial[((size_t)tile * A.S + base + lane) * T2_PARTS + f] = (double)((a0 + a1) + (a2 + a3));
+					float tot = (a0 + a1) + (a2 + a3);
+					for (int off = g >> 1; off >= 1; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+					if (tile_ok && j == 0 && sl < cnt && base + sl < A.S) A.partial[((size_t)tile * A.S + base + sl) * T2_PARTS + f] = (double)tot;
 				}
 				__syncwarp();
 				base += cnt;

@@ -461,35 +461,37 @@ __global__ void __launch_bounds__(1024) mfcc_stats_kernel(const double *__restri
 }
 
 // CMVN (MFCC.py:74-77) + diff_feature (utils.py:24-31).  Output row r of utterance u uses raw frames r+nd, r+nd-1, r+nd-2.
+// thread = (output row, cepstral coefficient i): one read of c[t], c[t-1], c[t-2] serves the row's static, delta and delta-delta
+// columns (the same float64 arithmetic as one thread per output element, which this kernel replaced: 2.5x fewer threads, no
+// per-element divisions); columns beyond (nd + 1) nc are zero-filled up to ld
 __global__ void mfcc_norm_kernel(const float *__restrict__ ceps, int CL, const double *__restrict__ stats,
                                  const int *__restrict__ frame_off, const int *__restrict__ feat_off, int n_utt, int nc,
-                                 int nd, int cmvn, float *__restrict__ feat, int ld, long long total) {
+                                 int nd, int cmvn, float *__restrict__ feat, int ld, long long total_rows) {
 	const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= total) return;
-	const int row = (int)(idx / ld), col = (int)(idx - (long long)row * ld);
+	const long long row_ll = idx / CL;
+	if (row_ll >= total_rows) return;
+	const int row = (int)row_ll, i = (int)(idx - row_ll * CL);
+	float *out = feat + (size_t)row * ld;
+	for (int c = (nd + 1) * nc + i; c < ld; c += CL) out[c] = 0.f;
+	if (i >= nc) return;
 	const int u = find_segment(feat_off, n_utt, row);
 	const int T_u = frame_off[u + 1] - frame_off[u];
 	const int t = frame_off[u] + (row - feat_off[u]) + nd;   // raw frame index (global)
-	const int k = col / nc, i = col - k * nc;
-	float v = 0.f;
-	if (k <= nd) {
-		double mean = 0.0, inv = 1.0;
-		if (cmvn && T_u > 1) {
-			mean = stats[(size_t)u * 2 * nc + i];
-			inv = stats[(size_t)u * 2 * nc + nc + i];
-		}
-		const double c0 = (double)ceps[(size_t)t * CL + i];
-		if (k == 0) v = (float)((c0 - mean) * inv);
-		else {
-			const double c1 = (double)ceps[(size_t)(t - 1) * CL + i];
-			if (k == 1) v = (float)((c0 - c1) * inv);
-			else {
-				const double c2 = (double)ceps[(size_t)(t - 2) * CL + i];
-				v = (float)((c0 - 2.0 * c1 + c2) * inv);
-			}
+	double mean = 0.0, inv = 1.0;
+	if (cmvn && T_u > 1) {
+		mean = stats[(size_t)u * 2 * nc + i];
+		inv = stats[(size_t)u * 2 * nc + nc + i];
+	}
+	const double c0 = (double)ceps[(size_t)t * CL + i];
+	out[i] = (float)((c0 - mean) * inv);
+	if (nd >= 1) {
+		const double c1 = (double)ceps[(size_t)(t - 1) * CL + i];
+		out[nc + i] = (float)((c0 - c1) * inv);
+		if (nd >= 2) {
+			const double c2 = (double)ceps[(size_t)(t - 2) * CL + i];
+			out[2 * nc + i] = (float)((c0 - 2.0 * c1 + c2) * inv);
 		}
 	}
-	feat[idx] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -881,10 +883,10 @@ int launch_mfcc(MfccPlan *p, const void *d_pcm, int is_f32, const long long *smp
 		mfcc_stats_kernel<<<n_utt, 1024, 0, st>>>(p->partials.as<double>(), s->d_cta_start, s->d_frame_off, p->nc, p->stats.as<double>());
 		SRB_CUDA(cudaGetLastError());
 	}
-	const long long total = (long long)s->rows_total * ld;
+	const long long total = (long long)s->rows_total * p->CL;
 	const int blocks = (int)((total + 255) / 256);
 	mfcc_norm_kernel<<<blocks, 256, 0, st>>>(p->ceps.as<float>(), p->CL, p->stats.as<double>(), s->d_frame_off, s->d_feat_off, n_utt, p->nc, nd, cmvn,
-	                                        d_feat, ld, total);
+	                                        d_feat, ld, (long long)s->rows_total);
 	SRB_CUDA(cudaGetLastError());
 	if (feat_off) memcpy(feat_off, s->feat_off.data(), sizeof(int) * (n_utt + 1));
 	return 0;
