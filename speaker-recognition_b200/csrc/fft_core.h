@@ -26,6 +26,31 @@ struct alignas(8) cpx {
 SRB_HD cpx cadd(cpx a, cpx b) { return cpx{a.x + b.x, a.y + b.y}; }
 SRB_HD cpx csub(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
 SRB_HD cpx cmul(cpx a, cpx b) { return cpx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+// complex add / subtract as ONE packed fp32x2 instruction on the device (sm_100 FADD2: both halves round to nearest exactly like two
+// scalar adds, so host replay and device agree bit for bit); a complex value lives in an aligned register pair, the moves are renames
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ cpx cadd2(cpx a, cpx b) {
+	unsigned long long ra, rb, rc;
+	cpx c;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+	asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(rc));
+	return c;
+}
+__device__ __forceinline__ cpx csub2(cpx a, cpx b) {
+	unsigned long long ra, rb, rc;
+	cpx c;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+	asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+	asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(c.x), "=f"(c.y) : "l"(rc));
+	return c;
+}
+#else
+SRB_HD cpx cadd2(cpx a, cpx b) { return cadd(a, b); }
+SRB_HD cpx csub2(cpx a, cpx b) { return csub(a, b); }
+#endif
 SRB_HD cpx cmulj_neg(cpx a) { return cpx{a.y, -a.x}; }   // a * (-i)
 
 // One Stockham radix-4 pass over `batch` independent M-point transforms laid out [batch][M].
@@ -114,11 +139,11 @@ SRB_HD void power_unpack(const cpx *Z, float *P, int M, int batch, int p_stride,
 
 // forward 4-point DFT, outputs in natural order
 SRB_HD void dft4(cpx &a, cpx &b, cpx &c, cpx &d) {
-	const cpx apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d);
-	const cpx jbmd = cmulj_neg(csub(b, d));      // -i (b - d)
-	a = cadd(apc, bpd);
+	const cpx apc = cadd2(a, c), amc = csub2(a, c), bpd = cadd2(b, d);
+	const cpx jbmd = cmulj_neg(csub2(b, d));     // -i (b - d): the swap of the halves keeps these two scalar
+	a = cadd2(apc, bpd);
 	b = cadd(amc, jbmd);
-	c = csub(apc, bpd);
+	c = csub2(apc, bpd);
 	d = csub(amc, jbmd);
 }
 
@@ -159,16 +184,20 @@ SRB_HD void dft16(const cpx *v, cpx *o) {
 
 // ---- warp-per-frame layout (mfcc.cu mfcc_frames_warp_kernel): one warp owns one frame; lane = (h, u), h = lane >> 4 the half,
 // u = lane & 15; the half-warps run the sub-transforms r = h (round 0) and r = h + 2 (round 1).  All buffers are per warp:
-//   T / Zs   4 tiles of 256 complex elements, tile r at r * 256.  Transpose tile: element (row, col) at row * 16 + (col ^ row)
-//            (XOR swizzle: both the column writes of step A and the column reads of step B touch 16 distinct bank pairs);
-//            sub-transform output Y_r[q] IN PLACE over the same tile at q ^ (4 r) (the XOR makes the four r of neighbouring bins
-//            fall into different bank pairs when the power stage reads Z[k] = Y_{k & 3}[k >> 2] with consecutive k per lane)
+//   T / Zs   4 tiles, tile r at r * WF_TILE complex elements.  Transpose tile: element (row, col) at row * 17 + col -- a PADDED row
+//            (17 elements) instead of an XOR swizzle: the column writes of step A (lanes = rows) and the column reads of step B
+//            (lanes = columns) still touch 16 distinct bank pairs, and every address is a per-lane base plus a compile-time
+//            constant (the swizzle cost a LOP3 + LEA per access: ~350 integer instructions per frame);
+//            sub-transform output Y_r[q] IN PLACE over the same tile, at (q >> 4) * 17 + (q & 15); the tile stride 276 = 4 (mod 16)
+//            makes the four r of neighbouring bins fall into different bank pairs when the power stage reads Z[k] = Y_{k & 3}[k >> 2]
+//            with consecutive k per lane (tests/test_fft_schedule_cpu.py counts the wavefronts of every access pattern)
 //   P        power spectrum, bins 0..1024, bin k at k + 4 (k >> 4): every run of 16 bins is skewed by 16 bytes, so that the
 //            128-bit reads of the mel stage (lanes on segments that start 16 bins apart) spread over the banks
-constexpr int WF_TILE = 256;
+constexpr int WF_TROW = 17;
+constexpr int WF_TILE = 276;
 constexpr int WF_PLEN = 1296;           // floats: skewed bins 0..1024 (1024 + 4 * 64 + 1) plus the 16-bin reach of a mel segment that starts on the last 4-bin group
-SRB_HD int wf_t_index(int row, int col) { return row * 16 + (col ^ row); }
-SRB_HD int wf_z_index(int r, int q) { return r * WF_TILE + (q ^ (4 * r)); }
+SRB_HD int wf_t_index(int row, int col) { return row * WF_TROW + col; }
+SRB_HD int wf_z_index(int r, int q) { return r * WF_TILE + q + (q >> 4); }
 SRB_HD int wf_p_index(int k) { return k + 4 * (k >> 4); }
 
 // step A for (r, u): z[n2] = packed frame element u + 16 n2 (loaded once by the caller and used for both rounds), tw1r = row r of
@@ -190,7 +219,7 @@ SRB_HD void wf_step_b_store(const cpx (&in)[16], cpx *Z, int r, int u) {
 	cpx out[16];
 	dft16(in, out);
 #pragma unroll
-	for (int q1 = 0; q1 < 16; ++q1) Z[wf_z_index(r, 16 * q1 + u)] = out[q1];
+	for (int q1 = 0; q1 < 16; ++q1) Z[r * WF_TILE + q1 * WF_TROW + u] = out[q1];      // = wf_z_index(r, 16 q1 + u), u < 16
 }
 // bins k and 1024 - k of the real 2048-point power spectrum from ONE pair of packed results: with e = Z[k] + conj(Z[1024-k]),
 // o = Z[k] - conj(Z[1024-k]), w = exp(-2 pi i k / 2048), (a, b) = w o:
@@ -200,7 +229,7 @@ SRB_HD void wf_power_pair(const cpx *Z, int k, cpx w, float &pk, float &pmk) {
 	const cpx zk = Z[wf_z_index(k & 3, k >> 2)];
 	cpx zc = Z[wf_z_index(km & 3, km >> 2)];
 	zc.y = -zc.y;
-	const cpx e = cadd(zk, zc), o = csub(zk, zc);
+	const cpx e = cadd2(zk, zc), o = csub2(zk, zc);
 	const cpx wo = cmul(w, o);
 	const float yr = 0.5f * (e.x + wo.y), yi = 0.5f * (e.y - wo.x);
 	const float mr = 0.5f * (e.x - wo.y), mi = 0.5f * (e.y + wo.x);

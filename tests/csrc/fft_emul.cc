@@ -61,3 +61,8 @@ extern "C" void emul_warp_power_spectrum(const float *y, int batch, float *P) {
 		for (int k = 0; k <= 1024; ++k) P[(size_t)b * 1025 + k] = Ps[wf_p_index(k)];
 	}
 }
+
+// the layout functions themselves, for the shared-memory wavefront count of tests/test_fft_schedule_cpu.py
+extern "C" int emul_wf_t_index(int row, int col) { return wf_t_index(row, col); }
+extern "C" int emul_wf_z_index(int r, int q) { return wf_z_index(r, q); }
+extern "C" int emul_wf_tile() { return WF_TILE; }

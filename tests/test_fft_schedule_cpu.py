@@ -54,3 +54,40 @@ def test_warp_per_frame_power_spectrum_matches_numpy(emul):
     assert np.all(P >= 0)
     assert np.max(np.abs(P - ref) / scale) < 2e-6
     assert np.all(P[2] == 0)
+
+
+def _wavefronts(addrs, width):
+    """shared-memory wavefronts of one warp-wide access: 32 banks of 4 bytes; a 64-bit access is served one half-warp at a time;
+    within a phase a bank takes one wavefront per DISTINCT word mapped to it"""
+    lanes_per_phase = {4: 32, 8: 16, 16: 8}[width]
+    tot = 0
+    for p in range(0, 32, lanes_per_phase):
+        bank = {}
+        for a in addrs[p:p + lanes_per_phase]:
+            for w in range(width // 4):
+                bank.setdefault((a // 4 + w) % 32, set()).add(a // 4 + w)
+        tot += max(len(v) for v in bank.values())
+    return tot
+
+
+def test_warp_per_frame_tiles_are_bank_conflict_free(emul):
+    """the transpose tiles of the warp-per-frame FFT (fft_core.h wf_t_index / wf_z_index: padded rows, tile stride 4 mod 16): every
+    column write of step A, column read and in-place write of step B and the power stage's Z[k] reads cost exactly the two
+    wavefronts a 64-bit access needs; the mirrored reads Z[1024 - k] cost at most four"""
+    ti, zi, TS = emul.emul_wf_t_index, emul.emul_wf_z_index, emul.emul_wf_tile()
+    assert TS % 16 == 4 and TS >= 16 * 17
+    lanes = [(l >> 4, l & 15) for l in range(32)]
+    for rnd in range(2):
+        for c in range(16):
+            assert _wavefronts([8 * ((h + 2 * rnd) * TS + ti(u, c)) for h, u in lanes], 8) == 2          # step A store, column q2 = c
+            assert _wavefronts([8 * ((h + 2 * rnd) * TS + ti(c, u)) for h, u in lanes], 8) == 2          # step B load, row n1 = c
+            assert _wavefronts([8 * zi(h + 2 * rnd, 16 * c + u) for h, u in lanes], 8) == 2               # step B store, q1 = c
+            # in place: a lane stores exactly where it loaded
+            for h, u in lanes:
+                r = h + 2 * rnd
+                assert sorted(zi(r, 16 * q1 + u) for q1 in range(16)) == sorted(r * TS + ti(n1, u) for n1 in range(16))
+    for i in range(16):
+        ks = [l + 32 * i for l in range(32)]
+        assert _wavefronts([8 * zi(k & 3, k >> 2) for k in ks], 8) == 2
+        kms = [(1024 - k) & 1023 for k in ks]
+        assert _wavefronts([8 * zi(k & 3, k >> 2) for k in kms], 8) <= 4
