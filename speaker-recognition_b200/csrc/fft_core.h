@@ -133,6 +133,7 @@ SRB_HD void power_unpack(const cpx *Z, float *P, int M, int batch, int p_stride,
 // Register-resident building blocks of the fast MFCC path (M = 1024, at most 256 non-zero packed inputs):
 // the zero-padded 1024-point transform splits exactly into four 256-point transforms of pre-twiddled inputs,
 //     Z[4q + r] = sum_{n<256} (z[n] W_1024^{n r}) W_256^{n q},        r = 0..3, q = 0..255,
+// tables: wf_c[r][n2] = W_64^{n2 r} (4 x 16) and wf_t[j][u] = W_1024^{u j} (64 x 16, j = r + 4 q2), see wf_step_a,
 // and each 256-point transform is two radix-16 steps held in registers (16 threads x 16 points) with one
 // transpose through shared memory in between.
 // ------------------------------------------------------------------------------------------------
@@ -200,15 +201,17 @@ SRB_HD int wf_t_index(int row, int col) { return row * WF_TROW + col; }
 SRB_HD int wf_z_index(int r, int q) { return r * WF_TILE + q + (q >> 4); }
 SRB_HD int wf_p_index(int k) { return k + 4 * (k >> 4); }
 
-// step A for (r, u): z[n2] = packed frame element u + 16 n2 (loaded once by the caller and used for both rounds), tw1r = row r of
-// the first twiddle table W_1024^{n r} (row 0 is all ones), twA[q2][u] = W_256^{u q2}; result into tile r of T
-SRB_HD void wf_step_a(const cpx (&z)[16], const cpx *tw1r, const cpx *twA, cpx *Ttile, int u) {
+// step A for (r, u): z[n2] = packed frame element u + 16 n2 (loaded once by the caller and used for both rounds).  The pre-twiddle
+// W_1024^{(u + 16 n2) r} is split into W_64^{n2 r} -- cr[n2], the same for all 16 lanes of a half-warp: one broadcast wavefront per
+// load -- and W_1024^{u r}, which is linear in the transform and merges with the inter-step twiddle W_256^{u q2} into ONE table
+// tTr[q2 * 64 + u] = W_1024^{u (r + 4 q2)} (the caller passes row r of the [64][16] table W_1024^{u j}); result into tile r of T
+SRB_HD void wf_step_a(const cpx (&z)[16], const cpx *cr, const cpx *tTr, cpx *Ttile, int u) {
 	cpx in[16], out[16];
 #pragma unroll
-	for (int n2 = 0; n2 < 16; ++n2) in[n2] = cmul(z[n2], tw1r[u + 16 * n2]);
+	for (int n2 = 0; n2 < 16; ++n2) in[n2] = cmul(z[n2], cr[n2]);
 	dft16(in, out);
 #pragma unroll
-	for (int q2 = 0; q2 < 16; ++q2) Ttile[wf_t_index(u, q2)] = cmul(out[q2], twA[q2 * 16 + u]);
+	for (int q2 = 0; q2 < 16; ++q2) Ttile[wf_t_index(u, q2)] = cmul(out[q2], tTr[q2 * 64 + u]);
 }
 // step B for (r, u), in place: all 16 lanes of the half-warp load, (warp barrier), then transform and store Y_r[16 q1 + u]
 SRB_HD void wf_step_b_load(const cpx *Ttile, int u, cpx (&in)[16]) {

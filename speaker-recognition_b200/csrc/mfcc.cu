@@ -233,7 +233,7 @@ constexpr int MFW_YLEN = 512;                     // longest frame of the fast p
 constexpr int MFW_TW2 = 520;                      // unpack twiddles k = 0..512 (padded)
 constexpr int MFW_STAGE_SAMPLES = 544;            // raw samples of one frame incl. the one before it, rounded out to 16-byte blocks (<= 67 x 8)
 constexpr size_t MFW_STAGE_BYTES = 2 * MFW_STAGE_SAMPLES * sizeof(int16_t);      // two int16 buffers (double-buffered), or one float buffer
-constexpr size_t MFW_CTAB_BYTES = (size_t)(4 * 256 + 256 + MFW_TW2) * sizeof(cpx);
+constexpr size_t MFW_CTAB_BYTES = (size_t)(4 * 16 + 64 * 16 + MFW_TW2) * sizeof(cpx);      // W_64^{n2 r} | W_1024^{u j} | unpack twiddles
 constexpr size_t MFW_WARP_BYTES = MFW_STAGE_BYTES + (size_t)srbfft::WF_PLEN * sizeof(float) + (size_t)4 * srbfft::WF_TILE * sizeof(cpx);
 // mel / DCT tables in shared memory: first bins int[n_segp] | weights float4[4][n_segp] | segptr int[nbp] | logfloor float[nbp] | dct double[nb][16]
 static inline size_t mfw_mel_bytes(int n_seg, int nb) {
@@ -254,9 +254,9 @@ __global__ void __launch_bounds__(MFW_THREADS, 1) mfcc_frames_warp_kernel(const 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int L = A.L, nb = A.nb, nc = A.nc, shift = A.shift, n_seg = A.n_seg;
 	const int n_segp = (n_seg + 3) & ~3, nbp = (nb + 1 + 3) & ~3;
-	cpx *s_tw1 = reinterpret_cast<cpx *>(mf_smem);          // [4][256] W_1024^{n r} (row 0 = 1)
-	cpx *s_twA = s_tw1 + 4 * 256;                           // [16][16]  W_256^{u q2}
-	cpx *s_tw2 = s_twA + 256;                               // [0..512]  exp(-2 pi i k / 2048)
+	cpx *s_tw1 = reinterpret_cast<cpx *>(mf_smem);          // [4][16]  W_64^{n2 r}: the half-warp-uniform part of the pre-twiddle
+	cpx *s_twA = s_tw1 + 4 * 16;                            // [64][16] W_1024^{u j}, j = r + 4 q2: the rest of it merged with the inter-step twiddle
+	cpx *s_tw2 = s_twA + 64 * 16;                           // [0..512] exp(-2 pi i k / 2048)
 	int *s_segfirst = reinterpret_cast<int *>(s_tw2 + MFW_TW2);             // [n_segp] first bin of every 16-bin segment (multiple of 4)
 	float4 *s_w16 = reinterpret_cast<float4 *>(s_segfirst + n_segp);        // [4][n_segp] segment weights, quarter-major
 	int *s_segptr = reinterpret_cast<int *>(s_w16 + 4 * n_segp);            // [nb + 1]
@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(MFW_THREADS, 1) mfcc_frames_warp_kernel(const 
 	float *Pb = reinterpret_cast<float *>(wb + MFW_STAGE_BYTES);            // [WF_PLEN] windowed frame (first 512 floats), then the skewed power spectrum
 	cpx *TZ = reinterpret_cast<cpx *>(Pb + srbfft::WF_PLEN);                // [4][256] transpose tiles / sub-transform outputs, later the mel scratch
 
-	for (int i = tid; i < 4 * 256; i += MFW_THREADS) s_tw1[i] = i < 256 ? cpx{1.f, 0.f} : A.tw1[i - 256];
-	for (int i = tid; i < 256; i += MFW_THREADS) s_twA[i] = A.twA[i];
+	for (int i = tid; i < 4 * 16; i += MFW_THREADS) s_tw1[i] = A.tw1[i];
+	for (int i = tid; i < 64 * 16; i += MFW_THREADS) s_twA[i] = A.twA[i];
 	for (int i = tid; i <= 512; i += MFW_THREADS) s_tw2[i] = A.tw2[i];
 	for (int i = tid; i < n_seg; i += MFW_THREADS) s_segfirst[i] = A.mel_seg[i].x;
 	for (int i = tid; i < 4 * n_seg; i += MFW_THREADS) s_w16[(i / n_seg) * n_segp + (i % n_seg)] = reinterpret_cast<const float4 *>(A.mel_w16)[i];
@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(MFW_THREADS, 1) mfcc_frames_warp_kernel(const 
 				const cpx *yb = reinterpret_cast<const cpx *>(Pb);
 #pragma unroll
 				for (int n2 = 0; n2 < 16; ++n2) z[n2] = yb[u + 16 * n2];
-				srbfft::wf_step_a(z, s_tw1 + h * 256, s_twA, TZ + h * srbfft::WF_TILE, u);
-				srbfft::wf_step_a(z, s_tw1 + (h + 2) * 256, s_twA, TZ + (h + 2) * srbfft::WF_TILE, u);
+				srbfft::wf_step_a(z, s_tw1 + h * 16, s_twA + h * 16, TZ + h * srbfft::WF_TILE, u);
+				srbfft::wf_step_a(z, s_tw1 + (h + 2) * 16, s_twA + (h + 2) * 16, TZ + (h + 2) * srbfft::WF_TILE, u);
 			}
 			__syncwarp();
 			// ---- second radix-16 step, in place tile by tile
@@ -588,12 +588,11 @@ static int build_tables(MfccPlan *p) {
 		for (int j = ptr[b] + 1; j < ptr[b + 1]; ++j)
 			if (col[j] != col[j - 1] + 1) p->fast = false;
 	if (p->fast) {
-		std::vector<cpx> tw1(3 * 256), twA(256);
-		for (int r = 1; r < 4; ++r)
-			for (int n = 0; n < 256; ++n)
-				tw1[(r - 1) * 256 + n] = cpx{(float)cos(-2.0 * M_PI * n * r / 1024), (float)sin(-2.0 * M_PI * n * r / 1024)};
-		for (int q2 = 0; q2 < 16; ++q2)
-			for (int u = 0; u < 16; ++u) twA[q2 * 16 + u] = cpx{(float)cos(-2.0 * M_PI * u * q2 / 256), (float)sin(-2.0 * M_PI * u * q2 / 256)};
+		std::vector<cpx> tw1(4 * 16), twA(64 * 16);      // W_64^{n2 r} and W_1024^{u j} (fft_core.h wf_step_a)
+		for (int r = 0; r < 4; ++r)
+			for (int n2 = 0; n2 < 16; ++n2) tw1[r * 16 + n2] = cpx{(float)cos(-2.0 * M_PI * n2 * r / 64), (float)sin(-2.0 * M_PI * n2 * r / 64)};
+		for (int j = 0; j < 64; ++j)
+			for (int u = 0; u < 16; ++u) twA[j * 16 + u] = cpx{(float)cos(-2.0 * M_PI * u * j / 1024), (float)sin(-2.0 * M_PI * u * j / 1024)};
 		// 16-bin segments of the runs, each starting on a 4-bin boundary (see the mel stage of mfcc_frames_warp_kernel)
 		std::vector<int2> seg;
 		std::vector<float> w16;

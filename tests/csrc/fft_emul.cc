@@ -34,11 +34,11 @@ extern "C" int emul_power_spectrum(const float *y, int N, int batch, int n_worke
 // transpose tiles, in-place step B, paired power unpack; P = power spectrum [batch][1025] natural order (de-skewed here)
 extern "C" void emul_warp_power_spectrum(const float *y, int batch, float *P) {
 	const int N = 2048, M = 1024;
-	std::vector<cpx> tw1(4 * 256), twA(256), tw2(513);
+	std::vector<cpx> wc(4 * 16), wt(64 * 16), tw2(513);
 	for (int r = 0; r < 4; ++r)
-		for (int n = 0; n < 256; ++n) tw1[r * 256 + n] = cpx{(float)std::cos(-2.0 * M_PI * n * r / 1024), (float)std::sin(-2.0 * M_PI * n * r / 1024)};
-	for (int q2 = 0; q2 < 16; ++q2)
-		for (int u = 0; u < 16; ++u) twA[q2 * 16 + u] = cpx{(float)std::cos(-2.0 * M_PI * u * q2 / 256), (float)std::sin(-2.0 * M_PI * u * q2 / 256)};
+		for (int n2 = 0; n2 < 16; ++n2) wc[r * 16 + n2] = cpx{(float)std::cos(-2.0 * M_PI * n2 * r / 64), (float)std::sin(-2.0 * M_PI * n2 * r / 64)};
+	for (int j = 0; j < 64; ++j)
+		for (int u = 0; u < 16; ++u) wt[j * 16 + u] = cpx{(float)std::cos(-2.0 * M_PI * u * j / 1024), (float)std::sin(-2.0 * M_PI * u * j / 1024)};
 	for (int k = 0; k <= 512; ++k) tw2[k] = cpx{(float)std::cos(-2.0 * M_PI * k / N), (float)std::sin(-2.0 * M_PI * k / N)};
 	(void)M;
 	for (int b = 0; b < batch; ++b) {
@@ -50,7 +50,7 @@ extern "C" void emul_warp_power_spectrum(const float *y, int batch, float *P) {
 				const int h = lane >> 4, u = lane & 15, r = h + 2 * round;
 				cpx z[16];
 				for (int n2 = 0; n2 < 16; ++n2) z[n2] = ybuf[u + 16 * n2];
-				wf_step_a(z, tw1.data() + r * 256, twA.data(), TZ.data() + r * WF_TILE, u);
+				wf_step_a(z, wc.data() + r * 16, wt.data() + r * 16, TZ.data() + r * WF_TILE, u);
 			}
 		for (int round = 0; round < 2; ++round) {
 			cpx regs[32][16];
