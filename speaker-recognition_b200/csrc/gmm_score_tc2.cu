@@ -25,7 +25,7 @@ bool tc2_supported(const PackedModels &pm, int D) {
 	return !pm.h_tc2.empty() && pm.tc2_Kp == t2_kp(D) && pm.tc2_Kp <= T2_KP_MAX && tc2_stages(pm.tc2_Kp, D) > 0;
 }
 
-// d_ftiles: frame tiles of TC_M frames (device), d_partial: [n_ftiles][S][4] doubles
+// d_ftiles: frame tiles of TC_M frames (device), d_partial: [n_ftiles][S][T2_PARTS] doubles (the caller sizes it for 4 parts: the FMA route)
 int launch_score_tc2(PackedModels &pm, const float *dX, int ld, int D, const int4 *d_ftiles, int n_ftiles, double *d_partial, float *d_frame_ll,
                      int ldf, int clamp, int frame_log2, cudaStream_t st) {
 	Context &c = ctx();

@@ -20,18 +20,23 @@
 // to ~1400 cycles per block against 960 of tensor time, ncu):
 //   warp 18 producer (both CTAs): cp.async.bulk of the block's hard-entry list and of this CTA's half block (fp16 head image and
 //           tail image, one 256 Kp-byte copy) into a ring of up to 6 stages
-//   warp 19 leader CTA: MMA issuer -- waits for its own stage and for the peer's (relayed), issues 3 x Kp/16
-//           tcgen05.mma.cta_group::2.kind::f16 (M 256 = 2 x 128, N 128, K 16) with the A operand (PHI head | tail) in TENSOR MEMORY,
-//           tcgen05.commit multicast to both CTAs frees the stage and publishes the accumulator slot (three 128-column slots)
+//   warp 19 leader CTA: MMA issuer -- waits for its own stage and for the peer's (relayed), then ONE elected lane issues the block's
+//           3 x Kp/16 tcgen05.mma.cta_group::2.kind::f16 (M 256 = 2 x 128, N 128, K 16) with the A operand (PHI head | tail) in TENSOR
+//           MEMORY and both commits (multicast to both CTAs: free the stage, publish the accumulator slot -- three 128-column slots);
+//           with one election per block the operands stay in uniform registers (15 UTCHMMA back to back in SASS)
 //           peer CTA: relay -- forwards "my half of stage s has landed" to the leader with a remote mbarrier arrive
 //   warps 0-15 epilogue, thread = frame row = TMEM lane, the four warps of a lane quarter own the four 32-column groups of every
 //           block: per unit they build PHI (global -> registers -> tcgen05.st) and keep the raw x'' in shared memory; per block
-//           they sum the hard entries' t^2 per column while the MMAs run, tcgen05.ld the accumulator, release the slot (remote
-//           arrive on the leader's barrier), subtract the exact terms, and fold the 32 values into an online log2-sum-exp2;
-//           at a speaker's end every warp hands its (max, sum) to the finishers through a shared-memory ring -- no barrier
-//           between the epilogue warps (round 1: a named barrier per block and the merge on one of the four warps)
-//   warps 16-17 finishers (64 rows each): merge the four column groups of a speaker, log2, clamp, per-frame output and the
-//           per-(tile, speaker, lane quarter) partial sums
+//           they tcgen05.ld the accumulator, release the slot (remote arrive on the leader's barrier), subtract the exact terms of
+//           the hard entries (t^2 summed per flagged column through per-thread scratch), and fold the 32 values into an online
+//           log2-sum-exp2; at a speaker's end every warp hands its (max, sum) to the finishers through a shared-memory ring -- no
+//           barrier between the epilogue warps.  All shared-memory and barrier accesses of the block loop use 32-bit shared-window
+//           addresses computed once per thread (a generic pointer costs an S2R CgaCtaId + LEA conversion per use in a cluster kernel)
+//   warps 16-17 finishers (64 rows each): merge the four column groups of a speaker, log2, clamp, per-frame output; the row's value
+//           is parked in shared memory and the per-(tile, speaker) row sums are taken 32 speakers at a time with lane = speaker
+// What bounds the kernel (measured: DESIGN.md 4.1a, profiles/r2g_scorer_ab.txt): the serial per-block chain of an epilogue warp, not
+// the tensor pipe, the MUFU unit or the instruction count.  SRB_T2_PROF builds count cycles per warp role, SRB_T2_FAKE builds leave
+// out parts of the work (timing only, wrong results) -- experiments/ab_build.py, experiments/tc2_prof.py.
 // B images are K-major in the no-swizzle canonical layout (8-row x 16-byte core matrices = 8 rows x 8 halfs; LBO = 1024 B between
 // K-adjacent core matrices of a 64-row half block, SBO = 128 B between 8-row groups), stored in HBM in shared-memory order.
 #pragma once
@@ -57,7 +62,7 @@ struct Tc2Args {
 	int spk_per_chunk;
 	float *frame_ll;           // optional [S][ldf]
 	int ldf;
-	double *partial;           // [n_ftiles][S][4]
+	double *partial;           // [n_ftiles][S][T2_PARTS]: one row sum per finisher warp
 	int clamp, frame_log2;
 	int D;
 	int bstages;               // B ring depth
