@@ -683,7 +683,7 @@ def main():
                          "algorithmic_flops_per_frame": mfcc_flops_frame, "frames": raw_frames,
                          "hbm_gbs": (2.0 * 256 + 4.0 * N_CEPS) * raw_frames / (feat_ms * 1e-3) / 1e9,
                          "note": "FFT butterflies are add-heavy (no FMA pairing), so the FMA-pipe fraction understates the issue-slot use; "
-                                 "neither HBM (%.1f %% of peak) nor the FMA pipe binds: the kernel is issue/latency-bound (profiles/)"
+                                 "neither HBM (%.1f %% of peak) nor the FMA pipe binds: the kernel is bound by the shared-memory pipe (88 %% l1tex throughput, profiles/r2g_mfcc_warp.txt)"
                                  % (100.0 * (2.0 * 256 + 4.0 * N_CEPS) * raw_frames / (feat_ms * 1e-3) / 1e9 / hbm_peak)}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
