@@ -669,6 +669,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) gmm_s
 			// end of a speaker segment: this warp's running (max, sum) of its 32-column group goes to the finishers.  The ring is
 			// checked once per FOUR hand-overs (the finishers release in order: the last slot of the next four being free means all are)
 			auto handoff = [&]() {
+				// (waiting for the slot about to be written at EVERY hand-over instead -- a full ring of slack -- measured 0.5 % slower)
 				if ((fslot8 & 24u) == 0) tc2::wait_a(a_fin_empty + fslot8 + 24u, ph_f ^ 1);
 				T2E(4, 5);
 				tc2::sts64(a_fin + fslot8 * (4 * TC_M), m_run, s_run);
